@@ -1,0 +1,184 @@
+/*
+ * wn_b200.h — C-ABI of the B200-native fast generalized winding number engine (libwn_b200.so).
+ *
+ * This is the drop-in boundary for the lagrange::winding::FastWindingNumber hot path: plain pointers and sizes, no
+ * C++/torch types. Every entry point names the reference interface it replaces (paths relative to the adobe/lagrange
+ * checkout). The engine behind lagrange's wrapper is HDK_Sample::UT_SolidAngle<float,float> (third-party, fetched by
+ * cmake/recipes/external/winding_number.cmake:21-26); lagrange binds exactly two of its methods:
+ *
+ *     m_engine.init(num_triangles, triangles_ptr, num_vertices, m_vertices.data());   FastWindingNumber.cpp:57
+ *     m_engine.computeSolidAngle(q)  [accuracy_scale = 2, order = 2 defaults]         FastWindingNumber.cpp:66,75
+ *
+ * INTEGRATION.md shows the binding a lagrange maintainer would write over these functions.
+ *
+ * Conventions
+ *   - All functions return wn_status (0 = ok). On failure wn_last_error() returns a thread-local message.
+ *   - Pointers named *_xyz hold packed float triples. Data pointers may be host or device pointers; residency is
+ *     detected with cudaPointerGetAttributes. Host buffers are staged through pinned memory inside the call.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream). Calls with device buffers are
+ *     asynchronous with respect to the host on that stream; calls with host buffers return after the results landed.
+ *   - Query entry points are re-entrant: one engine may be queried from many host threads (the reference is called
+ *     from OpenVDB's TBB workers, modules/volume/src/mesh_to_volume.cpp:175-183); calls serialise per engine.
+ *   - There is NO CPU fallback: without a CUDA device every compute entry point fails with WN_ERR_CUDA.
+ */
+#ifndef WN_B200_H
+#define WN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define WN_API __declspec(dllexport)
+#else
+#define WN_API __attribute__((visibility("default")))
+#endif
+
+typedef struct wn_engine wn_engine;
+
+typedef enum wn_status {
+    WN_OK = 0,
+    WN_ERR_INVALID_ARGUMENT = 1, /* null pointer, negative size, index out of range, malformed topology */
+    WN_ERR_CUDA = 2,             /* CUDA runtime/driver error, or no device */
+    WN_ERR_OUT_OF_MEMORY = 3,
+    WN_ERR_UNSUPPORTED = 4       /* e.g. more than 2^27 triangles */
+} wn_status;
+
+/* Radius used by the far-field acceptance test  |q - P|^2 > beta^2 * R^2. */
+typedef enum wn_radius_mode {
+    WN_RADIUS_BOX_CORNER = 0, /* reference: distance from the area-weighted centroid to the farthest AABB corner */
+    WN_RADIUS_VERTEX = 1      /* exact: distance to the farthest vertex of the cluster (never larger than BOX_CORNER) */
+} wn_radius_mode;
+
+typedef struct wn_options {
+    uint32_t struct_size;     /* = sizeof(wn_options); set by wn_options_init */
+    int32_t device;           /* CUDA device ordinal, -1 = current device */
+    float accuracy_scale;     /* default beta for queries that pass beta <= 0; reference default 2 (UT_SolidAngle) */
+    int32_t order;            /* Taylor order of the far field: 0, 1 or 2; reference default 2 */
+    int32_t leaf_size;        /* LBVH build: max triangles per leaf (1..16). Imported topologies are always 1 */
+    int32_t morton_bits;      /* LBVH build: 30 or 63 */
+    int32_t radius_mode;      /* wn_radius_mode */
+    int32_t approximate_single_triangles; /* 1 = far single-triangle leaves use their dipole expansion like the
+                                             reference (A.4: "single-triangle children get a record too"); 0 = they are
+                                             always evaluated exactly (cheaper and more accurate). Imported topologies
+                                             default to 1, the LBVH build to 0 */
+    int32_t keep_build_data;  /* 1 = keep per-node raw moments for wn_debug_node_moments */
+    int32_t reserved[7];
+} wn_options;
+
+typedef struct wn_info {
+    uint32_t struct_size;
+    int32_t device;
+    int64_t num_vertices;
+    int64_t num_triangles;
+    int64_t num_tree_nodes;      /* nodes of the hierarchy (internal + leaves) before packing */
+    int64_t num_entries;         /* records in the packed depth-first array the traversal walks (incl. root) */
+    int64_t num_leaf_entries;
+    int64_t tree_bytes;          /* bytes of the packed tree (node records + links + triangle records) */
+    int64_t build_scratch_bytes; /* peak temporary device memory used by the build */
+    float build_ms;              /* device time of the whole build (CUDA events) */
+    float build_ms_morton;       /* K1 bounds + Morton codes */
+    float build_ms_sort;         /* K2 radix sort */
+    float build_ms_hierarchy;    /* K3 LBVH topology (0 for imported topologies) */
+    float build_ms_moments;      /* K4 bottom-up moments */
+    float build_ms_pack;         /* K5 depth-first packing */
+    int32_t max_depth;
+    int32_t width;               /* 2 = LBVH, 4 = imported UT_BVH<4>-style topology */
+    float accuracy_scale;
+    int32_t order;
+} wn_info;
+
+/* Totals over one batch of queries; they define the algorithmic flops of a tree query:
+ * flops = 10 * node_tests + 83 * far_field_evals + 75 * exact_triangles. */
+typedef struct wn_query_stats {
+    uint64_t node_tests;
+    uint64_t far_field_evals;
+    uint64_t exact_triangles;
+    uint64_t warp_node_visits;   /* nodes a warp stepped through (divergence = 32 * visits / node_tests) */
+} wn_query_stats;
+
+WN_API const char* wn_last_error(void);
+WN_API const char* wn_version(void);
+WN_API wn_status wn_options_init(wn_options* opt);
+
+/* ---- construction -------------------------------------------------------------------------------------------
+ * Replaces UT_SolidAngle::init(ntris, tri_pts, npts, positions) as called at FastWindingNumber.cpp:54-57.
+ * Input buffers are copied (the reference keeps converted copies alive for the same reason, :40-52,82-84); the
+ * caller may free them when the call returns. GPU build: K1 bounds + Morton codes, K2 radix sort, K3 LBVH, K4
+ * bottom-up order-2 moments, K5 depth-first packing. nT == 0 builds an empty engine (Omega = 0 everywhere). */
+WN_API wn_status wn_create(const float* v_xyz, int64_t num_vertices, const int32_t* tri, int64_t num_triangles,
+                           const wn_options* opt, wn_engine** out);
+
+/* Same, but the hierarchy topology is supplied by the caller ("oracle-tree mode"): `child` holds
+ * num_nodes * width slots (width 2..4), node 0 is the root, slot encoding: c >= 0 internal node index, c == -1 empty
+ * (trailing), c <= -2 triangle index -(c+2). Every triangle must appear exactly once. Moments, radii and packing
+ * are still computed on the GPU (K4, K5). With a UT_BVH<4> topology this reproduces the reference's tree, so query
+ * results agree with the reference algorithm to float rounding. */
+WN_API wn_status wn_create_from_topology(const float* v_xyz, int64_t num_vertices, const int32_t* tri, int64_t num_triangles,
+                                         const int32_t* child, int64_t num_nodes, int32_t width, const wn_options* opt,
+                                         wn_engine** out);
+
+WN_API wn_status wn_destroy(wn_engine* e);
+WN_API wn_status wn_get_info(const wn_engine* e, wn_info* info);
+
+/* ---- tree queries (K6) --------------------------------------------------------------------------------------
+ * Replace UT_SolidAngle::computeSolidAngle(q, accuracy_scale) (FastWindingNumber.cpp:66,75), batched.
+ * beta <= 0 selects the engine default. `flags`: see WN_QUERY_*. */
+#define WN_QUERY_DEFAULT 0u
+#define WN_QUERY_PRESORTED 1u /* points are already spatially coherent: skip the Morton sort of the queries (K9) */
+
+/* out_omega[i] = solid angle at q_i, in (-4pi k, 4pi k): what FastWindingNumber::solid_angle returns (:69-76). */
+WN_API wn_status wn_solid_angle(const wn_engine* e, const float* q_xyz, int64_t n, float beta, uint32_t flags,
+                                float* out_omega, void* stream);
+/* out_inside[i] = 1 iff (double)omega / (4.0 * pi) > 0.5 : FastWindingNumber::is_inside (:60-67). */
+WN_API wn_status wn_is_inside(const wn_engine* e, const float* q_xyz, int64_t n, float beta, uint32_t flags,
+                              uint8_t* out_inside, void* stream);
+
+/* Implicit cell-centred lattice, the mesh_to_volume call pattern (modules/volume/src/mesh_to_volume.cpp:147-149,
+ * 175-182): p(i,j,k) = origin + spacing * ((i,j,k) + 0.5), evaluated in float; x fastest, then y, then z.
+ * Only the z-slab [z_begin, z_end) is evaluated (multi-GPU sharding); the output holds dims[0]*dims[1]*(z_end-z_begin)
+ * values starting at the slab's first point. Either output may be NULL (not both). */
+WN_API wn_status wn_query_grid(const wn_engine* e, const float origin[3], const float spacing[3], const int64_t dims[3],
+                               int64_t z_begin, int64_t z_end, float beta, float* out_omega, uint8_t* out_inside, void* stream);
+
+/* Counters of the traversal for a batch of points (same traversal as wn_solid_angle, results discarded). */
+WN_API wn_status wn_query_stats_points(const wn_engine* e, const float* q_xyz, int64_t n, float beta, uint32_t flags,
+                                       wn_query_stats* stats, void* stream);
+WN_API wn_status wn_query_stats_grid(const wn_engine* e, const float origin[3], const float spacing[3], const int64_t dims[3],
+                                     int64_t z_begin, int64_t z_end, float beta, wn_query_stats* stats, void* stream);
+
+/* ---- exact brute-force mode (K7) ----------------------------------------------------------------------------
+ * Sum of exact Van Oosterom-Strackee triangle solid angles over ALL triangles (UTsignedSolidAngleTri):
+ * tree-independent ground truth on the device. Either output may be NULL (not both). */
+WN_API wn_status wn_exact(const wn_engine* e, const float* q_xyz, int64_t n, float* out_omega, uint8_t* out_inside, void* stream);
+WN_API wn_status wn_exact_grid(const wn_engine* e, const float origin[3], const float spacing[3], const int64_t dims[3],
+                               int64_t z_begin, int64_t z_end, float* out_omega, uint8_t* out_inside, void* stream);
+
+/* ---- tree replication across GPUs ---------------------------------------------------------------------------
+ * The packed tree is position independent: wn_tree_pack writes it into one contiguous buffer (host or device) that
+ * can be broadcast (NCCL over NVLink) and adopted on another device with wn_create_from_packed. */
+WN_API wn_status wn_tree_packed_size(const wn_engine* e, int64_t* nbytes);
+WN_API wn_status wn_tree_pack(const wn_engine* e, void* dst, int64_t nbytes, void* stream);
+WN_API wn_status wn_create_from_packed(const void* src, int64_t nbytes, const wn_options* opt, wn_engine** out);
+
+/* ---- debug / parity hooks -----------------------------------------------------------------------------------
+ * Raw per-node moments in the reference's stored form (23 floats, SURVEY.md A.4 order: P(3), maxPDist2, N(3),
+ * Nxx,Nyy,Nzz, Nxy+Nyx, Nyz+Nzy, Nzx+Nxz, Nxxx,Nyyy,Nzzz, 2(Nxyz+Nyzx+Nzxy), 2Nxxy+Nyxx, 2Nxxz+Nzxx, 2Nyyz+Nzyy,
+ * 2Nyyx+Nxyy, 2Nzzx+Nxzz, 2Nzzy+Nyzz) for hierarchy node `node` (internal nodes first, numbered as in the supplied
+ * topology; then leaves: num_internal + triangle index). Host output. Needs keep_build_data = 1. */
+WN_API wn_status wn_debug_node_moments(const wn_engine* e, int64_t first_node, int64_t count, float* out_23);
+/* Hierarchy topology as built on the device: child[num_internal * width] with the wn_create_from_topology encoding. */
+WN_API wn_status wn_debug_topology(const wn_engine* e, int32_t* child, int64_t capacity_nodes, int64_t* num_internal);
+/* Stand-alone radix sort of (key,value) pairs on the device (K2), exposed for tests. Host pointers. */
+WN_API wn_status wn_debug_sort_pairs_u64(uint64_t* keys, uint32_t* values, int64_t n, int32_t begin_bit, int32_t end_bit);
+WN_API wn_status wn_debug_sort_pairs_u32(uint32_t* keys, uint32_t* values, int64_t n, int32_t begin_bit, int32_t end_bit);
+/* FP32 FMA peak microbenchmark: runs `iters` dependent-chain FMAs per thread on a full grid, returns TFLOP/s. */
+WN_API wn_status wn_debug_fma_peak(int32_t device, int32_t iters, float* tflops, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WN_B200_H */

@@ -1,0 +1,285 @@
+// wn_build_core.cuh — per-thread bodies of the hierarchy build (K1, K3, K4, K5) as host/device functions.
+//
+// Every body is "what thread `tid` does"; the sm_100a kernels in wn_build.cuh call them with tid = global thread id,
+// and tests/emul/wn_emul.cpp calls the same bodies in a sequential loop on the host (test infrastructure: it lets the
+// CPU-only test tier check Karras topology, the atomic-counter climb, the skip-link packing and the record folding
+// against the oracle without a GPU). The device path never runs on the host.
+//
+// Node ids: internal nodes 0 .. nI-1 (root = 0), leaf l (one triangle) = nI + l. `prim[l]` = triangle id of leaf l.
+#pragma once
+
+#include "wn_device.cuh"
+
+#if defined(__CUDA_ARCH__)
+#define WN_ATOMIC_ADD_INT(p, v) atomicAdd((p), (v))
+#define WN_ATOMIC_MAX_INT(p, v) atomicMax((p), (v))
+#define WN_ATOMIC_MAX_U32(p, v) atomicMax((p), (v))
+#define WN_THREADFENCE() __threadfence()
+#define WN_LDCG_INT(p) __ldcg((p))
+#define WN_LDCG_F4(p) __ldcg((p))
+#else
+static inline int wn_host_atomic_add(int* p, int v)
+{
+    const int o = *p;
+    *p = o + v;
+    return o;
+}
+static inline int wn_host_atomic_max(int* p, int v)
+{
+    const int o = *p;
+    if (v > o) *p = v;
+    return o;
+}
+static inline unsigned wn_host_atomic_max_u(unsigned* p, unsigned v)
+{
+    const unsigned o = *p;
+    if (v > o) *p = v;
+    return o;
+}
+#define WN_ATOMIC_ADD_INT(p, v) wn_host_atomic_add((p), (v))
+#define WN_ATOMIC_MAX_INT(p, v) wn_host_atomic_max((p), (v))
+#define WN_ATOMIC_MAX_U32(p, v) wn_host_atomic_max_u((p), (v))
+#define WN_THREADFENCE() ((void)0)
+#define WN_LDCG_INT(p) (*(p))
+#define WN_LDCG_F4(p) (*(p))
+#endif
+
+#define WN_MAX_WIDTH 4
+#define WN_ERR_TOPOLOGY_BAD_CHILD 1
+#define WN_ERR_TOPOLOGY_DEPTH 2
+
+struct WnBuild
+{
+    // mesh
+    const float* v_xyz;  // [nV*3]
+    const int* tri;      // [nT*3]
+    int nV, nT;
+    // topology
+    int nI, nL, W;
+    int* child;          // [nI*W] node ids, -1 empty
+    int* parent;         // [nI+nL], root -1
+    unsigned char* slot; // [nI+nL]
+    const unsigned* prim; // [nL]
+    // bottom-up state
+    float4* local;       // [(nI+nL) * 9] WnLocal records
+    int* arrive;         // [nI] zero-initialised
+    int* ntri;           // [nI+nL]
+    int* size;           // [nI+nL] entries in the packed subtree (1 for leaves / collapsed nodes)
+    unsigned char* collapsed; // [nI]
+    unsigned* r2v;       // [nI+nL] vertex-radius^2 as ordered uint (float bits), zero-initialised (WN_RADIUS_VERTEX)
+    int* err;            // [1] error flag
+    int* max_depth;      // [1]
+    // options
+    int leaf_size, order, radius_mode, approx_single;
+    // packed output
+    float4* rec[6];      // [n_entries]
+    int* link;           // [n_entries]
+    float4* tris;        // [nT*3]
+    unsigned* tri_order; // [nT] triangle id at each depth-first position
+};
+
+WN_HD void wn_store_local(float4* dst, const WnLocal& d)
+{
+    const float* f = (const float*)&d;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) dst[k] = make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
+}
+WN_HD void wn_load_local(const float4* src, WnLocal& d, bool coherent)
+{
+    float* f = (float*)&d;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const float4 v = coherent ? WN_LDCG_F4(src + k) : src[k];
+        f[4 * k] = v.x;
+        f[4 * k + 1] = v.y;
+        f[4 * k + 2] = v.z;
+        f[4 * k + 3] = v.w;
+    }
+}
+
+WN_HD WnV3 wn_vertex(const float* v_xyz, int i)
+{
+    return wn_v3(v_xyz[3 * (int64_t)i], v_xyz[3 * (int64_t)i + 1], v_xyz[3 * (int64_t)i + 2]);
+}
+
+// ---- K3' : import a caller-supplied topology (neutral encoding -> node ids, parents, slots) ----------------------
+// child_in: [nI*W], c >= 0 internal, -1 empty, <= -2 triangle -(c+2).  seen: [nI+nL] zero-initialised reference counts.
+WN_HD void wn_import_node(const WnBuild& b, const int* child_in, int* seen, int i)
+{
+    bool empty_seen = false;
+    for (int s = 0; s < b.W; ++s) {
+        const int c = child_in[(int64_t)i * b.W + s];
+        int node = -1;
+        if (c == WN_CHILD_EMPTY) {
+            empty_seen = true;
+        } else if (c >= 0) {
+            if (c >= b.nI || c == 0 || empty_seen)
+                *b.err = WN_ERR_TOPOLOGY_BAD_CHILD;
+            else
+                node = c;
+        } else {
+            const int t = wn_dec_tri(c);
+            if (t < 0 || t >= b.nL || empty_seen)
+                *b.err = WN_ERR_TOPOLOGY_BAD_CHILD;
+            else
+                node = b.nI + t;
+        }
+        b.child[(int64_t)i * b.W + s] = node;
+        if (node >= 0) {
+            b.parent[node] = i;
+            b.slot[node] = (unsigned char)s;
+            WN_ATOMIC_ADD_INT(&seen[node], 1);
+        }
+    }
+    if (b.child[(int64_t)i * b.W] < 0) *b.err = WN_ERR_TOPOLOGY_BAD_CHILD; // an internal node needs a child
+}
+// every non-root node must be referenced exactly once
+WN_HD void wn_import_check(const WnBuild& b, const int* seen, int node)
+{
+    const int want = node == 0 ? 0 : 1;
+    if (seen[node] != want) *b.err = WN_ERR_TOPOLOGY_BAD_CHILD;
+}
+
+// ---- K4 : per-leaf moments, then climb with arrival counters -----------------------------------------------------
+WN_HD void wn_climb_leaf(const WnBuild& b, int l)
+{
+    const int t = (int)b.prim[l];
+    const int i0 = b.tri[3 * (int64_t)t], i1 = b.tri[3 * (int64_t)t + 1], i2 = b.tri[3 * (int64_t)t + 2];
+    WnLocal d;
+    wn_tri_local(wn_vertex(b.v_xyz, i0), wn_vertex(b.v_xyz, i1), wn_vertex(b.v_xyz, i2), d);
+    int node = b.nI + l;
+    wn_store_local(b.local + (int64_t)node * 9, d);
+    b.ntri[node] = 1;
+    b.size[node] = 1;
+    int guard = 0;
+    while (true) {
+        const int p = b.parent[node];
+        if (p < 0) break;
+        int nch = 0;
+        for (int s = 0; s < b.W; ++s) nch += b.child[(int64_t)p * b.W + s] >= 0 ? 1 : 0;
+        WN_THREADFENCE();
+        const int old = WN_ATOMIC_ADD_INT(&b.arrive[p], 1);
+        if (old + 1 < nch) break;
+        // last arriver merges (children in slot order => deterministic)
+        WN_THREADFENCE();
+        WnLocal ch[WN_MAX_WIDTH];
+        int n = 0, nt = 0, sz = 1;
+        for (int s = 0; s < b.W; ++s) {
+            const int c = b.child[(int64_t)p * b.W + s];
+            if (c < 0) continue;
+            wn_load_local(b.local + (int64_t)c * 9, ch[n], true);
+            nt += WN_LDCG_INT(&b.ntri[c]);
+            sz += WN_LDCG_INT(&b.size[c]);
+            ++n;
+        }
+        WnLocal m;
+        wn_merge_children(ch, n, m);
+        wn_store_local(b.local + (int64_t)p * 9, m);
+        const bool col = b.leaf_size > 1 && nt <= b.leaf_size;
+        b.collapsed[p] = col ? 1 : 0;
+        b.ntri[p] = nt;
+        b.size[p] = col ? 1 : sz;
+        node = p;
+        if (++guard > (1 << 20)) {
+            *b.err = WN_ERR_TOPOLOGY_DEPTH;
+            break;
+        }
+    }
+}
+
+// ---- K4b : exact vertex radius (WN_RADIUS_VERTEX): every leaf pushes its farthest vertex distance to all ancestors --
+WN_HD void wn_vertex_radius_leaf(const WnBuild& b, int l)
+{
+    const int t = (int)b.prim[l];
+    const WnV3 a = wn_vertex(b.v_xyz, b.tri[3 * (int64_t)t]);
+    const WnV3 bb = wn_vertex(b.v_xyz, b.tri[3 * (int64_t)t + 1]);
+    const WnV3 c = wn_vertex(b.v_xyz, b.tri[3 * (int64_t)t + 2]);
+    int node = b.nI + l;
+    int guard = 0;
+    while (node >= 0) {
+        // P lives at floats 6,7,8 of the WnLocal record
+        const float* rec = (const float*)(b.local + (int64_t)node * 9);
+        const float px = rec[6], py = rec[7], pz = rec[8];
+        float r2 = 0.0f;
+        {
+            const float dx = a.x - px, dy = a.y - py, dz = a.z - pz;
+            r2 = wn_max(r2, dx * dx + dy * dy + dz * dz);
+        }
+        {
+            const float dx = bb.x - px, dy = bb.y - py, dz = bb.z - pz;
+            r2 = wn_max(r2, dx * dx + dy * dy + dz * dz);
+        }
+        {
+            const float dx = c.x - px, dy = c.y - py, dz = c.z - pz;
+            r2 = wn_max(r2, dx * dx + dy * dy + dz * dz);
+        }
+        // one ulp of slack upward so rounding can never make the radius smaller than a vertex distance
+        r2 = r2 * 1.0000004f;
+        WN_ATOMIC_MAX_U32(&b.r2v[node], (unsigned)wn_float_as_int(r2));
+        node = b.parent[node];
+        if (++guard > (1 << 20)) break;
+    }
+}
+
+// ---- K5 : depth-first index by walking up, then pack -------------------------------------------------------------
+WN_HD void wn_pack_node(const WnBuild& b, int node)
+{
+    int idx = 0, tf = 0, depth = 0;
+    bool hidden = false;
+    int cur = node;
+    while (true) {
+        const int p = b.parent[cur];
+        if (p < 0) break;
+        if (b.collapsed[p]) hidden = true;
+        idx += 1;
+        const int sl = b.slot[cur];
+        for (int s = 0; s < sl; ++s) {
+            const int c = b.child[(int64_t)p * b.W + s];
+            if (c >= 0) {
+                idx += b.size[c];
+                tf += b.ntri[c];
+            }
+        }
+        cur = p;
+        if (++depth > (1 << 20)) {
+            *b.err = WN_ERR_TOPOLOGY_DEPTH;
+            return;
+        }
+    }
+    if (cur != 0) { // not connected to the root
+        *b.err = WN_ERR_TOPOLOGY_BAD_CHILD;
+        return;
+    }
+    WN_ATOMIC_MAX_INT(b.max_depth, depth);
+    const bool is_tri_leaf = node >= b.nI;
+    if (is_tri_leaf) {
+        const int t = (int)b.prim[node - b.nI];
+        const WnV3 a = wn_vertex(b.v_xyz, b.tri[3 * (int64_t)t]);
+        const WnV3 bb = wn_vertex(b.v_xyz, b.tri[3 * (int64_t)t + 1]);
+        const WnV3 c = wn_vertex(b.v_xyz, b.tri[3 * (int64_t)t + 2]);
+        b.tris[3 * (int64_t)tf] = make_float4(a.x, a.y, a.z, 0.0f);
+        b.tris[3 * (int64_t)tf + 1] = make_float4(bb.x, bb.y, bb.z, 0.0f);
+        b.tris[3 * (int64_t)tf + 2] = make_float4(c.x, c.y, c.z, 0.0f);
+        b.tri_order[tf] = (unsigned)t;
+    }
+    if (hidden) return;
+    const bool leaf_entry = is_tri_leaf || b.collapsed[node];
+    WnLocal d;
+    wn_load_local(b.local + (int64_t)node * 9, d, false);
+    float r2;
+    const float inf = wn_int_as_float(0x7f800000);
+    if (node == 0) {
+        r2 = inf; // the reference never approximates the root (A.5)
+    } else if (is_tri_leaf && !b.approx_single) {
+        r2 = inf; // a lone triangle is cheaper exact than expanded
+    } else if (b.radius_mode == 1) {
+        r2 = wn_min(wn_int_as_float((int)b.r2v[node]), wn_box_corner_r2(d));
+    } else {
+        r2 = wn_box_corner_r2(d);
+    }
+    float4 rec[6];
+    wn_pack_record(d, r2, leaf_entry, b.order, rec);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) b.rec[k][idx] = rec[k];
+    b.link[idx] = leaf_entry ? wn_leaf_link(tf, b.ntri[node]) : idx + b.size[node];
+}

@@ -1,0 +1,1162 @@
+// wn_capi.cu — the C-ABI of libwn_b200.so (include/wn_b200.h): engine lifetime, build orchestration, query launchers.
+// The only translation unit of the library; kernels live in the .cuh files it includes.
+//
+// Reference call sites replaced (adobe/lagrange, modules/winding/src/FastWindingNumber.cpp):
+//   :54-57  m_engine.init(...)                 -> wn_create / wn_create_from_topology
+//   :66     computeSolidAngle(q)/(4pi) > 0.5   -> wn_is_inside / wn_query_grid(out_inside)
+//   :75     computeSolidAngle(q)               -> wn_solid_angle / wn_query_grid(out_omega)
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <climits>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/wn_b200.h"
+#include "wn_query.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+wn_status fail(wn_status s, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return s;
+}
+
+#define WN_CUDA(call)                                                                                              \
+    do {                                                                                                           \
+        cudaError_t err__ = (call);                                                                                \
+        if (err__ != cudaSuccess) {                                                                                \
+            cudaGetLastError();                                                                                    \
+            return fail(err__ == cudaErrorMemoryAllocation ? WN_ERR_OUT_OF_MEMORY : WN_ERR_CUDA, "%s failed: %s (%s:%d)", #call, \
+                        cudaGetErrorString(err__), __FILE__, __LINE__);                                            \
+        }                                                                                                          \
+    } while (0)
+
+struct DeviceGuard
+{
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) {
+            cudaGetLastError();
+            prev = -1;
+            return;
+        }
+        ok = (dev == prev) || cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+struct DevBuf
+{
+    void* p = nullptr;
+    size_t bytes = 0;
+    cudaError_t reserve(size_t need)
+    {
+        if (need <= bytes) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        const size_t want = need + need / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) bytes = want;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+};
+
+struct PinnedBuf
+{
+    void* p = nullptr;
+    size_t bytes = 0;
+    cudaError_t reserve(size_t need)
+    {
+        if (need <= bytes) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMallocHost(&p, need);
+        if (e == cudaSuccess) bytes = need;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        bytes = 0;
+    }
+};
+
+bool is_device_pointer(const void* p)
+{
+    if (!p) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+size_t align_up(size_t v, size_t a)
+{
+    return (v + a - 1) / a * a;
+}
+
+// Position independent packed tree: one device allocation, header first.
+struct PackedHeader
+{
+    uint64_t magic; // 'WNB200T1'
+    int64_t total_bytes;
+    int64_t n_entries;
+    int64_t n_tris;
+    int64_t off_rec[6];
+    int64_t off_link;
+    int64_t off_tris;
+    int64_t off_tri_order;
+    int32_t width;
+    int32_t order;
+    float accuracy_scale;
+    int32_t max_depth;
+    int64_t n_leaf_entries;
+    int64_t num_vertices;
+    int64_t num_tree_nodes;
+    int64_t reserved[4];
+};
+constexpr uint64_t kMagic = 0x3154303032424e57ull;
+
+PackedHeader make_header(int64_t n_entries, int64_t n_tris)
+{
+    PackedHeader h;
+    memset(&h, 0, sizeof(h));
+    h.magic = kMagic;
+    size_t off = align_up(sizeof(PackedHeader), 256);
+    for (int k = 0; k < 6; ++k) {
+        h.off_rec[k] = (int64_t)off;
+        off = align_up(off + (size_t)n_entries * sizeof(float4), 256);
+    }
+    h.off_link = (int64_t)off;
+    off = align_up(off + (size_t)n_entries * sizeof(int), 256);
+    h.off_tris = (int64_t)off;
+    off = align_up(off + (size_t)n_tris * 3 * sizeof(float4), 256);
+    h.off_tri_order = (int64_t)off;
+    off = align_up(off + (size_t)n_tris * sizeof(unsigned), 256);
+    h.total_bytes = (int64_t)off;
+    h.n_entries = n_entries;
+    h.n_tris = n_tris;
+    return h;
+}
+
+} // namespace
+
+struct wn_engine
+{
+    int device = 0;
+    wn_options opt;
+    wn_info info;
+    PackedHeader hdr;
+    char* blob = nullptr; // packed tree on the device
+    WnTreeView view;
+    // kept build data (keep_build_data)
+    float4* kept_local = nullptr;
+    int* kept_child = nullptr;
+    unsigned* kept_prim = nullptr;
+    int kept_nI = 0, kept_nL = 0, kept_W = 0;
+    // per-engine query scratch, guarded by mu
+    mutable std::mutex mu;
+    mutable DevBuf s_in, s_out_f, s_out_b, s_sort, s_stats, s_partial;
+    mutable PinnedBuf p_small;
+};
+
+namespace {
+
+void set_view(wn_engine* e)
+{
+    for (int k = 0; k < 6; ++k) e->view.rec[k] = (const float4*)(e->blob + e->hdr.off_rec[k]);
+    e->view.link = (const int*)(e->blob + e->hdr.off_link);
+    e->view.tri = (const float4*)(e->blob + e->hdr.off_tris);
+    e->view.n_entries = (int)e->hdr.n_entries;
+    e->view.n_tris = (int)e->hdr.n_tris;
+}
+
+wn_status resolve_device(const wn_options* opt, int* dev)
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(WN_ERR_CUDA, "no CUDA device available (%s): libwn_b200 has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    int d = opt ? opt->device : -1;
+    if (d < 0) WN_CUDA(cudaGetDevice(&d));
+    if (d >= count) return fail(WN_ERR_INVALID_ARGUMENT, "device %d out of range (%d devices)", d, count);
+    *dev = d;
+    return WN_OK;
+}
+
+struct Timer
+{
+    cudaEvent_t ev[8];
+    int n = 0;
+    cudaStream_t s;
+    explicit Timer(cudaStream_t st) : s(st)
+    {
+        for (auto& e : ev) cudaEventCreate(&e);
+    }
+    ~Timer()
+    {
+        for (auto& e : ev) cudaEventDestroy(e);
+    }
+    void mark() { cudaEventRecord(ev[n++], s); }
+    float ms(int a, int b)
+    {
+        float m = 0;
+        cudaEventElapsedTime(&m, ev[a], ev[b]);
+        return m;
+    }
+};
+
+// Everything after the topology exists: moments, radii, packing. `b` has mesh + topology + options filled in.
+wn_status finish_build(wn_engine* e, WnBuild& b, std::vector<void*>& temps, size_t& scratch_bytes, Timer& tm, cudaStream_t st)
+{
+    const int64_t nN = (int64_t)b.nI + b.nL;
+    auto dalloc = [&](void** p, size_t bytes) -> cudaError_t {
+        cudaError_t r = cudaMalloc(p, bytes ? bytes : 1);
+        if (r == cudaSuccess) {
+            temps.push_back(*p);
+            scratch_bytes += bytes;
+        }
+        return r;
+    };
+    int* small = nullptr; // err, max_depth
+    WN_CUDA(dalloc((void**)&b.local, (size_t)nN * 9 * sizeof(float4)));
+    WN_CUDA(dalloc((void**)&b.arrive, (size_t)b.nI * sizeof(int)));
+    WN_CUDA(dalloc((void**)&b.ntri, (size_t)nN * sizeof(int)));
+    WN_CUDA(dalloc((void**)&b.size, (size_t)nN * sizeof(int)));
+    WN_CUDA(dalloc((void**)&b.collapsed, (size_t)b.nI));
+    WN_CUDA(dalloc((void**)&b.r2v, (size_t)nN * sizeof(unsigned)));
+    WN_CUDA(dalloc((void**)&small, 2 * sizeof(int)));
+    b.err = small;
+    b.max_depth = small + 1;
+    WN_CUDA(cudaMemsetAsync(b.arrive, 0, (size_t)b.nI * sizeof(int), st));
+    WN_CUDA(cudaMemsetAsync(b.collapsed, 0, (size_t)b.nI, st));
+    WN_CUDA(cudaMemsetAsync(b.r2v, 0, (size_t)nN * sizeof(unsigned), st));
+    WN_CUDA(cudaMemsetAsync(small, 0, 2 * sizeof(int), st));
+    wn::k_moments_climb<<<wn::grid_for(b.nL), wn::kBuildThreads, 0, st>>>(b);
+    if (b.radius_mode == WN_RADIUS_VERTEX) wn::k_vertex_radius<<<wn::grid_for(b.nL), wn::kBuildThreads, 0, st>>>(b);
+    WN_CUDA(cudaGetLastError());
+    tm.mark(); // moments done
+    int h_small[2] = {0, 0}, h_size = 0, h_ntri = 0;
+    WN_CUDA(cudaMemcpyAsync(h_small, small, sizeof(h_small), cudaMemcpyDeviceToHost, st));
+    WN_CUDA(cudaMemcpyAsync(&h_size, b.size, sizeof(int), cudaMemcpyDeviceToHost, st));
+    WN_CUDA(cudaMemcpyAsync(&h_ntri, b.ntri, sizeof(int), cudaMemcpyDeviceToHost, st));
+    WN_CUDA(cudaStreamSynchronize(st));
+    if (h_small[0] == 3) return fail(WN_ERR_INVALID_ARGUMENT, "triangle references a vertex index outside [0, num_vertices)");
+    if (h_small[0] != 0 || h_ntri != b.nL)
+        return fail(WN_ERR_INVALID_ARGUMENT, "malformed hierarchy topology (error %d, %d of %d triangles reachable from the root)",
+                    h_small[0], h_ntri, b.nL);
+    e->hdr = make_header(h_size, b.nL);
+    WN_CUDA(cudaMalloc((void**)&e->blob, (size_t)e->hdr.total_bytes));
+    set_view(e);
+    for (int k = 0; k < 6; ++k) b.rec[k] = (float4*)(e->blob + e->hdr.off_rec[k]);
+    b.link = (int*)(e->blob + e->hdr.off_link);
+    b.tris = (float4*)(e->blob + e->hdr.off_tris);
+    b.tri_order = (unsigned*)(e->blob + e->hdr.off_tri_order);
+    wn::k_pack<<<wn::grid_for(nN), wn::kBuildThreads, 0, st>>>(b);
+    WN_CUDA(cudaGetLastError());
+    tm.mark(); // pack done
+    WN_CUDA(cudaMemcpyAsync(h_small, small, sizeof(h_small), cudaMemcpyDeviceToHost, st));
+    WN_CUDA(cudaStreamSynchronize(st));
+    if (h_small[0] != 0) return fail(WN_ERR_INVALID_ARGUMENT, "malformed hierarchy topology while packing (error %d)", h_small[0]);
+    e->hdr.width = b.W;
+    e->hdr.order = b.order;
+    e->hdr.accuracy_scale = e->opt.accuracy_scale;
+    e->hdr.max_depth = h_small[1];
+    e->hdr.num_vertices = b.nV;
+    e->hdr.num_tree_nodes = nN;
+    WN_CUDA(cudaMemcpyAsync(e->blob, &e->hdr, sizeof(PackedHeader), cudaMemcpyHostToDevice, st));
+    WN_CUDA(cudaStreamSynchronize(st));
+    return WN_OK;
+}
+
+void fill_info(wn_engine* e)
+{
+    wn_info& in = e->info;
+    in.struct_size = sizeof(wn_info);
+    in.device = e->device;
+    in.num_vertices = e->hdr.num_vertices;
+    in.num_triangles = e->hdr.n_tris;
+    in.num_tree_nodes = e->hdr.num_tree_nodes;
+    in.num_entries = e->hdr.n_entries;
+    in.tree_bytes = e->hdr.total_bytes;
+    in.max_depth = e->hdr.max_depth;
+    in.width = e->hdr.width;
+    in.accuracy_scale = e->opt.accuracy_scale;
+    in.order = e->hdr.order;
+}
+
+wn_status validate_options(const wn_options* in, wn_options* out, bool imported)
+{
+    wn_options_init(out);
+    if (imported) out->approximate_single_triangles = 1;
+    if (in) {
+        if (in->struct_size != sizeof(wn_options)) return fail(WN_ERR_INVALID_ARGUMENT, "wn_options.struct_size mismatch (call wn_options_init)");
+        *out = *in;
+    }
+    if (imported) out->leaf_size = 1;
+    if (!(out->accuracy_scale > 0.0f)) return fail(WN_ERR_INVALID_ARGUMENT, "accuracy_scale must be > 0");
+    if (out->order < 0 || out->order > 2) return fail(WN_ERR_INVALID_ARGUMENT, "order must be 0, 1 or 2");
+    if (out->leaf_size < 1 || out->leaf_size > WN_MAX_LEAF_SIZE) return fail(WN_ERR_INVALID_ARGUMENT, "leaf_size must be in [1, %d]", WN_MAX_LEAF_SIZE);
+    if (out->morton_bits != 30 && out->morton_bits != 63) return fail(WN_ERR_INVALID_ARGUMENT, "morton_bits must be 30 or 63");
+    if (out->radius_mode != WN_RADIUS_BOX_CORNER && out->radius_mode != WN_RADIUS_VERTEX) return fail(WN_ERR_INVALID_ARGUMENT, "bad radius_mode");
+    return WN_OK;
+}
+
+wn_status create_impl(const float* v_xyz, int64_t nV, const int32_t* tri, int64_t nT, const int32_t* child_in, int64_t num_nodes,
+                      int32_t width, const wn_options* opt_in, wn_engine** out)
+{
+    if (!out) return fail(WN_ERR_INVALID_ARGUMENT, "out is null");
+    *out = nullptr;
+    if (nV < 0 || nT < 0 || (nV > 0 && !v_xyz) || (nT > 0 && !tri)) return fail(WN_ERR_INVALID_ARGUMENT, "null mesh buffers or negative sizes");
+    if (nT >= WN_MAX_TRIANGLES || nV > INT_MAX / 4) return fail(WN_ERR_UNSUPPORTED, "at most 2^27-1 triangles are supported");
+    const bool imported = child_in != nullptr;
+    if (imported && (width < 2 || width > WN_MAX_WIDTH || num_nodes < 1 || num_nodes > INT_MAX / 8))
+        return fail(WN_ERR_INVALID_ARGUMENT, "topology width must be 2..4 and num_nodes >= 1");
+    wn_options opt;
+    wn_status s = validate_options(opt_in, &opt, imported);
+    if (s != WN_OK) return s;
+    int dev = 0;
+    s = resolve_device(&opt, &dev);
+    if (s != WN_OK) return s;
+    DeviceGuard guard(dev);
+    if (!guard.ok) return fail(WN_ERR_CUDA, "cannot select CUDA device %d", dev);
+
+    wn_engine* e = new (std::nothrow) wn_engine;
+    if (!e) return fail(WN_ERR_OUT_OF_MEMORY, "host allocation failed");
+    e->device = dev;
+    e->opt = opt;
+    memset(&e->info, 0, sizeof(e->info));
+    memset(&e->hdr, 0, sizeof(e->hdr));
+    memset(&e->view, 0, sizeof(e->view));
+
+    std::vector<void*> temps;
+    size_t scratch_bytes = 0;
+    cudaStream_t st = nullptr; // legacy default stream: build is synchronous for the caller
+    auto cleanup = [&](wn_status r) {
+        for (void* p : temps) cudaFree(p);
+        temps.clear();
+        if (r != WN_OK) {
+            wn_destroy(e);
+            e = nullptr;
+        }
+        return r;
+    };
+    auto dalloc = [&](void** p, size_t bytes) -> cudaError_t {
+        cudaError_t r = cudaMalloc(p, bytes ? bytes : 1);
+        if (r == cudaSuccess) {
+            temps.push_back(*p);
+            scratch_bytes += bytes;
+        }
+        return r;
+    };
+#define WN_TRY(expr)                          \
+    do {                                      \
+        wn_status s__ = (expr);               \
+        if (s__ != WN_OK) return cleanup(s__); \
+    } while (0)
+#define WN_CUDA_C(call)                                                                                          \
+    do {                                                                                                         \
+        cudaError_t err__ = (call);                                                                              \
+        if (err__ != cudaSuccess) {                                                                              \
+            cudaGetLastError();                                                                                  \
+            return cleanup(fail(err__ == cudaErrorMemoryAllocation ? WN_ERR_OUT_OF_MEMORY : WN_ERR_CUDA,        \
+                                "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), __FILE__, __LINE__)); \
+        }                                                                                                        \
+    } while (0)
+
+    if (nT == 0) {
+        // empty engine: Omega = 0 everywhere (documented choice)
+        e->hdr = make_header(0, 0);
+        e->hdr.width = imported ? width : 2;
+        e->hdr.order = opt.order;
+        e->hdr.accuracy_scale = opt.accuracy_scale;
+        e->hdr.num_vertices = nV;
+        WN_CUDA_C(cudaMalloc((void**)&e->blob, (size_t)e->hdr.total_bytes));
+        WN_CUDA_C(cudaMemcpy(e->blob, &e->hdr, sizeof(PackedHeader), cudaMemcpyHostToDevice));
+        set_view(e);
+        fill_info(e);
+        *out = e;
+        return cleanup(WN_OK);
+    }
+
+    Timer tm(st);
+    WnBuild b;
+    memset(&b, 0, sizeof(b));
+    b.nV = (int)nV;
+    b.nT = (int)nT;
+    b.nL = (int)nT;
+    b.leaf_size = opt.leaf_size;
+    b.order = opt.order;
+    b.radius_mode = opt.radius_mode;
+    b.approx_single = opt.approximate_single_triangles;
+
+    // mesh on the device (copied: the caller may free its buffers when we return)
+    float* d_v = nullptr;
+    int* d_tri = nullptr;
+    WN_CUDA_C(dalloc((void**)&d_v, (size_t)nV * 3 * sizeof(float)));
+    WN_CUDA_C(dalloc((void**)&d_tri, (size_t)nT * 3 * sizeof(int)));
+    WN_CUDA_C(cudaMemcpyAsync(d_v, v_xyz, (size_t)nV * 3 * sizeof(float), cudaMemcpyDefault, st));
+    WN_CUDA_C(cudaMemcpyAsync(d_tri, tri, (size_t)nT * 3 * sizeof(int), cudaMemcpyDefault, st));
+    b.v_xyz = d_v;
+    b.tri = d_tri;
+
+    int* d_small = nullptr; // bounds[6], err
+    WN_CUDA_C(dalloc((void**)&d_small, 8 * sizeof(int)));
+    {
+        const int init[8] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN, 0, 0};
+        WN_CUDA_C(cudaMemcpyAsync(d_small, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    }
+    tm.mark(); // 0: start
+    unsigned* d_prim = nullptr;
+    if (!imported) {
+        b.W = 2;
+        b.nI = nT >= 2 ? (int)nT - 1 : 1;
+        const int64_t nN = (int64_t)b.nI + b.nL;
+        uint64_t *k0 = nullptr, *k1 = nullptr;
+        unsigned *v0 = nullptr, *v1 = nullptr;
+        void* sort_scratch = nullptr;
+        WN_CUDA_C(dalloc((void**)&k0, (size_t)nT * sizeof(uint64_t)));
+        WN_CUDA_C(dalloc((void**)&k1, (size_t)nT * sizeof(uint64_t)));
+        WN_CUDA_C(dalloc((void**)&v0, (size_t)nT * sizeof(unsigned)));
+        WN_CUDA_C(dalloc((void**)&v1, (size_t)nT * sizeof(unsigned)));
+        WN_CUDA_C(dalloc(&sort_scratch, (size_t)wn::sort_scratch_bytes(nT)));
+        const int blocks = std::min(wn::grid_for(nT), 148 * 8);
+        wn::k_centroid_bounds<<<blocks, wn::kBuildThreads, 0, st>>>(d_v, d_tri, (int)nT, (int)nV, d_small, d_small + 6);
+        WN_CUDA_C(cudaGetLastError());
+        {
+            // indices are validated by k_centroid_bounds before any kernel dereferences them
+            int h_err = 0;
+            WN_CUDA_C(cudaMemcpyAsync(&h_err, d_small + 6, sizeof(int), cudaMemcpyDeviceToHost, st));
+            WN_CUDA_C(cudaStreamSynchronize(st));
+            if (h_err) return cleanup(fail(WN_ERR_INVALID_ARGUMENT, "triangle references a vertex index outside [0, num_vertices)"));
+        }
+        const int bpa = opt.morton_bits == 63 ? 21 : 10;
+        wn::k_morton<uint64_t><<<wn::grid_for(nT), wn::kBuildThreads, 0, st>>>(d_v, d_tri, (int)nT, d_small, bpa, k0, v0);
+        WN_CUDA_C(cudaGetLastError());
+        tm.mark(); // 1: morton
+        const int which = wn::radix_sort_pairs<uint64_t>(k0, v0, k1, v1, nT, 0, opt.morton_bits, sort_scratch, st);
+        WN_CUDA_C(cudaGetLastError());
+        const uint64_t* keys = which ? k1 : k0;
+        d_prim = which ? v1 : v0;
+        tm.mark(); // 2: sort
+        WN_CUDA_C(dalloc((void**)&b.child, (size_t)b.nI * 2 * sizeof(int)));
+        WN_CUDA_C(dalloc((void**)&b.parent, (size_t)nN * sizeof(int)));
+        WN_CUDA_C(dalloc((void**)&b.slot, (size_t)nN));
+        WN_CUDA_C(cudaMemsetAsync(b.parent, 0xff, (size_t)nN * sizeof(int), st));
+        WN_CUDA_C(cudaMemsetAsync(b.slot, 0, (size_t)nN, st));
+        if (nT >= 2) {
+            wn::k_lbvh<<<wn::grid_for(nT - 1), wn::kBuildThreads, 0, st>>>(keys, (int)nT, b.child, b.parent, b.slot);
+            WN_CUDA_C(cudaGetLastError());
+        } else {
+            const int h_child[2] = {1, -1}; // root -> leaf 0 (node id nI + 0 = 1)
+            const int h_parent[2] = {-1, 0};
+            WN_CUDA_C(cudaMemcpyAsync(b.child, h_child, sizeof(h_child), cudaMemcpyHostToDevice, st));
+            WN_CUDA_C(cudaMemcpyAsync(b.parent, h_parent, sizeof(h_parent), cudaMemcpyHostToDevice, st));
+            WN_CUDA_C(cudaStreamSynchronize(st));
+        }
+        tm.mark(); // 3: hierarchy
+    } else {
+        b.W = width;
+        b.nI = (int)num_nodes;
+        const int64_t nN = (int64_t)b.nI + b.nL;
+        int* d_child_in = nullptr;
+        int* d_seen = nullptr;
+        WN_CUDA_C(dalloc((void**)&d_child_in, (size_t)b.nI * b.W * sizeof(int)));
+        WN_CUDA_C(dalloc((void**)&d_seen, (size_t)nN * sizeof(int)));
+        WN_CUDA_C(dalloc((void**)&d_prim, (size_t)nT * sizeof(unsigned)));
+        WN_CUDA_C(dalloc((void**)&b.child, (size_t)b.nI * b.W * sizeof(int)));
+        WN_CUDA_C(dalloc((void**)&b.parent, (size_t)nN * sizeof(int)));
+        WN_CUDA_C(dalloc((void**)&b.slot, (size_t)nN));
+        WN_CUDA_C(cudaMemcpyAsync(d_child_in, child_in, (size_t)b.nI * b.W * sizeof(int), cudaMemcpyDefault, st));
+        WN_CUDA_C(cudaMemsetAsync(d_seen, 0, (size_t)nN * sizeof(int), st));
+        WN_CUDA_C(cudaMemsetAsync(b.parent, 0xff, (size_t)nN * sizeof(int), st));
+        WN_CUDA_C(cudaMemsetAsync(b.slot, 0, (size_t)nN, st));
+        b.err = d_small + 6;
+        // vertex index validation (the LBVH path does it in k_centroid_bounds)
+        wn::k_centroid_bounds<<<std::min(wn::grid_for(nT), 148 * 8), wn::kBuildThreads, 0, st>>>(d_v, d_tri, (int)nT, (int)nV, d_small, d_small + 6);
+        tm.mark(); // 1
+        wn::k_iota<<<wn::grid_for(nT), wn::kBuildThreads, 0, st>>>(d_prim, (int)nT);
+        tm.mark(); // 2
+        wn::k_import_topology<<<wn::grid_for(b.nI), wn::kBuildThreads, 0, st>>>(b, d_child_in, d_seen);
+        wn::k_import_check<<<wn::grid_for(nN), wn::kBuildThreads, 0, st>>>(b, d_seen);
+        WN_CUDA_C(cudaGetLastError());
+        int h_err = 0;
+        WN_CUDA_C(cudaMemcpyAsync(&h_err, d_small + 6, sizeof(int), cudaMemcpyDeviceToHost, st));
+        WN_CUDA_C(cudaStreamSynchronize(st));
+        if (h_err == 3) return cleanup(fail(WN_ERR_INVALID_ARGUMENT, "triangle references a vertex index outside [0, num_vertices)"));
+        if (h_err) return cleanup(fail(WN_ERR_INVALID_ARGUMENT, "malformed hierarchy topology: bad child slot, or a node/triangle not referenced exactly once"));
+        tm.mark(); // 3
+    }
+    b.prim = d_prim;
+    WN_TRY(finish_build(e, b, temps, scratch_bytes, tm, st)); // marks 4 (moments) and 5 (pack)
+
+    fill_info(e);
+    e->info.build_scratch_bytes = (int64_t)scratch_bytes;
+    e->info.build_ms = tm.ms(0, 5);
+    e->info.build_ms_morton = tm.ms(0, 1);
+    e->info.build_ms_sort = tm.ms(1, 2);
+    e->info.build_ms_hierarchy = tm.ms(2, 3);
+    e->info.build_ms_moments = tm.ms(3, 4);
+    e->info.build_ms_pack = tm.ms(4, 5);
+    // leaf entries = entries whose R2 sign bit is set: count on the host from n_entries bookkeeping is not available,
+    // so derive it from sizes: for 1-triangle leaves it is nT; for collapsed leaves count on the device lazily (debug).
+    e->info.num_leaf_entries = opt.leaf_size == 1 ? nT : -1;
+
+    if (opt.keep_build_data) {
+        const int64_t nN = (int64_t)b.nI + b.nL;
+        auto keep = [&](void* p) {
+            temps.erase(std::remove(temps.begin(), temps.end(), p), temps.end());
+        };
+        e->kept_local = b.local;
+        keep(b.local);
+        e->kept_child = b.child;
+        keep(b.child);
+        e->kept_prim = d_prim;
+        keep(d_prim);
+        e->kept_nI = b.nI;
+        e->kept_nL = b.nL;
+        e->kept_W = b.W;
+        (void)nN;
+    }
+    *out = e;
+    return cleanup(WN_OK);
+#undef WN_TRY
+#undef WN_CUDA_C
+}
+
+// ---- query plumbing --------------------------------------------------------------------------------------------
+int env_int(const char* name, int dflt)
+{
+    const char* s = getenv(name);
+    return s && *s ? atoi(s) : dflt;
+}
+
+struct OutBufs
+{
+    float* d_omega = nullptr;
+    uint8_t* d_inside = nullptr;
+    float* h_omega = nullptr;
+    uint8_t* h_inside = nullptr;
+};
+
+// Resolve output residency: device pointers are used directly, host pointers get device staging.
+wn_status prepare_outputs(const wn_engine* e, int64_t n, float* out_omega, uint8_t* out_inside, OutBufs& ob)
+{
+    if (out_omega) {
+        if (is_device_pointer(out_omega)) {
+            ob.d_omega = out_omega;
+        } else {
+            WN_CUDA(e->s_out_f.reserve((size_t)n * sizeof(float)));
+            ob.d_omega = (float*)e->s_out_f.p;
+            ob.h_omega = out_omega;
+        }
+    }
+    if (out_inside) {
+        if (is_device_pointer(out_inside)) {
+            ob.d_inside = out_inside;
+        } else {
+            WN_CUDA(e->s_out_b.reserve((size_t)n));
+            ob.d_inside = (uint8_t*)e->s_out_b.p;
+            ob.h_inside = out_inside;
+        }
+    }
+    return WN_OK;
+}
+
+wn_status finish_outputs(int64_t n, const OutBufs& ob, cudaStream_t st)
+{
+    bool sync = false;
+    if (ob.h_omega) {
+        WN_CUDA(cudaMemcpyAsync(ob.h_omega, ob.d_omega, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
+        sync = true;
+    }
+    if (ob.h_inside) {
+        WN_CUDA(cudaMemcpyAsync(ob.h_inside, ob.d_inside, (size_t)n, cudaMemcpyDeviceToHost, st));
+        sync = true;
+    }
+    if (sync) WN_CUDA(cudaStreamSynchronize(st));
+    return WN_OK;
+}
+
+wn_status stage_points(const wn_engine* e, const float* q_xyz, int64_t n, const float** d_q, cudaStream_t st)
+{
+    if (is_device_pointer(q_xyz)) {
+        *d_q = q_xyz;
+        return WN_OK;
+    }
+    WN_CUDA(e->s_in.reserve((size_t)n * 3 * sizeof(float)));
+    WN_CUDA(cudaMemcpyAsync(e->s_in.p, q_xyz, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    *d_q = (const float*)e->s_in.p;
+    return WN_OK;
+}
+
+template <bool GRID, bool STATS>
+void launch_query(int qpl, int blocks, const wn::QueryArgs& a, cudaStream_t st)
+{
+    if (qpl == 2)
+        wn::k_query<2, GRID, STATS><<<blocks, wn::kQueryThreads, 0, st>>>(a);
+    else
+        wn::k_query<1, GRID, STATS><<<blocks, wn::kQueryThreads, 0, st>>>(a);
+}
+
+int pick_qpl(int64_t n)
+{
+    const int forced = env_int("WN_QPL", 0);
+    if (forced == 1 || forced == 2) return forced;
+    return n >= (1 << 20) ? 2 : 1;
+}
+
+wn_status points_impl(const wn_engine* e, const float* q_xyz, int64_t n, float beta, uint32_t flags, float* out_omega,
+                      uint8_t* out_inside, wn_query_stats* stats, void* stream)
+{
+    if (!e) return fail(WN_ERR_INVALID_ARGUMENT, "engine is null");
+    if (n < 0 || (n > 0 && !q_xyz)) return fail(WN_ERR_INVALID_ARGUMENT, "null query buffer or negative count");
+    if (!out_omega && !out_inside && !stats) return fail(WN_ERR_INVALID_ARGUMENT, "no output requested");
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (n == 0) return WN_OK;
+    DeviceGuard guard(e->device);
+    if (!guard.ok) return fail(WN_ERR_CUDA, "cannot select CUDA device %d", e->device);
+    std::lock_guard<std::mutex> lock(e->mu);
+    cudaStream_t st = (cudaStream_t)stream;
+    const float b = beta > 0.0f ? beta : e->opt.accuracy_scale;
+    const float* d_q = nullptr;
+    wn_status s = stage_points(e, q_xyz, n, &d_q, st);
+    if (s != WN_OK) return s;
+    OutBufs ob;
+    s = prepare_outputs(e, n, out_omega, out_inside, ob);
+    if (s != WN_OK) return s;
+
+    const unsigned* perm = nullptr;
+    const int64_t sort_min = env_int("WN_SORT_MIN", 4096);
+    if (!(flags & WN_QUERY_PRESORTED) && n >= sort_min && n <= (int64_t)UINT32_MAX && e->view.n_entries > 0) {
+        // K9: Morton order of the queries so that a warp's 32*QPL points are spatial neighbours
+        const size_t kb = align_up((size_t)n * sizeof(uint32_t), 256);
+        const size_t need = 4 * kb + (size_t)wn::sort_scratch_bytes(n) + 256;
+        WN_CUDA(e->s_sort.reserve(need));
+        char* base = (char*)e->s_sort.p;
+        uint32_t* k0 = (uint32_t*)base;
+        uint32_t* k1 = (uint32_t*)(base + kb);
+        unsigned* v0 = (unsigned*)(base + 2 * kb);
+        unsigned* v1 = (unsigned*)(base + 3 * kb);
+        int* bounds = (int*)(base + 4 * kb);
+        void* scratch = base + 4 * kb + 256;
+        const int init[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
+        WN_CUDA(cudaMemcpyAsync(bounds, init, sizeof(init), cudaMemcpyHostToDevice, st));
+        wn::k_point_bounds<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(d_q, n, bounds);
+        wn::k_point_morton<<<(int)((n + 255) / 256), 256, 0, st>>>(d_q, n, bounds, k0, v0);
+        const int which = wn::radix_sort_pairs<uint32_t>(k0, v0, k1, v1, n, 0, 30, scratch, st);
+        WN_CUDA(cudaGetLastError());
+        perm = which ? v1 : v0;
+    }
+
+    wn::QueryArgs a;
+    memset(&a, 0, sizeof(a));
+    a.tree = e->view;
+    a.beta2 = b * b;
+    a.q = d_q;
+    a.perm = perm;
+    a.n = n;
+    a.q_aligned16 = (((uintptr_t)d_q) & 15) == 0;
+    a.out_omega = ob.d_omega;
+    a.out_inside = ob.d_inside;
+    const int qpl = pick_qpl(n);
+    const int per_block = (wn::kQueryThreads / 32) * 32 * qpl;
+    const int blocks = (int)((n + per_block - 1) / per_block);
+    if (stats) {
+        WN_CUDA(e->s_stats.reserve(4 * sizeof(unsigned long long)));
+        WN_CUDA(cudaMemsetAsync(e->s_stats.p, 0, 4 * sizeof(unsigned long long), st));
+        a.stats = (unsigned long long*)e->s_stats.p;
+        launch_query<false, true>(qpl, blocks, a, st);
+    } else {
+        launch_query<false, false>(qpl, blocks, a, st);
+    }
+    WN_CUDA(cudaGetLastError());
+    if (stats) {
+        unsigned long long h[4];
+        WN_CUDA(cudaMemcpyAsync(h, e->s_stats.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+        WN_CUDA(cudaStreamSynchronize(st));
+        stats->node_tests = h[0];
+        stats->far_field_evals = h[1];
+        stats->exact_triangles = h[2];
+        stats->warp_node_visits = h[3];
+    }
+    return finish_outputs(n, ob, st);
+}
+
+wn_status check_grid(const float* origin, const float* spacing, const int64_t* dims, int64_t z0, int64_t z1, wn::GridDesc& g, int64_t& n)
+{
+    if (!origin || !spacing || !dims) return fail(WN_ERR_INVALID_ARGUMENT, "null grid description");
+    if (dims[0] < 0 || dims[1] < 0 || dims[2] < 0 || dims[0] > (1 << 24) || dims[1] > (1 << 24) || dims[2] > (1 << 24))
+        return fail(WN_ERR_INVALID_ARGUMENT, "grid dims must be in [0, 2^24]");
+    if (z0 < 0 || z1 < z0 || z1 > dims[2]) return fail(WN_ERR_INVALID_ARGUMENT, "z slab [%lld, %lld) outside [0, %lld)", (long long)z0, (long long)z1, (long long)dims[2]);
+    g.ox = origin[0];
+    g.oy = origin[1];
+    g.oz = origin[2];
+    g.sx = spacing[0];
+    g.sy = spacing[1];
+    g.sz = spacing[2];
+    g.nx = (int)dims[0];
+    g.ny = (int)dims[1];
+    g.nz = (int)dims[2];
+    g.z0 = (int)z0;
+    g.z1 = (int)z1;
+    n = dims[0] * dims[1] * (z1 - z0);
+    return WN_OK;
+}
+
+wn_status grid_impl(const wn_engine* e, const float* origin, const float* spacing, const int64_t* dims, int64_t z0, int64_t z1, float beta,
+                    float* out_omega, uint8_t* out_inside, wn_query_stats* stats, void* stream)
+{
+    if (!e) return fail(WN_ERR_INVALID_ARGUMENT, "engine is null");
+    if (!out_omega && !out_inside && !stats) return fail(WN_ERR_INVALID_ARGUMENT, "no output requested");
+    wn::GridDesc g;
+    int64_t n = 0;
+    wn_status s = check_grid(origin, spacing, dims, z0, z1, g, n);
+    if (s != WN_OK) return s;
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (n == 0) return WN_OK;
+    DeviceGuard guard(e->device);
+    if (!guard.ok) return fail(WN_ERR_CUDA, "cannot select CUDA device %d", e->device);
+    std::lock_guard<std::mutex> lock(e->mu);
+    cudaStream_t st = (cudaStream_t)stream;
+    const float b = beta > 0.0f ? beta : e->opt.accuracy_scale;
+    OutBufs ob;
+    s = prepare_outputs(e, n, out_omega, out_inside, ob);
+    if (s != WN_OK) return s;
+    wn::QueryArgs a;
+    memset(&a, 0, sizeof(a));
+    a.tree = e->view;
+    a.beta2 = b * b;
+    a.g = g;
+    a.out_omega = ob.d_omega;
+    a.out_inside = ob.d_inside;
+    const int qpl = pick_qpl(n);
+    a.tiles_x = (g.nx + 7) / 8;
+    a.tiles_y = (g.ny + 7) / 8;
+    const int tz = (int)((z1 - z0 + 4 * qpl - 1) / (4 * qpl));
+    const int64_t blocks64 = (int64_t)a.tiles_x * a.tiles_y * tz;
+    if (blocks64 > INT_MAX) return fail(WN_ERR_UNSUPPORTED, "grid slab too large for one launch; split the z range");
+    const int blocks = (int)blocks64;
+    if (stats) {
+        WN_CUDA(e->s_stats.reserve(4 * sizeof(unsigned long long)));
+        WN_CUDA(cudaMemsetAsync(e->s_stats.p, 0, 4 * sizeof(unsigned long long), st));
+        a.stats = (unsigned long long*)e->s_stats.p;
+        launch_query<true, true>(qpl, blocks, a, st);
+    } else {
+        launch_query<true, false>(qpl, blocks, a, st);
+    }
+    WN_CUDA(cudaGetLastError());
+    if (stats) {
+        unsigned long long h[4];
+        WN_CUDA(cudaMemcpyAsync(h, e->s_stats.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+        WN_CUDA(cudaStreamSynchronize(st));
+        stats->node_tests = h[0];
+        stats->far_field_evals = h[1];
+        stats->exact_triangles = h[2];
+        stats->warp_node_visits = h[3];
+    }
+    return finish_outputs(n, ob, st);
+}
+
+wn_status exact_impl(const wn_engine* e, bool grid, const float* q_xyz, int64_t n, const wn::GridDesc* g, float* out_omega,
+                     uint8_t* out_inside, void* stream)
+{
+    DeviceGuard guard(e->device);
+    if (!guard.ok) return fail(WN_ERR_CUDA, "cannot select CUDA device %d", e->device);
+    std::lock_guard<std::mutex> lock(e->mu);
+    cudaStream_t st = (cudaStream_t)stream;
+    const float* d_q = nullptr;
+    wn_status s = WN_OK;
+    if (!grid) {
+        s = stage_points(e, q_xyz, n, &d_q, st);
+        if (s != WN_OK) return s;
+    }
+    OutBufs ob;
+    s = prepare_outputs(e, n, out_omega, out_inside, ob);
+    if (s != WN_OK) return s;
+    wn::ExactArgs a;
+    memset(&a, 0, sizeof(a));
+    a.tris = e->view.tri;
+    a.nT = e->view.n_tris;
+    a.q = d_q;
+    a.n = n;
+    if (g) a.g = *g;
+    a.out_omega = ob.d_omega;
+    a.out_inside = ob.d_inside;
+    const bool small = n < 2048;
+    const int64_t qblocks = small ? (n + 7) / 8 : (n + 255) / 256;
+    const int ntiles = std::max(1, (a.nT + wn::kExactTile - 1) / wn::kExactTile);
+    // enough blocks to fill 148 SMs a few times over; chunks are whole tiles
+    const int64_t target_blocks = 148 * 16;
+    int nchunks = (int)std::min<int64_t>(ntiles, std::max<int64_t>(1, (target_blocks + qblocks - 1) / qblocks));
+    nchunks = std::min(nchunks, 65535);
+    const int tiles_per_chunk = (ntiles + nchunks - 1) / nchunks;
+    nchunks = (ntiles + tiles_per_chunk - 1) / tiles_per_chunk;
+    a.tris_per_chunk = tiles_per_chunk * wn::kExactTile;
+    a.nchunks = nchunks;
+    if (nchunks > 1) {
+        WN_CUDA(e->s_partial.reserve((size_t)nchunks * n * sizeof(float)));
+        a.partial = (float*)e->s_partial.p;
+    }
+    if (qblocks > INT_MAX) return fail(WN_ERR_UNSUPPORTED, "too many queries for one exact launch");
+    dim3 gridDim((unsigned)qblocks, (unsigned)nchunks);
+    if (small) {
+        if (grid)
+            wn::k_exact_small<true><<<gridDim, 256, 0, st>>>(a);
+        else
+            wn::k_exact_small<false><<<gridDim, 256, 0, st>>>(a);
+    } else {
+        if (grid)
+            wn::k_exact<true><<<gridDim, 256, 0, st>>>(a);
+        else
+            wn::k_exact<false><<<gridDim, 256, 0, st>>>(a);
+    }
+    if (nchunks > 1) wn::k_exact_reduce<<<(int)((n + 255) / 256), 256, 0, st>>>(a.partial, nchunks, n, ob.d_omega, ob.d_inside);
+    WN_CUDA(cudaGetLastError());
+    return finish_outputs(n, ob, st);
+}
+
+template <typename K>
+wn_status debug_sort(K* keys, uint32_t* values, int64_t n, int32_t begin_bit, int32_t end_bit)
+{
+    if (n < 0 || (n > 0 && (!keys || !values))) return fail(WN_ERR_INVALID_ARGUMENT, "null buffers");
+    if (begin_bit < 0 || end_bit > (int)sizeof(K) * 8 || begin_bit >= end_bit) return fail(WN_ERR_INVALID_ARGUMENT, "bad bit range");
+    if (n == 0) return WN_OK;
+    int dev = 0;
+    wn_status s = resolve_device(nullptr, &dev);
+    if (s != WN_OK) return s;
+    K *k0 = nullptr, *k1 = nullptr;
+    uint32_t *v0 = nullptr, *v1 = nullptr;
+    void* scratch = nullptr;
+    cudaError_t ce = cudaMalloc((void**)&k0, n * sizeof(K));
+    if (ce == cudaSuccess) ce = cudaMalloc((void**)&k1, n * sizeof(K));
+    if (ce == cudaSuccess) ce = cudaMalloc((void**)&v0, n * sizeof(uint32_t));
+    if (ce == cudaSuccess) ce = cudaMalloc((void**)&v1, n * sizeof(uint32_t));
+    if (ce == cudaSuccess) ce = cudaMalloc(&scratch, (size_t)wn::sort_scratch_bytes(n));
+    if (ce == cudaSuccess) ce = cudaMemcpy(k0, keys, n * sizeof(K), cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) ce = cudaMemcpy(v0, values, n * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) {
+        const int which = wn::radix_sort_pairs<K>(k0, v0, k1, v1, n, begin_bit, end_bit, scratch, nullptr);
+        ce = cudaGetLastError();
+        if (ce == cudaSuccess) ce = cudaMemcpy(keys, which ? k1 : k0, n * sizeof(K), cudaMemcpyDeviceToHost);
+        if (ce == cudaSuccess) ce = cudaMemcpy(values, which ? v1 : v0, n * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+    }
+    cudaFree(k0);
+    cudaFree(k1);
+    cudaFree(v0);
+    cudaFree(v1);
+    cudaFree(scratch);
+    WN_CUDA(ce);
+    return WN_OK;
+}
+
+} // namespace
+
+// =================================================================================================================
+extern "C" {
+
+const char* wn_last_error(void)
+{
+    return g_last_error.c_str();
+}
+
+const char* wn_version(void)
+{
+    return "lagrange_b200 winding 0.1 (sm_100a)";
+}
+
+wn_status wn_options_init(wn_options* opt)
+{
+    if (!opt) return fail(WN_ERR_INVALID_ARGUMENT, "opt is null");
+    memset(opt, 0, sizeof(*opt));
+    opt->struct_size = sizeof(wn_options);
+    opt->device = -1;
+    opt->accuracy_scale = 2.0f;
+    opt->order = 2;
+    opt->leaf_size = 1;
+    opt->morton_bits = 63;
+    opt->radius_mode = WN_RADIUS_BOX_CORNER;
+    opt->approximate_single_triangles = 0;
+    opt->keep_build_data = 0;
+    return WN_OK;
+}
+
+wn_status wn_create(const float* v_xyz, int64_t num_vertices, const int32_t* tri, int64_t num_triangles, const wn_options* opt, wn_engine** out)
+{
+    return create_impl(v_xyz, num_vertices, tri, num_triangles, nullptr, 0, 0, opt, out);
+}
+
+wn_status wn_create_from_topology(const float* v_xyz, int64_t num_vertices, const int32_t* tri, int64_t num_triangles, const int32_t* child,
+                                  int64_t num_nodes, int32_t width, const wn_options* opt, wn_engine** out)
+{
+    if (!child) return fail(WN_ERR_INVALID_ARGUMENT, "child table is null");
+    return create_impl(v_xyz, num_vertices, tri, num_triangles, child, num_nodes, width, opt, out);
+}
+
+wn_status wn_destroy(wn_engine* e)
+{
+    if (!e) return WN_OK;
+    {
+        DeviceGuard guard(e->device);
+        if (e->blob) cudaFree(e->blob);
+        if (e->kept_local) cudaFree(e->kept_local);
+        if (e->kept_child) cudaFree(e->kept_child);
+        if (e->kept_prim) cudaFree(e->kept_prim);
+        e->s_in.release();
+        e->s_out_f.release();
+        e->s_out_b.release();
+        e->s_sort.release();
+        e->s_stats.release();
+        e->s_partial.release();
+        e->p_small.release();
+    }
+    delete e;
+    return WN_OK;
+}
+
+wn_status wn_get_info(const wn_engine* e, wn_info* info)
+{
+    if (!e || !info) return fail(WN_ERR_INVALID_ARGUMENT, "null argument");
+    *info = e->info;
+    return WN_OK;
+}
+
+wn_status wn_solid_angle(const wn_engine* e, const float* q_xyz, int64_t n, float beta, uint32_t flags, float* out_omega, void* stream)
+{
+    if (!out_omega && n > 0) return fail(WN_ERR_INVALID_ARGUMENT, "out_omega is null");
+    return points_impl(e, q_xyz, n, beta, flags, out_omega, nullptr, nullptr, stream);
+}
+
+wn_status wn_is_inside(const wn_engine* e, const float* q_xyz, int64_t n, float beta, uint32_t flags, uint8_t* out_inside, void* stream)
+{
+    if (!out_inside && n > 0) return fail(WN_ERR_INVALID_ARGUMENT, "out_inside is null");
+    return points_impl(e, q_xyz, n, beta, flags, nullptr, out_inside, nullptr, stream);
+}
+
+wn_status wn_query_grid(const wn_engine* e, const float origin[3], const float spacing[3], const int64_t dims[3], int64_t z_begin,
+                        int64_t z_end, float beta, float* out_omega, uint8_t* out_inside, void* stream)
+{
+    return grid_impl(e, origin, spacing, dims, z_begin, z_end, beta, out_omega, out_inside, nullptr, stream);
+}
+
+wn_status wn_query_stats_points(const wn_engine* e, const float* q_xyz, int64_t n, float beta, uint32_t flags, wn_query_stats* stats, void* stream)
+{
+    if (!stats) return fail(WN_ERR_INVALID_ARGUMENT, "stats is null");
+    return points_impl(e, q_xyz, n, beta, flags, nullptr, nullptr, stats, stream);
+}
+
+wn_status wn_query_stats_grid(const wn_engine* e, const float origin[3], const float spacing[3], const int64_t dims[3], int64_t z_begin,
+                              int64_t z_end, float beta, wn_query_stats* stats, void* stream)
+{
+    if (!stats) return fail(WN_ERR_INVALID_ARGUMENT, "stats is null");
+    return grid_impl(e, origin, spacing, dims, z_begin, z_end, beta, nullptr, nullptr, stats, stream);
+}
+
+wn_status wn_exact(const wn_engine* e, const float* q_xyz, int64_t n, float* out_omega, uint8_t* out_inside, void* stream)
+{
+    if (!e) return fail(WN_ERR_INVALID_ARGUMENT, "engine is null");
+    if (n < 0 || (n > 0 && !q_xyz)) return fail(WN_ERR_INVALID_ARGUMENT, "null query buffer or negative count");
+    if (!out_omega && !out_inside) return fail(WN_ERR_INVALID_ARGUMENT, "no output requested");
+    if (n == 0) return WN_OK;
+    return exact_impl(e, false, q_xyz, n, nullptr, out_omega, out_inside, stream);
+}
+
+wn_status wn_exact_grid(const wn_engine* e, const float origin[3], const float spacing[3], const int64_t dims[3], int64_t z_begin, int64_t z_end,
+                        float* out_omega, uint8_t* out_inside, void* stream)
+{
+    if (!e) return fail(WN_ERR_INVALID_ARGUMENT, "engine is null");
+    if (!out_omega && !out_inside) return fail(WN_ERR_INVALID_ARGUMENT, "no output requested");
+    wn::GridDesc g;
+    int64_t n = 0;
+    wn_status s = check_grid(origin, spacing, dims, z_begin, z_end, g, n);
+    if (s != WN_OK) return s;
+    if (n == 0) return WN_OK;
+    return exact_impl(e, true, nullptr, n, &g, out_omega, out_inside, stream);
+}
+
+wn_status wn_tree_packed_size(const wn_engine* e, int64_t* nbytes)
+{
+    if (!e || !nbytes) return fail(WN_ERR_INVALID_ARGUMENT, "null argument");
+    *nbytes = e->hdr.total_bytes;
+    return WN_OK;
+}
+
+wn_status wn_tree_pack(const wn_engine* e, void* dst, int64_t nbytes, void* stream)
+{
+    if (!e || !dst) return fail(WN_ERR_INVALID_ARGUMENT, "null argument");
+    if (nbytes < e->hdr.total_bytes) return fail(WN_ERR_INVALID_ARGUMENT, "destination too small: need %lld bytes", (long long)e->hdr.total_bytes);
+    DeviceGuard guard(e->device);
+    if (!guard.ok) return fail(WN_ERR_CUDA, "cannot select CUDA device %d", e->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    WN_CUDA(cudaMemcpyAsync(dst, e->blob, (size_t)e->hdr.total_bytes, cudaMemcpyDefault, st));
+    if (!is_device_pointer(dst)) WN_CUDA(cudaStreamSynchronize(st));
+    return WN_OK;
+}
+
+wn_status wn_create_from_packed(const void* src, int64_t nbytes, const wn_options* opt_in, wn_engine** out)
+{
+    if (!out) return fail(WN_ERR_INVALID_ARGUMENT, "out is null");
+    *out = nullptr;
+    if (!src || nbytes < (int64_t)sizeof(PackedHeader)) return fail(WN_ERR_INVALID_ARGUMENT, "packed tree buffer missing or too small");
+    wn_options opt;
+    wn_status s = validate_options(opt_in, &opt, false);
+    if (s != WN_OK) return s;
+    int dev = 0;
+    s = resolve_device(&opt, &dev);
+    if (s != WN_OK) return s;
+    DeviceGuard guard(dev);
+    if (!guard.ok) return fail(WN_ERR_CUDA, "cannot select CUDA device %d", dev);
+    PackedHeader h;
+    WN_CUDA(cudaMemcpy(&h, src, sizeof(h), cudaMemcpyDefault));
+    if (h.magic != kMagic) return fail(WN_ERR_INVALID_ARGUMENT, "not a packed winding tree (bad magic)");
+    if (h.total_bytes > nbytes) return fail(WN_ERR_INVALID_ARGUMENT, "packed tree truncated: header says %lld bytes, got %lld", (long long)h.total_bytes, (long long)nbytes);
+    const PackedHeader ref = make_header(h.n_entries, h.n_tris);
+    if (ref.total_bytes != h.total_bytes || ref.off_tri_order != h.off_tri_order) return fail(WN_ERR_INVALID_ARGUMENT, "packed tree header is inconsistent");
+    wn_engine* e = new (std::nothrow) wn_engine;
+    if (!e) return fail(WN_ERR_OUT_OF_MEMORY, "host allocation failed");
+    e->device = dev;
+    e->opt = opt;
+    e->opt.accuracy_scale = opt_in ? opt.accuracy_scale : h.accuracy_scale;
+    e->opt.order = h.order;
+    memset(&e->info, 0, sizeof(e->info));
+    e->hdr = h;
+    cudaError_t ce = cudaMalloc((void**)&e->blob, (size_t)h.total_bytes);
+    if (ce == cudaSuccess) ce = cudaMemcpy(e->blob, src, (size_t)h.total_bytes, cudaMemcpyDefault);
+    if (ce != cudaSuccess) {
+        cudaGetLastError();
+        wn_destroy(e);
+        return fail(ce == cudaErrorMemoryAllocation ? WN_ERR_OUT_OF_MEMORY : WN_ERR_CUDA, "adopting packed tree failed: %s", cudaGetErrorString(ce));
+    }
+    set_view(e);
+    fill_info(e);
+    e->info.num_leaf_entries = -1;
+    *out = e;
+    return WN_OK;
+}
+
+wn_status wn_debug_node_moments(const wn_engine* e, int64_t first_node, int64_t count, float* out_23)
+{
+    if (!e || !out_23) return fail(WN_ERR_INVALID_ARGUMENT, "null argument");
+    if (!e->kept_local) return fail(WN_ERR_INVALID_ARGUMENT, "engine was built without keep_build_data");
+    const int64_t nN = (int64_t)e->kept_nI + e->kept_nL;
+    if (first_node < 0 || count < 0 || first_node + count > nN) return fail(WN_ERR_INVALID_ARGUMENT, "node range outside [0, %lld)", (long long)nN);
+    if (count == 0) return WN_OK;
+    DeviceGuard guard(e->device);
+    float* d_out = nullptr;
+    WN_CUDA(cudaMalloc((void**)&d_out, (size_t)count * 23 * sizeof(float)));
+    WnBuild b;
+    memset(&b, 0, sizeof(b));
+    b.local = e->kept_local;
+    wn::k_ref23<<<wn::grid_for(count), wn::kBuildThreads>>>(b, first_node, count, d_out);
+    cudaError_t ce = cudaMemcpy(out_23, d_out, (size_t)count * 23 * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(d_out);
+    WN_CUDA(ce);
+    return WN_OK;
+}
+
+wn_status wn_debug_topology(const wn_engine* e, int32_t* child, int64_t capacity_nodes, int64_t* num_internal)
+{
+    if (!e || !num_internal) return fail(WN_ERR_INVALID_ARGUMENT, "null argument");
+    if (!e->kept_child) return fail(WN_ERR_INVALID_ARGUMENT, "engine was built without keep_build_data");
+    *num_internal = e->kept_nI;
+    if (!child) return WN_OK;
+    if (capacity_nodes < e->kept_nI) return fail(WN_ERR_INVALID_ARGUMENT, "child buffer too small");
+    DeviceGuard guard(e->device);
+    const size_t n = (size_t)e->kept_nI * e->kept_W;
+    std::vector<int> h(n);
+    std::vector<unsigned> prim((size_t)e->kept_nL);
+    WN_CUDA(cudaMemcpy(h.data(), e->kept_child, n * sizeof(int), cudaMemcpyDeviceToHost));
+    WN_CUDA(cudaMemcpy(prim.data(), e->kept_prim, prim.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    for (size_t k = 0; k < n; ++k) {
+        const int c = h[k];
+        child[k] = c < 0 ? WN_CHILD_EMPTY : (c >= e->kept_nI ? wn_enc_tri((int)prim[(size_t)(c - e->kept_nI)]) : c);
+    }
+    return WN_OK;
+}
+
+wn_status wn_debug_sort_pairs_u64(uint64_t* keys, uint32_t* values, int64_t n, int32_t begin_bit, int32_t end_bit)
+{
+    return debug_sort<uint64_t>(keys, values, n, begin_bit, end_bit);
+}
+
+wn_status wn_debug_sort_pairs_u32(uint32_t* keys, uint32_t* values, int64_t n, int32_t begin_bit, int32_t end_bit)
+{
+    return debug_sort<uint32_t>(keys, values, n, begin_bit, end_bit);
+}
+
+wn_status wn_debug_fma_peak(int32_t device, int32_t iters, float* tflops, float* ms_out)
+{
+    if (!tflops) return fail(WN_ERR_INVALID_ARGUMENT, "null argument");
+    wn_options o;
+    wn_options_init(&o);
+    o.device = device;
+    int dev = 0;
+    wn_status s = resolve_device(&o, &dev);
+    if (s != WN_OK) return s;
+    DeviceGuard guard(dev);
+    if (iters <= 0) iters = 4096;
+    cudaDeviceProp prop;
+    WN_CUDA(cudaGetDeviceProperties(&prop, dev));
+    const int blocks = prop.multiProcessorCount * 8;
+    float* sink = nullptr;
+    WN_CUDA(cudaMalloc((void**)&sink, sizeof(float)));
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    wn::k_fma_peak<<<blocks, 256>>>(iters / 8 + 1, sink); // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(a);
+        wn::k_fma_peak<<<blocks, 256>>>(iters, sink);
+        cudaEventRecord(b);
+        cudaEventSynchronize(b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        best = std::min(best, ms);
+    }
+    cudaError_t ce = cudaGetLastError();
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(sink);
+    WN_CUDA(ce);
+    const double flops = (double)blocks * 256.0 * (double)iters * 64.0 * 2.0;
+    *tflops = (float)(flops / (best * 1e-3) / 1e12);
+    if (ms_out) *ms_out = best;
+    return WN_OK;
+}
+
+} // extern "C"

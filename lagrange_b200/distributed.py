@@ -1,0 +1,71 @@
+"""Multi-GPU plumbing: one process per GPU (torch.distributed), query sets sharded, tree replicated once.
+
+The path shards naturally: queries are independent, so rank r classifies its own contiguous
+slice (z-slabs of a lattice, index ranges of a point set) and there is NO collective on the query path. The only
+exchange step is the one-time replication of the packed tree: built on `src`, broadcast with NCCL over NVLink/NVSwitch
+(gloo on CPU for the host-logic tests), adopted with wn_create_from_packed on the other ranks.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+__all__ = ["slab_range", "shard_range", "broadcast_packed", "replicate_engine"]
+
+
+def shard_range(n: int, rank: int, world: int):
+    """Contiguous, balanced [begin, end) of n items for `rank` of `world`; the ranges tile [0, n) exactly."""
+    return (n * rank) // world, (n * (rank + 1)) // world
+
+
+def slab_range(nz: int, rank: int, world: int, align: int = 1):
+    """z-slab [z0, z1) of a lattice with nz layers. `align` rounds interior cuts to multiples of the kernel's tile depth."""
+    z0, z1 = shard_range(nz, rank, world)
+    if align > 1:
+        z0 = min(nz, (z0 + align // 2) // align * align) if rank > 0 else 0
+        z1 = min(nz, (z1 + align // 2) // align * align) if rank < world - 1 else nz
+    return z0, z1
+
+
+def broadcast_packed(blob, src: int = 0, device=None, group=None):
+    """Broadcast a packed tree. `blob`: uint8 torch tensor / numpy array on `src`, ignored elsewhere.
+
+    Returns a uint8 torch tensor on `device` holding the bytes on every rank. Two collectives: the size, then the bytes.
+    """
+    import torch
+    import torch.distributed as dist
+
+    rank = dist.get_rank(group)
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    size = torch.zeros(1, dtype=torch.int64, device=device)
+    if rank == src:
+        if isinstance(blob, np.ndarray):
+            blob = torch.from_numpy(blob)
+        blob = blob.to(device=device, dtype=torch.uint8).contiguous()
+        size[0] = blob.numel()
+    dist.broadcast(size, src=src, group=group)
+    n = int(size.item())
+    if rank != src:
+        blob = torch.empty(n, dtype=torch.uint8, device=device)
+    dist.broadcast(blob, src=src, group=group)
+    return blob
+
+
+def replicate_engine(engine, src: int = 0, group=None):
+    """Every rank returns a FastWindingNumber on its own GPU holding the tree that `src` built (engine is None elsewhere)."""
+    import torch
+    import torch.distributed as dist
+
+    from .winding import FastWindingNumber
+
+    rank = dist.get_rank(group)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    blob = None
+    if rank == src:
+        blob = torch.empty(engine.packed_size(), dtype=torch.uint8, device=dev)
+        engine.pack(out=blob)
+        torch.cuda.current_stream().synchronize()
+    blob = broadcast_packed(blob, src=src, device=dev, group=group)
+    if rank == src:
+        return engine
+    return FastWindingNumber.from_packed(blob, device=dev.index)

@@ -1,0 +1,349 @@
+"""Python mirror of ``lagrange::winding::FastWindingNumber`` over the C-ABI (include/wn_b200.h).
+
+Reference surface (modules/winding/include/lagrange/winding/FastWindingNumber.h:24-108):
+    FastWindingNumber(mesh); is_inside(pos) -> bool; solid_angle(pos) -> float
+kept with the same names, argument meaning and error behaviour (non-3D / non-triangle meshes raise, like
+la_runtime_assert at modules/winding/src/FastWindingNumber.cpp:91-96), plus the batched overloads BASELINE.json asks
+for: arrays of points and implicit cell-centred lattices (the mesh_to_volume call pattern,
+modules/volume/src/mesh_to_volume.cpp:147-149,175-182).
+
+Every call goes to the CUDA engine; there is no host evaluation path. Inputs may be numpy arrays (host; staged by the
+library) or torch CUDA tensors (used in place, asynchronous on the current torch stream).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _capi
+from .mesh import SurfaceMesh
+
+__all__ = ["FastWindingNumber", "Error"]
+
+
+class Error(RuntimeError):
+    """Counterpart of lagrange::Error (modules/core/include/lagrange/utils/Error.h)."""
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _current_stream_ptr():
+    try:
+        import torch
+
+        if torch.cuda.is_available():
+            return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    except Exception:
+        pass
+    return ctypes.c_void_p(0)
+
+
+class _Buf:
+    """A float32/int32/uint8 buffer the C-ABI can read or write: numpy (host) or torch (host or device)."""
+
+    def __init__(self, obj, dtype, shape=None, writable=False):
+        self.is_torch = _is_torch(obj)
+        if self.is_torch:
+            import torch
+
+            tdt = {np.float32: torch.float32, np.int32: torch.int32, np.uint8: torch.uint8}[dtype]
+            t = obj
+            if t.dtype != tdt or not t.is_contiguous():
+                if writable:
+                    raise Error("output tensor must be contiguous and of the right dtype")
+                t = t.to(tdt).contiguous()
+            self.obj = t
+            self.ptr = ctypes.c_void_p(t.data_ptr())
+            self.size = t.numel()
+            self.device = t.device
+        else:
+            a = np.asarray(obj)
+            if writable:
+                if a.dtype != dtype or not a.flags.c_contiguous or not a.flags.writeable:
+                    raise Error("output array must be C-contiguous, writable and of the right dtype")
+            else:
+                a = np.ascontiguousarray(a, dtype=dtype)
+            self.obj = a
+            self.ptr = ctypes.c_void_p(a.ctypes.data)
+            self.size = a.size
+            self.device = None
+
+
+def _alloc_like(points_buf, n, dtype):
+    """Output buffer on the same side as the input: torch CUDA tensor for device inputs, numpy otherwise."""
+    if points_buf is not None and points_buf.is_torch and points_buf.device.type == "cuda":
+        import torch
+
+        tdt = {np.float32: torch.float32, np.uint8: torch.uint8}[dtype]
+        return torch.empty(n, dtype=tdt, device=points_buf.device)
+    return np.empty(n, dtype=dtype)
+
+
+class FastWindingNumber:
+    """Fast winding number computation for triangle soups (B200 engine).
+
+    Parameters mirror the reference constructor (a triangle ``SurfaceMesh``); ``vertices, facets`` arrays are accepted
+    too. Coordinates are converted to float32 and indices to int32 like the reference does
+    (FastWindingNumber.cpp:40-52).
+
+    Options (additions to the reference surface):
+      accuracy_scale  beta of the far-field test |q-P|^2 > beta^2 R^2 (reference default 2)
+      order           Taylor order 0/1/2 (reference default 2)
+      topology        (n_nodes, width) int32 child table to import instead of building the LBVH (oracle-tree mode)
+      leaf_size, morton_bits, radius_mode ('box_corner' | 'vertex'), approximate_single_triangles, device
+    """
+
+    def __init__(self, mesh=None, facets=None, *, accuracy_scale=2.0, order=2, topology=None, leaf_size=1, morton_bits=63,
+                 radius_mode="box_corner", approximate_single_triangles=None, keep_build_data=False, device=None, _handle=None):
+        self._h = None
+        self._lib = _capi.lib()
+        if _handle is not None:
+            self._h = _handle
+            return
+        if mesh is None:
+            # default-constructed engine, like FastWindingNumber() (FastWindingNumber.h:45): querying it raises
+            return
+        if isinstance(mesh, SurfaceMesh):
+            if mesh.get_dimension() != 3:
+                raise Error("Fast winding number engine only supports 3D meshes")
+            if not mesh.is_triangle_mesh():
+                raise Error("Fast winding number engine only supports triangle meshes")
+            vertices, facets = mesh.vertices, mesh.facets
+        else:
+            vertices = mesh
+            if facets is None:
+                raise Error("FastWindingNumber(vertices, facets): facets missing")
+        v = _Buf(vertices, np.float32)
+        f = _Buf(facets, np.int32)
+        vshape = tuple(v.obj.shape)
+        fshape = tuple(f.obj.shape)
+        if len(vshape) != 2 or vshape[1] != 3:
+            raise Error("Fast winding number engine only supports 3D meshes")
+        if len(fshape) != 2 or fshape[1] != 3:
+            raise Error("Fast winding number engine only supports triangle meshes")
+        opt = _capi.wn_options()
+        _capi.check(self._lib.wn_options_init(ctypes.byref(opt)))
+        opt.accuracy_scale = float(accuracy_scale)
+        opt.order = int(order)
+        opt.leaf_size = int(leaf_size)
+        opt.morton_bits = int(morton_bits)
+        opt.radius_mode = {"box_corner": _capi.WN_RADIUS_BOX_CORNER, "vertex": _capi.WN_RADIUS_VERTEX}[radius_mode]
+        opt.keep_build_data = 1 if keep_build_data else 0
+        opt.device = -1 if device is None else int(device)
+        if approximate_single_triangles is None:
+            approximate_single_triangles = topology is not None
+        opt.approximate_single_triangles = 1 if approximate_single_triangles else 0
+        h = ctypes.c_void_p()
+        if topology is None:
+            st = self._lib.wn_create(v.ptr, vshape[0], f.ptr, fshape[0], ctypes.byref(opt), ctypes.byref(h))
+        else:
+            topo = np.ascontiguousarray(topology, dtype=np.int32)
+            if topo.ndim != 2:
+                raise Error("topology must be a (n_nodes, width) child table")
+            st = self._lib.wn_create_from_topology(v.ptr, vshape[0], f.ptr, fshape[0], ctypes.c_void_p(topo.ctypes.data), topo.shape[0],
+                                                   topo.shape[1], ctypes.byref(opt), ctypes.byref(h))
+        if st != _capi.WN_OK:
+            raise Error(self._lib.wn_last_error().decode())
+        self._h = h
+
+    # -- lifetime ------------------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.wn_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _handle(self):
+        if not self._h:
+            raise Error("FastWindingNumber: engine is empty (default constructed or closed)")
+        return self._h
+
+    def _check(self, st):
+        if st != _capi.WN_OK:
+            raise Error(self._lib.wn_last_error().decode())
+
+    @property
+    def info(self) -> dict:
+        i = _capi.wn_info()
+        self._check(self._lib.wn_get_info(self._handle(), ctypes.byref(i)))
+        return {k: getattr(i, k) for k, _ in _capi.wn_info._fields_ if k != "struct_size"}
+
+    # -- the reference surface, single point or batched -------------------------------------------------------------
+    def _points(self, pos):
+        if _is_torch(pos):
+            buf = _Buf(pos, np.float32)
+            shape = tuple(buf.obj.shape)
+        else:
+            a = np.ascontiguousarray(pos, dtype=np.float32)
+            buf = _Buf(a, np.float32)
+            shape = a.shape
+        single = len(shape) == 1
+        if shape[-1] != 3 or len(shape) > 2:
+            raise Error("query positions must have shape (3,) or (n, 3)")
+        n = 1 if single else shape[0]
+        return buf, n, single
+
+    def solid_angle(self, pos, accuracy_scale=None, presorted=False, out=None):
+        """Solid angle at the query point(s). ``pos``: (3,) -> float, or (n,3) -> float32 array (numpy or torch CUDA)."""
+        buf, n, single = self._points(pos)
+        res = _alloc_like(buf, n, np.float32) if out is None else out
+        ob = _Buf(res, np.float32, writable=True)
+        flags = _capi.WN_QUERY_PRESORTED if presorted else 0
+        self._check(self._lib.wn_solid_angle(self._handle(), buf.ptr, n, float(accuracy_scale or 0.0), flags, ob.ptr, _current_stream_ptr()))
+        return float(res[0]) if single else res
+
+    def is_inside(self, pos, accuracy_scale=None, presorted=False, out=None):
+        """True iff (double)solid_angle / (4 pi) > 0.5 (FastWindingNumber.cpp:66). (3,) -> bool, (n,3) -> uint8 array."""
+        buf, n, single = self._points(pos)
+        res = _alloc_like(buf, n, np.uint8) if out is None else out
+        ob = _Buf(res, np.uint8, writable=True)
+        flags = _capi.WN_QUERY_PRESORTED if presorted else 0
+        self._check(self._lib.wn_is_inside(self._handle(), buf.ptr, n, float(accuracy_scale or 0.0), flags, ob.ptr, _current_stream_ptr()))
+        return bool(res[0]) if single else res
+
+    # -- implicit lattice (mesh_to_volume pattern) --------------------------------------------------------------------
+    @staticmethod
+    def _grid_args(origin, spacing, dims, z_range):
+        o = (ctypes.c_float * 3)(*[float(x) for x in origin])
+        s = (ctypes.c_float * 3)(*[float(x) for x in spacing])
+        d = (ctypes.c_int64 * 3)(*[int(x) for x in dims])
+        z0, z1 = (0, int(dims[2])) if z_range is None else (int(z_range[0]), int(z_range[1]))
+        n = int(dims[0]) * int(dims[1]) * max(0, z1 - z0)
+        return o, s, d, z0, z1, n
+
+    def query_grid(self, origin, spacing, dims, z_range=None, accuracy_scale=None, want_omega=False, want_inside=True, device_output=False,
+                   out_omega=None, out_inside=None):
+        """Evaluate the cell-centred lattice p = origin + spacing*(ijk+0.5), x fastest; returns (omega, inside) (None if not wanted).
+
+        ``device_output`` allocates torch CUDA outputs (results stay in HBM); otherwise numpy (copied to the host)."""
+        o, s, d, z0, z1, n = self._grid_args(origin, spacing, dims, z_range)
+        def mk(dtype, given, want):
+            if given is not None:
+                return given
+            if not want:
+                return None
+            if device_output:
+                import torch
+
+                return torch.empty(n, dtype={np.float32: torch.float32, np.uint8: torch.uint8}[dtype], device="cuda")
+            return np.empty(n, dtype=dtype)
+        om = mk(np.float32, out_omega, want_omega)
+        ins = mk(np.uint8, out_inside, want_inside)
+        pom = _Buf(om, np.float32, writable=True).ptr if om is not None else None
+        pin = _Buf(ins, np.uint8, writable=True).ptr if ins is not None else None
+        self._check(self._lib.wn_query_grid(self._handle(), o, s, d, z0, z1, float(accuracy_scale or 0.0), pom, pin, _current_stream_ptr()))
+        return om, ins
+
+    def is_inside_grid(self, origin, spacing, dims, **kw):
+        return self.query_grid(origin, spacing, dims, want_inside=True, want_omega=False, **kw)[1]
+
+    def solid_angle_grid(self, origin, spacing, dims, **kw):
+        return self.query_grid(origin, spacing, dims, want_inside=False, want_omega=True, **kw)[0]
+
+    # -- exact brute force mode ------------------------------------------------------------------------------------------
+    def exact_solid_angle(self, pos, out=None):
+        buf, n, single = self._points(pos)
+        res = _alloc_like(buf, n, np.float32) if out is None else out
+        ob = _Buf(res, np.float32, writable=True)
+        self._check(self._lib.wn_exact(self._handle(), buf.ptr, n, ob.ptr, None, _current_stream_ptr()))
+        return float(res[0]) if single else res
+
+    def exact_is_inside(self, pos, out=None):
+        buf, n, single = self._points(pos)
+        res = _alloc_like(buf, n, np.uint8) if out is None else out
+        ob = _Buf(res, np.uint8, writable=True)
+        self._check(self._lib.wn_exact(self._handle(), buf.ptr, n, None, ob.ptr, _current_stream_ptr()))
+        return bool(res[0]) if single else res
+
+    def exact_grid(self, origin, spacing, dims, z_range=None, want_omega=True, want_inside=False):
+        o, s, d, z0, z1, n = self._grid_args(origin, spacing, dims, z_range)
+        om = np.empty(n, dtype=np.float32) if want_omega else None
+        ins = np.empty(n, dtype=np.uint8) if want_inside else None
+        pom = ctypes.c_void_p(om.ctypes.data) if om is not None else None
+        pin = ctypes.c_void_p(ins.ctypes.data) if ins is not None else None
+        self._check(self._lib.wn_exact_grid(self._handle(), o, s, d, z0, z1, pom, pin, _current_stream_ptr()))
+        return om, ins
+
+    # -- counters ------------------------------------------------------------------------------------------------------
+    def query_stats(self, pos, accuracy_scale=None, presorted=False) -> dict:
+        buf, n, _ = self._points(pos)
+        st = _capi.wn_query_stats()
+        flags = _capi.WN_QUERY_PRESORTED if presorted else 0
+        self._check(self._lib.wn_query_stats_points(self._handle(), buf.ptr, n, float(accuracy_scale or 0.0), flags, ctypes.byref(st),
+                                                    _current_stream_ptr()))
+        return self._stats_dict(st, n)
+
+    def query_stats_grid(self, origin, spacing, dims, z_range=None, accuracy_scale=None) -> dict:
+        o, s, d, z0, z1, n = self._grid_args(origin, spacing, dims, z_range)
+        st = _capi.wn_query_stats()
+        self._check(self._lib.wn_query_stats_grid(self._handle(), o, s, d, z0, z1, float(accuracy_scale or 0.0), ctypes.byref(st),
+                                                  _current_stream_ptr()))
+        return self._stats_dict(st, n)
+
+    @staticmethod
+    def _stats_dict(st, n):
+        T, A, E, V = st.node_tests, st.far_field_evals, st.exact_triangles, st.warp_node_visits
+        return {"queries": n, "node_tests": T, "far_field_evals": A, "exact_triangles": E, "warp_node_visits": V,
+                # 10 flop per test, 83 more per accepted far-field evaluation, 75 per exact triangle
+                "algorithmic_flops": 10 * T + 83 * A + 75 * E}
+
+    # -- replication across GPUs -----------------------------------------------------------------------------------------
+    def packed_size(self) -> int:
+        n = ctypes.c_int64()
+        self._check(self._lib.wn_tree_packed_size(self._handle(), ctypes.byref(n)))
+        return int(n.value)
+
+    def pack(self, out=None):
+        """Serialise the packed tree into a uint8 buffer (torch CUDA tensor if given/available, else numpy)."""
+        n = self.packed_size()
+        if out is None:
+            out = np.empty(n, dtype=np.uint8)
+        ob = _Buf(out, np.uint8, writable=True)
+        self._check(self._lib.wn_tree_pack(self._handle(), ob.ptr, ob.size, _current_stream_ptr()))
+        return out
+
+    @classmethod
+    def from_packed(cls, buf, accuracy_scale=None, device=None):
+        lib = _capi.lib()
+        b = _Buf(buf, np.uint8)
+        h = ctypes.c_void_p()
+        if b.is_torch and b.device.type == "cuda":
+            import torch
+
+            torch.cuda.current_stream().synchronize()  # the adopt copy runs on the default stream
+        opt = None
+        if accuracy_scale is not None or device is not None:
+            opt = _capi.wn_options()
+            _capi.check(lib.wn_options_init(ctypes.byref(opt)))
+            if accuracy_scale is not None:
+                opt.accuracy_scale = float(accuracy_scale)
+            if device is not None:
+                opt.device = int(device)
+        st = lib.wn_create_from_packed(b.ptr, b.size, ctypes.byref(opt) if opt is not None else None, ctypes.byref(h))
+        if st != _capi.WN_OK:
+            raise Error(lib.wn_last_error().decode())
+        return cls(_handle=h)
+
+    # -- parity hooks ------------------------------------------------------------------------------------------------------
+    def debug_node_moments(self, first=0, count=None) -> np.ndarray:
+        if count is None:
+            count = self.info["num_tree_nodes"] - first
+        out = np.empty((count, 23), dtype=np.float32)
+        self._check(self._lib.wn_debug_node_moments(self._handle(), first, count, ctypes.c_void_p(out.ctypes.data)))
+        return out
+
+    def debug_topology(self) -> np.ndarray:
+        n = ctypes.c_int64()
+        self._check(self._lib.wn_debug_topology(self._handle(), None, 0, ctypes.byref(n)))
+        w = self.info["width"]
+        out = np.empty((n.value, w), dtype=np.int32)
+        self._check(self._lib.wn_debug_topology(self._handle(), ctypes.c_void_p(out.ctypes.data), n.value, ctypes.byref(n)))
+        return out

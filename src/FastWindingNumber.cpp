@@ -1,0 +1,174 @@
+// Host layer of lagrange::winding::FastWindingNumber over the C-ABI of the CUDA engine (include/wn_b200.h).
+// Mirrors the structure of adobe/lagrange modules/winding/src/FastWindingNumber.cpp: an Impl that converts the mesh to
+// float / int (there :40-52), hands it to the engine (there m_engine.init, :57; here wn_create) and forwards queries
+// (there computeSolidAngle, :66,75; here wn_is_inside / wn_solid_angle), with the same explicit instantiations over
+// (float|double) x (uint32|uint64) (there :116-118 via LA_SURFACE_MESH_X).
+#include <lagrange/winding/FastWindingNumber.h>
+
+#include <wn_b200.h>
+
+#include <limits>
+#include <string>
+#include <vector>
+
+namespace lagrange {
+namespace winding {
+
+namespace {
+void check(wn_status s)
+{
+    if (s != WN_OK) throw Error(std::string("FastWindingNumber: ") + wn_last_error());
+}
+} // namespace
+
+struct FastWindingNumber::Impl
+{
+    wn_engine* engine = nullptr;
+    float beta = 2.f;
+    ~Impl() { wn_destroy(engine); }
+};
+
+void FastWindingNumber::initialize(const float* vertices, int64_t num_vertices, const int32_t* triangles, int64_t num_triangles,
+                                   const FastWindingNumberOptions& options)
+{
+    wn_options opt;
+    check(wn_options_init(&opt));
+    opt.accuracy_scale = options.accuracy_scale;
+    opt.order = options.order;
+    opt.leaf_size = options.leaf_size;
+    opt.morton_bits = options.morton_bits;
+    opt.radius_mode = options.vertex_radius ? WN_RADIUS_VERTEX : WN_RADIUS_BOX_CORNER;
+    opt.device = options.device;
+    m_impl = std::make_unique<Impl>();
+    m_impl->beta = options.accuracy_scale;
+    check(wn_create(vertices, num_vertices, triangles, num_triangles, &opt, &m_impl->engine));
+}
+
+template <typename Scalar, typename Index>
+FastWindingNumber::FastWindingNumber(const SurfaceMesh<Scalar, Index>& mesh)
+    : FastWindingNumber(mesh, FastWindingNumberOptions{})
+{}
+
+template <typename Scalar, typename Index>
+FastWindingNumber::FastWindingNumber(const SurfaceMesh<Scalar, Index>& mesh, const FastWindingNumberOptions& options)
+{
+    if (mesh.get_dimension() != 3) throw Error("Fast winding number engine only supports 3D meshes");
+    if (!mesh.is_triangle_mesh()) throw Error("Fast winding number engine only supports triangle meshes");
+    const size_t nv = static_cast<size_t>(mesh.get_num_vertices());
+    const size_t nf = static_cast<size_t>(mesh.get_num_facets());
+    if (nf > static_cast<size_t>(std::numeric_limits<int32_t>::max() / 3) || nv > static_cast<size_t>(std::numeric_limits<int32_t>::max()))
+        throw Error("Fast winding number engine: mesh too large for 32-bit indices");
+    // the engine works on float coordinates and int indices, whatever the mesh stores
+    std::vector<float> vertices(nv * 3);
+    const Scalar* vsrc = mesh.vertex_data();
+    for (size_t i = 0; i < nv * 3; ++i) vertices[i] = static_cast<float>(vsrc[i]);
+    std::vector<int32_t> triangles(nf * 3);
+    const Index* fsrc = mesh.corner_data();
+    for (size_t i = 0; i < nf * 3; ++i) triangles[i] = static_cast<int32_t>(fsrc[i]);
+    initialize(vertices.data(), static_cast<int64_t>(nv), triangles.data(), static_cast<int64_t>(nf), options);
+}
+
+FastWindingNumber::FastWindingNumber() = default;
+FastWindingNumber::~FastWindingNumber() = default;
+FastWindingNumber::FastWindingNumber(FastWindingNumber&& other) noexcept = default;
+FastWindingNumber& FastWindingNumber::operator=(FastWindingNumber&& other) noexcept = default;
+
+const wn_engine* FastWindingNumber::engine() const
+{
+    if (!m_impl || !m_impl->engine) throw Error("FastWindingNumber: engine is empty (default constructed or moved from)");
+    return m_impl->engine;
+}
+
+bool FastWindingNumber::is_inside(const std::array<float, 3>& pos) const
+{
+    const wn_engine* e = engine(); // throws on an empty engine before m_impl is touched
+    uint8_t r = 0;
+    check(wn_is_inside(e, pos.data(), 1, m_impl->beta, WN_QUERY_PRESORTED, &r, nullptr));
+    return r != 0;
+}
+
+float FastWindingNumber::solid_angle(const std::array<float, 3>& pos) const
+{
+    const wn_engine* e = engine();
+    float r = 0;
+    check(wn_solid_angle(e, pos.data(), 1, m_impl->beta, WN_QUERY_PRESORTED, &r, nullptr));
+    return r;
+}
+
+void FastWindingNumber::is_inside(const float* xyz, size_t n, uint8_t* out) const
+{
+    const wn_engine* e = engine();
+    check(wn_is_inside(e, xyz, static_cast<int64_t>(n), m_impl->beta, WN_QUERY_DEFAULT, out, nullptr));
+}
+
+void FastWindingNumber::solid_angle(const float* xyz, size_t n, float* out) const
+{
+    const wn_engine* e = engine();
+    check(wn_solid_angle(e, xyz, static_cast<int64_t>(n), m_impl->beta, WN_QUERY_DEFAULT, out, nullptr));
+}
+
+void FastWindingNumber::is_inside(const Lattice& l, uint8_t* out, int64_t z_begin, int64_t z_end) const
+{
+    const wn_engine* e = engine();
+    check(wn_query_grid(e, l.origin.data(), l.spacing.data(), l.dims.data(), z_begin, z_end < 0 ? l.dims[2] : z_end, m_impl->beta, nullptr, out,
+                        nullptr));
+}
+
+void FastWindingNumber::solid_angle(const Lattice& l, float* out, int64_t z_begin, int64_t z_end) const
+{
+    const wn_engine* e = engine();
+    check(wn_query_grid(e, l.origin.data(), l.spacing.data(), l.dims.data(), z_begin, z_end < 0 ? l.dims[2] : z_end, m_impl->beta, out, nullptr,
+                        nullptr));
+}
+
+void FastWindingNumber::exact_solid_angle(const float* xyz, size_t n, float* out) const
+{
+    check(wn_exact(engine(), xyz, static_cast<int64_t>(n), out, nullptr, nullptr));
+}
+
+void FastWindingNumber::set_accuracy_scale(float beta)
+{
+    if (!(beta > 0.f)) throw Error("FastWindingNumber: accuracy scale must be positive");
+    engine();
+    m_impl->beta = beta;
+}
+
+float FastWindingNumber::accuracy_scale() const
+{
+    engine();
+    return m_impl->beta;
+}
+
+float FastWindingNumber::build_milliseconds() const
+{
+    wn_info info;
+    check(wn_get_info(engine(), &info));
+    return info.build_ms;
+}
+
+int64_t FastWindingNumber::num_triangles() const
+{
+    wn_info info;
+    check(wn_get_info(engine(), &info));
+    return info.num_triangles;
+}
+
+int64_t FastWindingNumber::tree_bytes() const
+{
+    wn_info info;
+    check(wn_get_info(engine(), &info));
+    return info.tree_bytes;
+}
+
+// Same (Scalar, Index) grid as LA_SURFACE_MESH_X (modules/core/include/lagrange/SurfaceMeshTypes.h:49-53).
+#define WN_INSTANTIATE(Scalar, Index)                                                        \
+    template FastWindingNumber::FastWindingNumber(const SurfaceMesh<Scalar, Index>& mesh); \
+    template FastWindingNumber::FastWindingNumber(const SurfaceMesh<Scalar, Index>& mesh, const FastWindingNumberOptions&);
+WN_INSTANTIATE(float, uint32_t)
+WN_INSTANTIATE(double, uint32_t)
+WN_INSTANTIATE(float, uint64_t)
+WN_INSTANTIATE(double, uint64_t)
+#undef WN_INSTANTIATE
+
+} // namespace winding
+} // namespace lagrange

@@ -1,0 +1,194 @@
+// C++ test of the drop-in class, in the shape of the reference's own test file
+// (adobe/lagrange modules/winding/tests/test_fast_winding_number.cpp): its "[!benchmark]" case draws 10 000 uniform
+// samples in the mesh bbox with std::mt19937 and counts is_inside hits (:90-109). The reference asserts nothing; here
+// the same protocol runs on a procedural torus (the dragon mesh is not available) and is checked against analytic
+// inside/outside knowledge of the torus, plus the surface contract: error messages, move-only semantics, concurrent
+// const queries (the OpenVDB/TBB call pattern, modules/volume/src/mesh_to_volume.cpp:175-183).
+// Needs a GPU: run by tests/test_cpp_host_layer.py under the `gpu` marker.
+#include <lagrange/winding/FastWindingNumber.h>
+
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <random>
+#include <thread>
+#include <vector>
+
+using Scalar = float;
+using Index = uint32_t;
+using Mesh = lagrange::SurfaceMesh<Scalar, Index>;
+
+static int g_failures = 0;
+#define CHECK(cond)                                                         \
+    do {                                                                    \
+        if (!(cond)) {                                                      \
+            std::printf("FAIL %s:%d  %s\n", __FILE__, __LINE__, #cond);     \
+            ++g_failures;                                                   \
+        }                                                                   \
+    } while (0)
+
+// torus around the Y axis, two triangles per quad, outward oriented
+static Mesh make_torus(float R, float r, int nr, int np)
+{
+    Mesh mesh;
+    const double two_pi = 6.283185307179586;
+    for (int i = 0; i < nr; ++i)
+        for (int j = 0; j < np; ++j) {
+            const double u = two_pi * i / nr, w = two_pi * j / np;
+            const double rad = R + r * std::cos(w);
+            mesh.add_vertex({float(rad * std::cos(u)), float(r * std::sin(w)), float(rad * std::sin(u))});
+        }
+    for (int i = 0; i < nr; ++i)
+        for (int j = 0; j < np; ++j) {
+            const Index v00 = i * np + j, v01 = i * np + (j + 1) % np;
+            const Index v10 = ((i + 1) % nr) * np + j, v11 = ((i + 1) % nr) * np + (j + 1) % np;
+            mesh.add_triangle(v00, v01, v11);
+            mesh.add_triangle(v00, v11, v10);
+        }
+    return mesh;
+}
+
+static bool torus_contains(float R, float r, const std::array<float, 3>& p, float margin)
+{
+    const double d = std::sqrt(double(p[0]) * p[0] + double(p[2]) * p[2]) - R;
+    return std::sqrt(d * d + double(p[1]) * p[1]) < r - margin;
+}
+static bool torus_excludes(float R, float r, const std::array<float, 3>& p, float margin)
+{
+    const double d = std::sqrt(double(p[0]) * p[0] + double(p[2]) * p[2]) - R;
+    return std::sqrt(d * d + double(p[1]) * p[1]) > r + margin;
+}
+
+int main()
+{
+    const float R = 5.f, r = 1.f;
+    const Mesh mesh = make_torus(R, r, 200, 100);
+
+    // --- surface contract ---------------------------------------------------------------------------------------
+    {
+        lagrange::SurfaceMesh<double, uint64_t> flat(2);
+        flat.add_vertex({0.0, 0.0});
+        bool threw = false;
+        try {
+            lagrange::winding::FastWindingNumber e(flat);
+        } catch (const lagrange::Error& err) {
+            threw = std::string(err.what()) == "Fast winding number engine only supports 3D meshes";
+        }
+        CHECK(threw);
+        Mesh quad;
+        for (int k = 0; k < 4; ++k) quad.add_vertex({float(k & 1), float(k >> 1), 0.f});
+        quad.add_polygon({0, 1, 3, 2});
+        threw = false;
+        try {
+            lagrange::winding::FastWindingNumber e(quad);
+        } catch (const lagrange::Error& err) {
+            threw = std::string(err.what()) == "Fast winding number engine only supports triangle meshes";
+        }
+        CHECK(threw);
+        lagrange::winding::FastWindingNumber empty;
+        threw = false;
+        try {
+            empty.is_inside({0.f, 0.f, 0.f});
+        } catch (const lagrange::Error&) {
+            threw = true;
+        }
+        CHECK(threw);
+    }
+
+    lagrange::winding::FastWindingNumber engine(mesh);
+    std::printf("build %.3f ms, %lld triangles, tree %lld bytes\n", engine.build_milliseconds(), (long long)engine.num_triangles(),
+                (long long)engine.tree_bytes());
+    CHECK(engine.num_triangles() == 200 * 100 * 2);
+
+    // --- known answers --------------------------------------------------------------------------------------------
+    const float four_pi = 12.566370614359172f;
+    CHECK(engine.is_inside({5.f, 0.f, 0.f}));
+    CHECK(!engine.is_inside({0.f, 0.f, 0.f}));
+    CHECK(!engine.is_inside({0.f, 3.f, 0.f}));
+    CHECK(std::fabs(engine.solid_angle({5.f, 0.f, 0.f}) / four_pi - 1.f) < 1e-2f);
+    CHECK(std::fabs(engine.solid_angle({0.f, 0.f, 0.f}) / four_pi) < 1e-2f);
+
+    // move semantics: the moved-to engine answers, the moved-from one is empty
+    lagrange::winding::FastWindingNumber moved(std::move(engine));
+    CHECK(moved.is_inside({5.f, 0.f, 0.f}));
+    engine = std::move(moved);
+    CHECK(engine.is_inside({-5.f, 0.2f, 0.f}));
+
+    // --- the reference's benchmark protocol: 10 000 uniform bbox samples, one is_inside call each -------------------
+    const size_t num_samples = 10000;
+    std::uniform_real_distribution<Scalar> px(-6.f, 6.f), py(-1.f, 1.f), pz(-6.f, 6.f);
+    std::vector<std::array<float, 3>> samples(num_samples);
+    {
+        std::mt19937 gen;
+        for (auto& s : samples) s = {px(gen), py(gen), pz(gen)};
+    }
+    size_t num_inside = 0, wrong = 0;
+    auto t0 = std::chrono::steady_clock::now();
+    for (const auto& s : samples) {
+        const bool in = engine.is_inside(s);
+        num_inside += in;
+        if (torus_contains(R, r, s, 0.02f) && !in) ++wrong;
+        if (torus_excludes(R, r, s, 0.02f) && in) ++wrong;
+    }
+    auto t1 = std::chrono::steady_clock::now();
+    const double single_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    std::printf("pimpl wrapper, %zu single-point calls: %.2f ms (%.2f us/call), %zu inside\n", num_samples, single_ms,
+                1e3 * single_ms / num_samples, num_inside);
+    CHECK(wrong == 0);
+
+    // the batched overload must give the same answers as the single-point calls
+    std::vector<uint8_t> batch(num_samples);
+    t0 = std::chrono::steady_clock::now();
+    engine.is_inside(samples[0].data(), num_samples, batch.data());
+    t1 = std::chrono::steady_clock::now();
+    size_t batch_inside = 0;
+    for (auto b : batch) batch_inside += b;
+    std::printf("batched overload, same %zu samples: %.3f ms, %zu inside\n", num_samples,
+                std::chrono::duration<double, std::milli>(t1 - t0).count(), batch_inside);
+    CHECK(batch_inside == num_inside);
+
+    // tree vs exact mode on the same samples
+    std::vector<float> om_tree(num_samples), om_exact(num_samples);
+    engine.solid_angle(samples[0].data(), num_samples, om_tree.data());
+    engine.exact_solid_angle(samples[0].data(), num_samples, om_exact.data());
+    double max_err = 0;
+    for (size_t i = 0; i < num_samples; ++i) max_err = std::max(max_err, double(std::fabs(om_tree[i] - om_exact[i])) / four_pi);
+    std::printf("tree (beta=2) vs exact mode: max |dw| = %.3e\n", max_err);
+    CHECK(max_err < 2e-2);
+
+    // lattice overload agrees with explicit points
+    {
+        lagrange::winding::Lattice lat;
+        lat.origin = {-6.5f, -1.5f, -6.5f};
+        lat.spacing = {13.f / 40, 3.f / 16, 13.f / 40};
+        lat.dims = {40, 16, 40};
+        std::vector<uint8_t> g(40 * 16 * 40);
+        engine.is_inside(lat, g.data());
+        size_t mismatch = 0;
+        for (int k = 0; k < 40; k += 3)
+            for (int j = 0; j < 16; j += 2)
+                for (int i = 0; i < 40; i += 3) {
+                    const std::array<float, 3> p{lat.origin[0] + lat.spacing[0] * (float(i) + 0.5f), lat.origin[1] + lat.spacing[1] * (float(j) + 0.5f),
+                                                 lat.origin[2] + lat.spacing[2] * (float(k) + 0.5f)};
+                    mismatch += engine.is_inside(p) != (g[(size_t(k) * 16 + j) * 40 + i] != 0);
+                }
+        CHECK(mismatch == 0);
+    }
+
+    // --- concurrent const queries from several host threads ---------------------------------------------------------
+    {
+        std::atomic<size_t> bad{0};
+        std::vector<std::thread> pool;
+        for (int t = 0; t < 4; ++t)
+            pool.emplace_back([&, t]() {
+                for (size_t i = t; i < 2000; i += 4)
+                    if (engine.is_inside(samples[i]) != (batch[i] != 0)) ++bad;
+            });
+        for (auto& th : pool) th.join();
+        CHECK(bad == 0);
+    }
+
+    std::printf(g_failures ? "FAILED (%d)\n" : "ALL PASSED\n", g_failures);
+    return g_failures ? 1 : 0;
+}

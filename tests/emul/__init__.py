@@ -1,0 +1,112 @@
+"""Host emulation of the device build (TEST INFRASTRUCTURE ONLY): ctypes loader for tests/emul/wn_emul.cpp."""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "libwn_emul.so")
+_SRC = os.path.join(_HERE, "wn_emul.cpp")
+_CSRC = os.path.join(_HERE, "..", "..", "lagrange_b200", "csrc")
+_lib = None
+
+_f32p = ctypes.POINTER(ctypes.c_float)
+_i32p = ctypes.POINTER(ctypes.c_int32)
+_u32p = ctypes.POINTER(ctypes.c_uint32)
+_u64p = ctypes.POINTER(ctypes.c_uint64)
+
+
+def build(force=False):
+    deps = [_SRC] + [os.path.join(_CSRC, f) for f in ("wn_device.cuh", "wn_build_core.cuh")]
+    stale = (not os.path.exists(_LIB)) or any(os.path.getmtime(_LIB) < os.path.getmtime(d) for d in deps)
+    if force or stale:
+        subprocess.run(["/usr/bin/g++", "-O2", "-march=x86-64-v3", "-ffp-contract=off", "-fPIC", "-std=c++17", "-w", "-shared",
+                        "-o", _LIB, _SRC], check=True)
+    return _LIB
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = ctypes.CDLL(_LIB)
+        L.emul_build.restype = ctypes.c_void_p
+        L.emul_build.argtypes = [_f32p, ctypes.c_int64, _i32p, ctypes.c_int64, _i32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                 ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        L.emul_destroy.argtypes = [ctypes.c_void_p]
+        for name in ("emul_error", "emul_max_depth", "emul_width"):
+            getattr(L, name).restype = ctypes.c_int
+            getattr(L, name).argtypes = [ctypes.c_void_p]
+        for name in ("emul_num_internal", "emul_num_entries"):
+            getattr(L, name).restype = ctypes.c_int64
+            getattr(L, name).argtypes = [ctypes.c_void_p]
+        L.emul_get_topology.argtypes = [ctypes.c_void_p, _i32p]
+        L.emul_get_ref23.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, _f32p]
+        L.emul_get_packed.argtypes = [ctypes.c_void_p, _f32p, _i32p, _f32p, _u32p]
+        L.emul_query.argtypes = [ctypes.c_void_p, _f32p, ctypes.c_int64, ctypes.c_float, _f32p, _u64p]
+        L.emul_inside_from_omega.restype = ctypes.c_int
+        L.emul_inside_from_omega.argtypes = [ctypes.c_float]
+        L.emul_lattice_coord.restype = ctypes.c_float
+        L.emul_lattice_coord.argtypes = [ctypes.c_float, ctypes.c_float, ctypes.c_int]
+        _lib = L
+    return _lib
+
+
+class EmulEngine:
+    def __init__(self, vertices, facets, child=None, leaf_size=1, order=2, radius_mode=0, approx_single=None, morton_bits=63):
+        self.v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 3)
+        self.f = np.ascontiguousarray(facets, dtype=np.int32).reshape(-1, 3)
+        if approx_single is None:
+            approx_single = 1 if child is not None else 0
+        if child is not None:
+            child = np.ascontiguousarray(child, dtype=np.int32)
+            nn, w = child.shape
+            cp = child.ctypes.data_as(_i32p)
+        else:
+            nn, w, cp = 0, 0, None
+        self._h = lib().emul_build(self.v.ctypes.data_as(_f32p), len(self.v), self.f.ctypes.data_as(_i32p), len(self.f), cp, nn, w,
+                                   leaf_size, order, radius_mode, approx_single, morton_bits)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().emul_destroy(self._h)
+            self._h = None
+
+    error = property(lambda self: lib().emul_error(self._h))
+    num_internal = property(lambda self: int(lib().emul_num_internal(self._h)))
+    num_entries = property(lambda self: int(lib().emul_num_entries(self._h)))
+    max_depth = property(lambda self: lib().emul_max_depth(self._h))
+    width = property(lambda self: lib().emul_width(self._h))
+
+    def topology(self):
+        out = np.empty((self.num_internal, self.width), dtype=np.int32)
+        lib().emul_get_topology(self._h, out.ctypes.data_as(_i32p))
+        return out
+
+    def ref23(self, first=0, count=None):
+        if count is None:
+            count = self.num_internal + len(self.f) - first
+        out = np.empty((count, 23), dtype=np.float32)
+        lib().emul_get_ref23(self._h, first, count, out.ctypes.data_as(_f32p))
+        return out
+
+    def packed(self):
+        n, nt = self.num_entries, len(self.f)
+        rec = np.empty((6, n, 4), dtype=np.float32)
+        link = np.empty(n, dtype=np.int32)
+        tris = np.empty((nt, 3, 4), dtype=np.float32)
+        order = np.empty(nt, dtype=np.uint32)
+        lib().emul_get_packed(self._h, rec.ctypes.data_as(_f32p), link.ctypes.data_as(_i32p), tris.ctypes.data_as(_f32p),
+                              order.ctypes.data_as(_u32p))
+        return rec, link, tris, order
+
+    def solid_angle(self, queries, beta=2.0, counters=False):
+        q = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, 3)
+        out = np.empty(len(q), dtype=np.float32)
+        cnt = np.zeros(3, dtype=np.uint64)
+        lib().emul_query(self._h, q.ctypes.data_as(_f32p), len(q), beta, out.ctypes.data_as(_f32p),
+                         cnt.ctypes.data_as(_u64p) if counters else None)
+        return (out, cnt) if counters else out

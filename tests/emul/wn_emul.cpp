@@ -1,0 +1,231 @@
+// wn_emul.cpp — TEST INFRASTRUCTURE ONLY. Host emulation of the device build: runs the per-thread bodies of
+// lagrange_b200/csrc/wn_build_core.cuh / wn_device.cuh (the same source the sm_100a kernels inline) in sequential
+// loops, so the CPU-only test tier can check the Karras topology, the arrival-counter climb, the skip-link packing and
+// the folded far-field records against the oracle without a GPU. Never linked into the product.
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <numeric>
+#include <vector>
+
+#include "../../lagrange_b200/csrc/wn_build_core.cuh"
+
+namespace {
+
+struct Emul
+{
+    std::vector<float> v;
+    std::vector<int> tri;
+    std::vector<int> child, parent, arrive, ntri, size, link;
+    std::vector<unsigned char> slot, collapsed;
+    std::vector<unsigned> prim, r2v, tri_order;
+    std::vector<float4> local, rec[6], tris;
+    WnBuild b;
+    WnTreeView view;
+    int err = 0, max_depth = 0;
+};
+
+} // namespace
+
+extern "C" {
+
+// child_in == nullptr: LBVH build (Morton + stable sort + Karras). Otherwise imported topology (neutral encoding).
+void* emul_build(const float* v, int64_t nV, const int32_t* tri, int64_t nT, const int32_t* child_in, int64_t num_nodes, int width,
+                 int leaf_size, int order, int radius_mode, int approx_single, int morton_bits)
+{
+    Emul* e = new Emul;
+    e->v.assign(v, v + nV * 3);
+    e->tri.assign(tri, tri + nT * 3);
+    WnBuild& b = e->b;
+    memset(&b, 0, sizeof(b));
+    b.v_xyz = e->v.data();
+    b.tri = e->tri.data();
+    b.nV = (int)nV;
+    b.nT = (int)nT;
+    b.nL = (int)nT;
+    b.leaf_size = leaf_size;
+    b.order = order;
+    b.radius_mode = radius_mode;
+    b.approx_single = approx_single;
+    b.err = &e->err;
+    b.max_depth = &e->max_depth;
+    e->prim.resize(nT);
+    if (!child_in) {
+        b.W = 2;
+        b.nI = nT >= 2 ? (int)nT - 1 : 1;
+        // K1: bounds of centroids + Morton codes (same float ops as k_centroid_bounds / k_morton)
+        float lo[3] = {3.4e38f, 3.4e38f, 3.4e38f}, hi[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+        std::vector<float> cen(nT * 3);
+        for (int64_t t = 0; t < nT; ++t)
+            for (int a = 0; a < 3; ++a) {
+                const float c = (v[3 * tri[3 * t] + a] + v[3 * tri[3 * t + 1] + a] + v[3 * tri[3 * t + 2] + a]) * (1.0f / 3.0f);
+                cen[3 * t + a] = c;
+                if (c == c) {
+                    lo[a] = std::min(lo[a], c);
+                    hi[a] = std::max(hi[a], c);
+                }
+            }
+        const float ext = std::max(hi[0] - lo[0], std::max(hi[1] - lo[1], hi[2] - lo[2]));
+        const float inv = ext > 0.0f ? 1.0f / ext : 0.0f;
+        std::vector<uint64_t> keys(nT);
+        const int bpa = morton_bits == 63 ? 21 : 10;
+        for (int64_t t = 0; t < nT; ++t)
+            keys[t] = wn_morton((cen[3 * t] - lo[0]) * inv, (cen[3 * t + 1] - lo[1]) * inv, (cen[3 * t + 2] - lo[2]) * inv, bpa);
+        // K2: stable sort by key (what a stable LSD radix sort produces)
+        std::vector<unsigned> idx(nT);
+        std::iota(idx.begin(), idx.end(), 0u);
+        std::stable_sort(idx.begin(), idx.end(), [&](unsigned a, unsigned c) { return keys[a] < keys[c]; });
+        std::vector<uint64_t> sorted(nT);
+        for (int64_t i = 0; i < nT; ++i) sorted[i] = keys[idx[i]];
+        e->prim = idx;
+        const int64_t nN = (int64_t)b.nI + b.nL;
+        e->child.assign((size_t)b.nI * 2, -1);
+        e->parent.assign(nN, -1);
+        e->slot.assign(nN, 0);
+        if (nT >= 2) {
+            for (int i = 0; i < (int)nT - 1; ++i) wn_lbvh_node(sorted.data(), (int)nT, i, e->child.data(), e->parent.data(), e->slot.data());
+        } else {
+            e->child[0] = 1;
+            e->parent[1] = 0;
+        }
+        b.child = e->child.data();
+        b.parent = e->parent.data();
+        b.slot = e->slot.data();
+    } else {
+        b.W = width;
+        b.nI = (int)num_nodes;
+        const int64_t nN = (int64_t)b.nI + b.nL;
+        std::iota(e->prim.begin(), e->prim.end(), 0u);
+        e->child.assign((size_t)b.nI * b.W, -1);
+        e->parent.assign(nN, -1);
+        e->slot.assign(nN, 0);
+        b.child = e->child.data();
+        b.parent = e->parent.data();
+        b.slot = e->slot.data();
+        std::vector<int> seen(nN, 0);
+        for (int i = 0; i < b.nI; ++i) wn_import_node(b, child_in, seen.data(), i);
+        for (int i = 0; i < (int)nN; ++i) wn_import_check(b, seen.data(), i);
+    }
+    b.prim = e->prim.data();
+    const int64_t nN = (int64_t)b.nI + b.nL;
+    e->local.resize((size_t)nN * 9);
+    e->arrive.assign(b.nI, 0);
+    e->ntri.assign(nN, 0);
+    e->size.assign(nN, 0);
+    e->collapsed.assign(b.nI, 0);
+    e->r2v.assign(nN, 0);
+    b.local = e->local.data();
+    b.arrive = e->arrive.data();
+    b.ntri = e->ntri.data();
+    b.size = e->size.data();
+    b.collapsed = e->collapsed.data();
+    b.r2v = e->r2v.data();
+    if (e->err == 0) {
+        for (int l = 0; l < b.nL; ++l) wn_climb_leaf(b, l);
+        if (radius_mode == 1)
+            for (int l = 0; l < b.nL; ++l) wn_vertex_radius_leaf(b, l);
+    }
+    const int n_entries = (e->err == 0 && nT > 0) ? e->size[0] : 0;
+    for (int k = 0; k < 6; ++k) {
+        e->rec[k].resize(n_entries);
+        b.rec[k] = e->rec[k].data();
+    }
+    e->link.resize(n_entries);
+    e->tris.resize((size_t)nT * 3);
+    e->tri_order.resize(nT);
+    b.link = e->link.data();
+    b.tris = e->tris.data();
+    b.tri_order = e->tri_order.data();
+    if (e->err == 0 && nT > 0 && e->ntri[0] == b.nL)
+        for (int node = 0; node < (int)nN; ++node) wn_pack_node(b, node);
+    else if (nT > 0 && e->err == 0)
+        e->err = WN_ERR_TOPOLOGY_BAD_CHILD;
+    for (int k = 0; k < 6; ++k) e->view.rec[k] = e->rec[k].data();
+    e->view.link = e->link.data();
+    e->view.tri = e->tris.data();
+    e->view.n_entries = n_entries;
+    e->view.n_tris = (int)nT;
+    return e;
+}
+
+void emul_destroy(void* h)
+{
+    delete static_cast<Emul*>(h);
+}
+int emul_error(void* h)
+{
+    return static_cast<Emul*>(h)->err;
+}
+int64_t emul_num_internal(void* h)
+{
+    return static_cast<Emul*>(h)->b.nI;
+}
+int64_t emul_num_entries(void* h)
+{
+    return static_cast<Emul*>(h)->view.n_entries;
+}
+int emul_max_depth(void* h)
+{
+    return static_cast<Emul*>(h)->max_depth;
+}
+int emul_width(void* h)
+{
+    return static_cast<Emul*>(h)->b.W;
+}
+
+// neutral encoding, [nI * W]
+void emul_get_topology(void* h, int32_t* out)
+{
+    Emul* e = static_cast<Emul*>(h);
+    for (size_t k = 0; k < e->child.size(); ++k) {
+        const int c = e->child[k];
+        out[k] = c < 0 ? WN_CHILD_EMPTY : (c >= e->b.nI ? wn_enc_tri((int)e->prim[c - e->b.nI]) : c);
+    }
+}
+
+void emul_get_ref23(void* h, int64_t first, int64_t count, float* out)
+{
+    Emul* e = static_cast<Emul*>(h);
+    for (int64_t k = 0; k < count; ++k) {
+        WnLocal d;
+        wn_load_local(e->local.data() + (first + k) * 9, d, false);
+        wn_local_to_ref23(d, out + k * 23);
+    }
+}
+
+// packed arrays: rec [6][n_entries][4], link [n_entries], tris [nT][3][4], tri_order [nT]
+void emul_get_packed(void* h, float* rec, int32_t* link, float* tris, uint32_t* tri_order)
+{
+    Emul* e = static_cast<Emul*>(h);
+    const size_t n = e->link.size();
+    for (int k = 0; k < 6; ++k) memcpy(rec + k * n * 4, e->rec[k].data(), n * sizeof(float4));
+    memcpy(link, e->link.data(), n * sizeof(int));
+    memcpy(tris, e->tris.data(), e->tris.size() * sizeof(float4));
+    memcpy(tri_order, e->tri_order.data(), e->tri_order.size() * sizeof(unsigned));
+}
+
+void emul_query(void* h, const float* q, int64_t n, float beta, float* out, uint64_t* counters)
+{
+    Emul* e = static_cast<Emul*>(h);
+    unsigned long long cnt[3] = {0, 0, 0};
+    for (int64_t i = 0; i < n; ++i)
+        out[i] = wn_traverse_point(e->view, q[3 * i], q[3 * i + 1], q[3 * i + 2], beta * beta, counters ? cnt : nullptr);
+    if (counters) {
+        counters[0] = cnt[0];
+        counters[1] = cnt[1];
+        counters[2] = cnt[2];
+    }
+}
+
+int emul_inside_from_omega(float omega)
+{
+    return wn_inside_from_omega(omega) ? 1 : 0;
+}
+
+float emul_lattice_coord(float origin, float spacing, int i)
+{
+    return wn_lattice_coord(origin, spacing, i);
+}
+
+} // extern "C"

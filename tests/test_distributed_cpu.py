@@ -1,0 +1,65 @@
+"""CPU tier: the N>1 host logic (sharding + tree replication) with world_size 2 over gloo."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from lagrange_b200.distributed import broadcast_packed, shard_range, slab_range
+
+
+def test_ranges_tile_exactly():
+    for n in (0, 1, 7, 512, 1000003):
+        for world in (1, 2, 3, 4, 8):
+            cuts = [shard_range(n, r, world) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == n
+            assert all(cuts[i][1] == cuts[i + 1][0] for i in range(world - 1))
+            assert max(b - a for a, b in cuts) - min(b - a for a, b in cuts) <= 1
+    for nz in (512, 100, 37):
+        for world in (2, 4, 8):
+            cuts = [slab_range(nz, r, world, align=8) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == nz
+            assert all(cuts[i][1] == cuts[i + 1][0] for i in range(world - 1))
+            assert all(a % 8 == 0 for a, _ in cuts)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, nz, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # rank 0 owns the "packed tree"; everybody must end up with the same bytes
+        blob = None
+        if rank == 0:
+            blob = np.frombuffer(np.random.Generator(np.random.PCG64(5)).bytes(100003), dtype=np.uint8).copy()
+        got = broadcast_packed(blob, src=0, device=torch.device("cpu"))
+        expect = np.frombuffer(np.random.Generator(np.random.PCG64(5)).bytes(100003), dtype=np.uint8)
+        assert got.dtype == torch.uint8 and np.array_equal(got.numpy(), expect)
+        # every rank "classifies" its slab; no collective on the data path; results are gathered only for the check
+        z0, z1 = slab_range(nz, rank, world, align=4)
+        mine = torch.arange(z0, z1, dtype=torch.int64)
+        sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(sizes, torch.tensor([z1 - z0]))
+        assert sum(int(s) for s in sizes) == nz
+        np.save(os.path.join(out_dir, f"slab{rank}.npy"), mine.numpy())
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_ranks_gloo(tmp_path):
+    world, nz = 2, 37
+    mp.spawn(_worker, args=(world, _free_port(), nz, str(tmp_path)), nprocs=world, join=True)
+    slabs = np.concatenate([np.load(tmp_path / f"slab{r}.npy") for r in range(world)])
+    assert np.array_equal(slabs, np.arange(nz))

@@ -1,0 +1,320 @@
+"""GPU tier (-m gpu): the CUDA path, called through the C-ABI, against the oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): is_inside bit-identical to the reference algorithm wherever |w_ref - 0.5| > 1e-3;
+solid_angle within 1e-4 * 4 pi. With the oracle's topology imported (oracle-tree mode) the second bar is
+met literally and the traversal counters are integer-identical; with the GPU-built LBVH the tree differs from the
+reference's, so solid_angle is judged against exact64 with the restatement's own error as the yardstick.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from conftest import FOUR_PI, band_mask, small_config
+
+pytestmark = pytest.mark.gpu
+
+TOL_OMEGA = 1e-4 * FOUR_PI
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+@pytest.fixture(scope="module")
+def lb():
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tier needs a CUDA device"
+    import lagrange_b200
+
+    return lagrange_b200
+
+
+# ---- K2 radix sort ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 2, 31, 4096, 4097, 100003, 1 << 20])
+def test_radix_sort_is_a_stable_sort(lb, n):
+    import ctypes
+
+    from lagrange_b200 import _capi
+
+    rng = np.random.Generator(np.random.PCG64(n))
+    L = _capi.lib()
+    for dtype, fn, bits in ((np.uint64, L.wn_debug_sort_pairs_u64, 63), (np.uint32, L.wn_debug_sort_pairs_u32, 30)):
+        # few distinct keys => many ties => stability matters
+        keys = rng.integers(0, 1 << (bits if n < 5000 else 12), size=n, dtype=np.uint64).astype(dtype)
+        if n > 10:
+            keys[::7] = rng.integers(0, 1 << bits, size=len(keys[::7]), dtype=np.uint64).astype(dtype)
+        vals = np.arange(n, dtype=np.uint32)
+        k, v = keys.copy(), vals.copy()
+        _capi.check(fn(ctypes.c_void_p(k.ctypes.data), ctypes.c_void_p(v.ctypes.data), n, 0, bits))
+        order = np.argsort(keys, kind="stable")
+        assert np.array_equal(k, keys[order]) and np.array_equal(v, vals[order])
+
+
+# ---- oracle-tree mode: same topology as the reference restatement --------------------------------------------------------
+@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5])
+def test_oracle_tree_mode_matches_the_reference_algorithm(lb, oracle_mod, prim, cfg):
+    V, F, q, lattice = small_config(prim, cfg)
+    ref = oracle_mod.RefEngine(V, F)
+    topo = ref.topology()
+    eng = lb.FastWindingNumber(V, F, topology=topo, keep_build_data=True)
+    info = eng.info
+    assert info["width"] == 4 and info["num_entries"] == ref.num_nodes + len(F)
+    # K4 moments: bit-identical to the oracle's stored lanes
+    r23 = eng.debug_node_moments()
+    bd = ref.boxdata()
+    nI = ref.num_nodes
+    sel = topo != -1
+    nodes = np.where(topo >= 0, topo, nI - (topo + 2))
+    assert np.array_equal(bd[sel], r23[nodes[sel]])
+    assert np.array_equal(eng.debug_topology(), topo)
+    for beta in (2.0, 3.0):
+        o_ref, c_ref = ref.solid_angle(q, beta=beta, counters=True)
+        o_gpu = eng.solid_angle(q, accuracy_scale=beta)
+        assert np.abs(o_gpu - o_ref).max() < TOL_OMEGA, np.abs(o_gpu - o_ref).max() / FOUR_PI
+        # same accepted set per point => the traversal counters agree with the oracle's. The device forms |r|^2 with
+        # FMAs, so a point within an ulp of a node's threshold may flip: allow a 1e-5 relative slack, nothing more.
+        st = eng.query_stats(q, accuracy_scale=beta)
+        for got, want in zip((st["node_tests"], st["far_field_evals"], st["exact_triangles"]), (int(c) for c in c_ref)):
+            assert abs(got - want) <= 3 + 1e-5 * want, (st, c_ref)
+    ins_ref = ref.is_inside(q)
+    ins_gpu = eng.is_inside(q)
+    m = band_mask(ref.solid_angle(q) / FOUR_PI)
+    assert np.array_equal(ins_gpu[m], ins_ref[m])
+    assert np.mean(ins_gpu != ins_ref) < 1e-3
+    if lattice is not None:
+        om_g, ins_g = eng.query_grid(*lattice, want_omega=True, want_inside=True)
+        assert np.array_equal(om_g, eng.solid_angle(q)) and np.array_equal(ins_g, ins_gpu)
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_golden_fixtures(lb, path):
+    g = np.load(path)
+    eng = lb.FastWindingNumber(g["V"], g["F"], topology=g["topology"])
+    for beta in (2, 3):
+        om = eng.solid_angle(g["Q"], accuracy_scale=float(beta))
+        assert np.abs(om - g[f"ref_beta{beta}"]).max() < TOL_OMEGA
+        st = eng.query_stats(g["Q"], accuracy_scale=float(beta))
+        for got, want in zip((st["node_tests"], st["far_field_evals"], st["exact_triangles"]), g[f"cnt_beta{beta}"]):
+            assert abs(got - int(want)) <= 3, (st, g[f"cnt_beta{beta}"])
+    w = g["ref_beta2"] / FOUR_PI
+    m = band_mask(w)
+    assert np.array_equal(eng.is_inside(g["Q"])[m], g["inside_beta2"][m])
+    ex = eng.exact_solid_angle(g["Q"])
+    assert np.abs(ex - g["exact64"]).max() < TOL_OMEGA
+
+
+# ---- GPU-built LBVH --------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5])
+def test_lbvh_build_matches_host_emulation_and_exact(lb, oracle_mod, emul_mod, prim, cfg):
+    V, F, q, lattice = small_config(prim, cfg)
+    eng = lb.FastWindingNumber(V, F, keep_build_data=True)
+    em = emul_mod.EmulEngine(V, F)
+    # K1-K3: same Morton order and Karras topology as the sequential emulation of the same source
+    assert np.array_equal(eng.debug_topology(), em.topology())
+    # K4: moments bit-identical (unfused arithmetic on both sides)
+    assert np.array_equal(eng.debug_node_moments(), em.ref23())
+    assert eng.info["num_entries"] == em.num_entries and eng.info["max_depth"] == em.max_depth
+    o_gpu = eng.solid_angle(q)
+    o_em = em.solid_angle(q)
+    assert np.abs(o_gpu - o_em).max() < TOL_OMEGA
+    st = eng.query_stats(q)
+    _, c_em = em.solid_angle(q, counters=True)
+    assert abs(st["far_field_evals"] - int(c_em[1])) <= 1e-4 * int(c_em[1]) + 2  # FMA vs unfused test: rare boundary flips
+    # accuracy: judged against exact64 with the reference restatement's own error as the yardstick
+    ex = oracle_mod.exact64(V, F, q)
+    ref = oracle_mod.RefEngine(V, F)
+    o_ref = ref.solid_angle(q)
+    err_gpu = np.abs(o_gpu - ex) / FOUR_PI
+    err_ref = np.abs(o_ref - ex) / FOUR_PI
+    assert err_gpu.max() < max(3.0 * err_ref.max(), 2e-3) and err_gpu.mean() < max(2.0 * err_ref.mean(), 5e-4)
+    # is_inside: identical to the reference algorithm away from the 0.5 level set (band widened by both trees' error)
+    ins_gpu, ins_ref = eng.is_inside(q), ref.is_inside(q)
+    m = band_mask(o_ref / FOUR_PI, band=1e-3 + err_gpu.max() + err_ref.max())
+    assert np.array_equal(ins_gpu[m], ins_ref[m])
+    # beta sweep converges to exact (cfg5's sweep, reduced)
+    for beta, bound in ((4.0, 1.5e-3), (8.0, 1e-4)):
+        assert np.abs(eng.solid_angle(q, accuracy_scale=beta) - ex).max() / FOUR_PI < bound
+
+
+@pytest.mark.parametrize("opts", [dict(leaf_size=4), dict(leaf_size=16), dict(morton_bits=30), dict(radius_mode="vertex"),
+                                  dict(order=1), dict(order=0), dict(approximate_single_triangles=True)])
+def test_lbvh_options_match_host_emulation(lb, emul_mod, prim, opts):
+    V, F, q, _ = small_config(prim, 1)
+    eng = lb.FastWindingNumber(V, F, **opts)
+    ekw = dict(opts)
+    if "radius_mode" in ekw:
+        ekw["radius_mode"] = 1
+    if "approximate_single_triangles" in ekw:
+        ekw["approx_single"] = 1 if ekw.pop("approximate_single_triangles") else 0
+    em = emul_mod.EmulEngine(V, F, **ekw)
+    assert eng.info["num_entries"] == em.num_entries
+    assert np.abs(eng.solid_angle(q) - em.solid_angle(q)).max() < TOL_OMEGA
+
+
+# ---- batching must not change per-point results ------------------------------------------------------------------------------
+def test_results_do_not_depend_on_batch_composition(lb, prim):
+    V, F = prim.generate_torus(5, 1, 60, 30)
+    eng = lb.FastWindingNumber(V, F)
+    q = prim.uniform_points_in_bbox(*prim.mesh_bbox(V), 50000, seed=11)
+    base = eng.solid_angle(q)  # Morton-sorted internally
+    assert np.array_equal(eng.solid_angle(q, presorted=True), base)  # original (incoherent) order, no sort
+    perm = np.random.Generator(np.random.PCG64(1)).permutation(len(q))
+    assert np.array_equal(eng.solid_angle(q[perm])[np.argsort(perm)], base)
+    for i in (0, 17, 49999):  # the reference's single-point signature
+        assert eng.solid_angle(q[i]) == base[i]
+        assert eng.is_inside(q[i]) == bool(base[i] >= np.float32(6.2831854820251465))
+    assert np.array_equal(eng.solid_angle(q[:1000]), base[:1000])  # QPL=1 path vs QPL=2 path? (size dependent)
+    os.environ["WN_QPL"] = "1"
+    try:
+        assert np.array_equal(eng.solid_angle(q), base)
+    finally:
+        os.environ["WN_QPL"] = "2"
+    try:
+        assert np.array_equal(eng.solid_angle(q), base)
+    finally:
+        del os.environ["WN_QPL"]
+
+
+def test_grid_overload_equals_points_and_slabs_tile(lb, prim):
+    V, F = prim.generate_torus(5, 1, 50, 24)
+    eng = lb.FastWindingNumber(V, F)
+    o, s, d = prim.lattice_for_bbox(*prim.mesh_bbox(V), (37, 11, 29))
+    P = prim.lattice_points(o, s, d)
+    om, ins = eng.query_grid(o, s, d, want_omega=True, want_inside=True)
+    assert np.array_equal(om, eng.solid_angle(P)) and np.array_equal(ins, eng.is_inside(P))
+    parts = [eng.query_grid(o, s, d, z_range=(a, b), want_omega=True)[0] for a, b in ((0, 5), (5, 6), (6, 29))]
+    assert np.array_equal(np.concatenate(parts), om)
+    assert eng.query_grid(o, s, d, z_range=(4, 4))[1].size == 0
+    ex_om, ex_ins = eng.exact_grid(o, s, d, want_omega=True, want_inside=True)
+    assert np.array_equal(ex_om, eng.exact_solid_angle(P))
+    st_g = eng.query_stats_grid(o, s, d)
+    st_p = eng.query_stats(P)
+    assert [st_g[k] for k in ("node_tests", "far_field_evals", "exact_triangles")] == [st_p[k] for k in ("node_tests", "far_field_evals", "exact_triangles")]
+
+
+# ---- K7 exact mode -----------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 100, 5000])
+def test_exact_mode_is_ground_truth(lb, oracle_mod, prim, n):
+    V, F = prim.generate_torus(5, 1, 120, 50)  # 24 000 triangles: several chunks and tiles
+    eng = lb.FastWindingNumber(V, F)
+    q = prim.uniform_points_in_bbox(*prim.mesh_bbox(V), n, seed=n)
+    ex = oracle_mod.exact64(V, F, q)
+    om = eng.exact_solid_angle(q)
+    assert np.abs(om - ex).max() < 2e-5 * FOUR_PI
+    m = band_mask(ex / FOUR_PI)
+    assert np.array_equal(eng.exact_is_inside(q).astype(bool)[m], (ex / FOUR_PI > 0.5)[m])
+
+
+# ---- edge cases the reference's surface defines ------------------------------------------------------------------------------
+def test_edge_cases(lb, oracle_mod):
+    empty = lb.FastWindingNumber(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.int32))
+    q = np.array([[0, 0, 0], [1, 2, 3]], dtype=np.float32)
+    assert np.all(empty.solid_angle(q) == 0) and not empty.is_inside(q).any() and np.all(empty.exact_solid_angle(q) == 0)
+    assert empty.solid_angle(np.zeros((0, 3), np.float32)).shape == (0,)
+    V = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1], [2, 2, 2]], dtype=np.float32)
+    F = np.array([[0, 1, 2], [0, 1, 2], [0, 1, 1], [4, 4, 4], [0, 2, 3], [0, 3, 1], [1, 3, 2], [0, 2, 1]], dtype=np.int32)
+    qq = np.array([[0.1, 0.1, 0.1], [3, 3, 3], [0, 0, 0], [1, 0, 0], [0.25, 0.25, 0], [-1, 0.5, 0.2]], dtype=np.float32)
+    ex = oracle_mod.exact64(V, F, qq)
+    for kw in ({}, {"leaf_size": 4}, {"topology": oracle_mod.RefEngine(V, F).topology()}):
+        eng = lb.FastWindingNumber(V, F, **kw)
+        assert np.abs(eng.solid_angle(qq, accuracy_scale=50.0) - ex).max() < 1e-4
+        assert np.abs(eng.exact_solid_angle(qq) - ex).max() < 1e-5
+    one = lb.FastWindingNumber(V, F[4:5])
+    assert abs(one.solid_angle([0.1, 0.1, 0.1]) - oracle_mod.exact64(V, F[4:5], qq[:1])[0]) < 1e-5
+    with pytest.raises(lb.Error, match="vertex index"):
+        lb.FastWindingNumber(V, np.array([[0, 1, 7]], dtype=np.int32))
+    with pytest.raises(lb.Error, match="topology"):
+        lb.FastWindingNumber(V, F[:2], topology=np.array([[-2, -2, -1, -1]], dtype=np.int32))
+    with pytest.raises(lb.Error):
+        lb.FastWindingNumber(V, F).solid_angle(np.zeros((4, 2), np.float32))
+    # non-finite queries must not hang or poison their neighbours
+    eng = lb.FastWindingNumber(V, F)
+    bad = np.array([[np.nan, 0, 0], [0.1, 0.1, 0.1], [np.inf, 0, 0]], dtype=np.float32)
+    r = eng.solid_angle(bad)
+    assert abs(r[1] - eng.solid_angle([0.1, 0.1, 0.1])) == 0
+
+
+def test_device_pointers_and_pack_roundtrip(lb, prim):
+    import torch
+
+    V, F = prim.generate_subdivided_sphere("icosahedron", 4)
+    eng = lb.FastWindingNumber(torch.from_numpy(V).cuda(), torch.from_numpy(F).cuda())  # device-resident mesh
+    q = prim.uniform_points_in_bbox([-1.2] * 3, [1.2] * 3, 20000, seed=5)
+    host = eng.solid_angle(q)
+    dq = torch.from_numpy(q).cuda()
+    dev = eng.solid_angle(dq)
+    assert dev.is_cuda and np.array_equal(dev.cpu().numpy(), host)
+    assert np.array_equal(eng.is_inside(dq).cpu().numpy(), eng.is_inside(q))
+    o, s, d = prim.lattice_for_bbox([-1.0] * 3, [1.0] * 3, 24)
+    om_d, ins_d = eng.query_grid(o, s, d, want_omega=True, device_output=True)
+    om_h, ins_h = eng.query_grid(o, s, d, want_omega=True)
+    assert om_d.is_cuda and np.array_equal(om_d.cpu().numpy(), om_h) and np.array_equal(ins_d.cpu().numpy(), ins_h)
+    # inside count ~ sphere volume / cell volume
+    cell = float(np.prod(s))
+    assert abs(ins_h.sum() * cell - 4.0 / 3.0 * np.pi) < 0.15
+    # packed tree: host and device round trips give engines with identical answers
+    blob = eng.pack()
+    clone = lb.FastWindingNumber.from_packed(blob)
+    assert np.array_equal(clone.solid_angle(q), host)
+    dblob = torch.empty(eng.packed_size(), dtype=torch.uint8, device="cuda")
+    eng.pack(out=dblob)
+    clone2 = lb.FastWindingNumber.from_packed(dblob)
+    assert np.array_equal(clone2.solid_angle(q), host)
+    with pytest.raises(lb.Error, match="magic"):
+        lb.FastWindingNumber.from_packed(np.zeros(4096, np.uint8))
+
+
+def test_cpp_host_layer():
+    """The drop-in C++ class (include/lagrange/winding/FastWindingNumber.h) through the reference's benchmark protocol."""
+    import subprocess
+
+    from lagrange_b200 import build
+
+    build.build_all()
+    r = subprocess.run([build.CPP_TEST], capture_output=True, text=True, timeout=600)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0 and "ALL PASSED" in r.stdout
+
+
+# ---- full-size properties (BASELINE configs at their real sizes) ----------------------------------------------------------------
+def test_cfg1_full_size_against_the_oracle(lb, oracle_mod, prim):
+    V, F = prim.config_mesh(1)
+    _, lattice = prim.config_queries(1, V, F)
+    ref = oracle_mod.RefEngine(V, F)
+    eng_ref_tree = lb.FastWindingNumber(V, F, topology=ref.topology())
+    eng = lb.FastWindingNumber(V, F)
+    ins_ref, om_ref = ref.grid(*lattice, want_omega=True)
+    om_t, ins_t = eng_ref_tree.query_grid(*lattice, want_omega=True)
+    assert np.abs(om_t - om_ref).max() < TOL_OMEGA
+    m = band_mask(om_ref / FOUR_PI)
+    assert np.array_equal(ins_t[m], ins_ref[m])
+    om_l, ins_l = eng.query_grid(*lattice, want_omega=True)
+    mismatch = int((ins_l[m] != ins_ref[m]).sum())
+    assert mismatch <= 5, mismatch  # different tree: agreement is statistical near the surface
+    sub = slice(None, None, 97)
+    P = prim.lattice_points(*lattice)[sub]
+    ex = oracle_mod.exact64(V, F, P)
+    assert np.abs(om_l[sub] - ex).max() / FOUR_PI < 1.5e-2
+    assert np.abs(eng.exact_solid_angle(P) - ex).max() / FOUR_PI < 2e-5
+
+
+def test_cfg2_full_size_sphere_properties(lb, prim):
+    import torch
+
+    V, F = prim.config_mesh(2)
+    assert len(F) == 1310720
+    eng = lb.FastWindingNumber(V, F)
+    info = eng.info
+    assert info["num_entries"] == 2 * len(F) - 1 and info["build_ms"] > 0
+    kind, (o, s, d) = prim.config_queries(2, V, F)
+    # one 64-layer slab of the 512^3 lattice through the middle; results stay on the device
+    z0, z1 = 224, 288
+    ins = eng.query_grid(o, s, d, z_range=(z0, z1), device_output=True)[1].view(z1 - z0, 512, 512)
+    # analytic: the unit sphere. Points farther than one cell diagonal from the surface must be classified exactly.
+    ax = torch.tensor(o[0], device="cuda") + torch.tensor(s[0], device="cuda") * (torch.arange(512, device="cuda", dtype=torch.float32) + 0.5)
+    zz, yy, xx = torch.meshgrid(ax[z0:z1], ax, ax, indexing="ij")
+    rad = torch.sqrt(xx * xx + yy * yy + zz * zz)
+    clear = (rad - 1.0).abs() > 0.01
+    assert torch.equal(ins.bool()[clear], (rad < 1.0)[clear])
+    # symmetry of the lattice and of the icosphere under the central inversion z -> -z of this slab
+    assert (ins != ins.flip(0)).float().mean() < 1e-4
