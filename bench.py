@@ -325,7 +325,7 @@ def main():
         "peak_source": "live FMA microbenchmark k_fma_peak (MEASURED_PEAKS.json has no FP32 CUDA-core figure)",
         "flops_per_query": flops_per_query, "tests_per_query": stats["node_tests"] / stats["queries"],
         "evals_per_query": stats["far_field_evals"] / stats["queries"], "exact_tris_per_query": stats["exact_triangles"] / stats["queries"],
-        "lane_utilisation": stats["node_tests"] / max(1, 32 * stats["warp_node_visits"]),
+        "lane_utilisation": stats["node_tests"] / max(1, stats["lane_slots"]),
         "traffic": None,
         "hbm": {"achieved_gbs": algo_bytes / (ms_local * 1e-3) / 1e9, "peak_gbs": hbm_peak, "peak_source": hbm_src,
                 "frac": algo_bytes / (ms_local * 1e-3) / 1e9 / hbm_peak},

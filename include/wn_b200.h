@@ -97,7 +97,8 @@ typedef struct wn_query_stats {
     uint64_t node_tests;
     uint64_t far_field_evals;
     uint64_t exact_triangles;
-    uint64_t warp_node_visits;   /* nodes a warp stepped through (divergence = 32 * visits / node_tests) */
+    uint64_t lane_slots;         /* (lane, query) slots the warps stepped through = 32 * QPL per visited record;
+                                    lane utilisation of the traversal = node_tests / lane_slots */
 } wn_query_stats;
 
 WN_API const char* wn_last_error(void);

@@ -43,7 +43,7 @@ class wn_info(ctypes.Structure):
 
 class wn_query_stats(ctypes.Structure):
     _fields_ = [("node_tests", ctypes.c_uint64), ("far_field_evals", ctypes.c_uint64), ("exact_triangles", ctypes.c_uint64),
-                ("warp_node_visits", ctypes.c_uint64)]
+                ("lane_slots", ctypes.c_uint64)]
 
 
 _vp = ctypes.c_void_p

@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(kBuildThreads) k_centroid_bounds(const float* 
         }
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            const float c = (v[3 * (int64_t)i0 + a] + v[3 * (int64_t)i1 + a] + v[3 * (int64_t)i2 + a]) * (1.0f / 3.0f);
+            const float c = wn_centroid_coord(v[3 * (int64_t)i0 + a], v[3 * (int64_t)i1 + a], v[3 * (int64_t)i2 + a]);
             if (c == c) { // ignore NaN centroids
                 lo[a] = fminf(lo[a], c);
                 hi[a] = fmaxf(hi[a], c);
@@ -84,14 +84,14 @@ __global__ void __launch_bounds__(kBuildThreads) k_morton(const float* __restric
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nT) return;
     const float lx = ordered_to_float(bounds[0]), ly = ordered_to_float(bounds[1]), lz = ordered_to_float(bounds[2]);
-    const float ex = ordered_to_float(bounds[3]) - lx, ey = ordered_to_float(bounds[4]) - ly, ez = ordered_to_float(bounds[5]) - lz;
+    const float ex = WN_SUB(ordered_to_float(bounds[3]), lx), ey = WN_SUB(ordered_to_float(bounds[4]), ly), ez = WN_SUB(ordered_to_float(bounds[5]), lz);
     const float ext = fmaxf(ex, fmaxf(ey, ez)); // cubic cells: one scale for all axes
-    const float inv = ext > 0.0f ? 1.0f / ext : 0.0f;
+    const float inv = ext > 0.0f ? WN_DIV(1.0f, ext) : 0.0f;
     const int i0 = tri[3 * (int64_t)t], i1 = tri[3 * (int64_t)t + 1], i2 = tri[3 * (int64_t)t + 2];
-    const float cx = (v[3 * (int64_t)i0] + v[3 * (int64_t)i1] + v[3 * (int64_t)i2]) * (1.0f / 3.0f);
-    const float cy = (v[3 * (int64_t)i0 + 1] + v[3 * (int64_t)i1 + 1] + v[3 * (int64_t)i2 + 1]) * (1.0f / 3.0f);
-    const float cz = (v[3 * (int64_t)i0 + 2] + v[3 * (int64_t)i1 + 2] + v[3 * (int64_t)i2 + 2]) * (1.0f / 3.0f);
-    keys[t] = (K)wn_morton((cx - lx) * inv, (cy - ly) * inv, (cz - lz) * inv, bits_per_axis);
+    const float cx = wn_centroid_coord(v[3 * (int64_t)i0], v[3 * (int64_t)i1], v[3 * (int64_t)i2]);
+    const float cy = wn_centroid_coord(v[3 * (int64_t)i0 + 1], v[3 * (int64_t)i1 + 1], v[3 * (int64_t)i2 + 1]);
+    const float cz = wn_centroid_coord(v[3 * (int64_t)i0 + 2], v[3 * (int64_t)i1 + 2], v[3 * (int64_t)i2 + 2]);
+    keys[t] = (K)wn_morton(wn_unit_coord(cx, lx, inv), wn_unit_coord(cy, ly, inv), wn_unit_coord(cz, lz, inv), bits_per_axis);
     vals[t] = (unsigned)t;
 }
 

@@ -712,7 +712,7 @@ wn_status points_impl(const wn_engine* e, const float* q_xyz, int64_t n, float b
         stats->node_tests = h[0];
         stats->far_field_evals = h[1];
         stats->exact_triangles = h[2];
-        stats->warp_node_visits = h[3];
+        stats->lane_slots = h[3];
     }
     return finish_outputs(n, ob, st);
 }
@@ -787,7 +787,7 @@ wn_status grid_impl(const wn_engine* e, const float* origin, const float* spacin
         stats->node_tests = h[0];
         stats->far_field_evals = h[1];
         stats->exact_triangles = h[2];
-        stats->warp_node_visits = h[3];
+        stats->lane_slots = h[3];
     }
     return finish_outputs(n, ob, st);
 }

@@ -163,14 +163,26 @@ WN_HD uint32_t wn_expand_bits10(uint32_t v)
     v = (v | (v << 2)) & 0x09249249u;
     return v;
 }
+// One coordinate of a triangle centroid / its position in the unit cube of the scene bounds. Unfused on purpose: nvcc
+// would otherwise contract (sum * 1/3) - lo into one FMA and the device's Morton order would differ from the host
+// emulation's in the last bit.
+WN_HD float wn_centroid_coord(float a, float b, float c)
+{
+    return WN_MUL(WN_ADD(WN_ADD(a, b), c), 1.0f / 3.0f);
+}
+WN_HD float wn_unit_coord(float c, float lo, float inv_extent)
+{
+    return WN_MUL(WN_SUB(c, lo), inv_extent);
+}
+
 // p is already normalised to [0,1)^3 (clamped here). bits per axis = 21 (63-bit code) or 10 (30-bit code).
 WN_HD uint64_t wn_morton(float px, float py, float pz, int bits_per_axis)
 {
     const float scale = bits_per_axis == 21 ? 2097152.0f : 1024.0f;
     const float hi = scale - 1.0f;
-    float fx = wn_min(wn_max(px * scale, 0.0f), hi);
-    float fy = wn_min(wn_max(py * scale, 0.0f), hi);
-    float fz = wn_min(wn_max(pz * scale, 0.0f), hi);
+    float fx = wn_min(wn_max(WN_MUL(px, scale), 0.0f), hi);
+    float fy = wn_min(wn_max(WN_MUL(py, scale), 0.0f), hi);
+    float fz = wn_min(wn_max(WN_MUL(pz, scale), 0.0f), hi);
     // NaN -> 0 (comparisons above are false for NaN: wn_max returns b = 0 when a is NaN)
     const uint32_t ix = (uint32_t)fx, iy = (uint32_t)fy, iz = (uint32_t)fz;
     if (bits_per_axis == 21) return (wn_expand_bits21(ix) << 2) | (wn_expand_bits21(iy) << 1) | wn_expand_bits21(iz);
@@ -592,9 +604,9 @@ WN_HD float wn_traverse_point(const WnTreeView& t, float qx, float qy, float qz,
     while (i < t.n_entries) {
         const float4 f0 = t.rec[0][i];
         const bool leaf = wn_float_as_int(f0.w) < 0;
-        const float thr = beta2 * fabsf(f0.w);
+        const float thr = WN_MUL(fabsf(f0.w), beta2);
         const float rx = qx - f0.x, ry = qy - f0.y, rz = qz - f0.z;
-        const float l2 = rx * rx + ry * ry + rz * rz;
+        const float l2 = WN_ADD(WN_ADD(WN_MUL(rx, rx), WN_MUL(ry, ry)), WN_MUL(rz, rz)); // unfused, like the reference
         bool near = l2 <= thr;
         if (cnt) cnt[0]++;
         if (!near) {

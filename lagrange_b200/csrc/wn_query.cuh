@@ -48,7 +48,7 @@ struct QueryArgs
     // outputs (either may be null)
     float* out_omega;
     uint8_t* out_inside;
-    unsigned long long* stats; // [4] tests, approx, exact, warp visits
+    unsigned long long* stats; // [4] tests, approx, exact, lane slots
 };
 
 template <int QPL, bool GRID, bool STATS>
@@ -128,7 +128,10 @@ __global__ void __launch_bounds__(kQueryThreads) k_query(const QueryArgs a)
         const float4 f0 = __ldg(r0 + i);
         const int lk = __ldg(link + i);
         const bool leaf = __float_as_int(f0.w) < 0;
-        const float thr = a.beta2 * fabsf(f0.w);
+        // The accept/descend decision is formed exactly like the reference forms it (unfused |r|^2 <= R^2 * beta^2,
+        // SURVEY.md A.5), so a point takes the same branch at every node as in the CPU algorithm: a decision flipped by
+        // an FMA's single rounding would change Omega by that node's whole truncation error (~1e-4 * 4 pi at beta = 2).
+        const float thr = __fmul_rn(fabsf(f0.w), a.beta2);
         float rx[QPL], ry[QPL], rz[QPL], l2[QPL];
         bool nearq[QPL], farq[QPL];
         bool anyfar = false;
@@ -138,14 +141,14 @@ __global__ void __launch_bounds__(kQueryThreads) k_query(const QueryArgs a)
             rx[k] = qx[k] - f0.x;
             ry[k] = qy[k] - f0.y;
             rz[k] = qz[k] - f0.z;
-            l2[k] = rx[k] * rx[k] + ry[k] * ry[k] + rz[k] * rz[k];
+            l2[k] = __fadd_rn(__fadd_rn(__fmul_rn(rx[k], rx[k]), __fmul_rn(ry[k], ry[k])), __fmul_rn(rz[k], rz[k]));
             const bool nr = l2[k] <= thr;
             nearq[k] = active && nr;
             farq[k] = active && !nr;
             anyfar |= farq[k];
             if (STATS) cT += active ? 1 : 0;
         }
-        if (STATS) cV += (lane == 0) ? 1 : 0;
+        if (STATS) cV += (lane == 0) ? 32 * QPL : 0;
         if (__any_sync(kFull, anyfar)) {
             const float4 f1 = __ldg(r1 + i), f2 = __ldg(r2 + i), f3 = __ldg(r3 + i), f4 = __ldg(r4 + i), f5 = __ldg(r5 + i);
             const int after = leaf ? i + 1 : lk;

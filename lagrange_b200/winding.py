@@ -290,8 +290,8 @@ class FastWindingNumber:
 
     @staticmethod
     def _stats_dict(st, n):
-        T, A, E, V = st.node_tests, st.far_field_evals, st.exact_triangles, st.warp_node_visits
-        return {"queries": n, "node_tests": T, "far_field_evals": A, "exact_triangles": E, "warp_node_visits": V,
+        T, A, E, V = st.node_tests, st.far_field_evals, st.exact_triangles, st.lane_slots
+        return {"queries": n, "node_tests": T, "far_field_evals": A, "exact_triangles": E, "lane_slots": V,
                 # 10 flop per test, 83 more per accepted far-field evaluation, 75 per exact triangle
                 "algorithmic_flops": 10 * T + 83 * A + 75 * E}
 

@@ -59,7 +59,7 @@ void* emul_build(const float* v, int64_t nV, const int32_t* tri, int64_t nT, con
         std::vector<float> cen(nT * 3);
         for (int64_t t = 0; t < nT; ++t)
             for (int a = 0; a < 3; ++a) {
-                const float c = (v[3 * tri[3 * t] + a] + v[3 * tri[3 * t + 1] + a] + v[3 * tri[3 * t + 2] + a]) * (1.0f / 3.0f);
+                const float c = wn_centroid_coord(v[3 * tri[3 * t] + a], v[3 * tri[3 * t + 1] + a], v[3 * tri[3 * t + 2] + a]);
                 cen[3 * t + a] = c;
                 if (c == c) {
                     lo[a] = std::min(lo[a], c);
@@ -71,7 +71,8 @@ void* emul_build(const float* v, int64_t nV, const int32_t* tri, int64_t nT, con
         std::vector<uint64_t> keys(nT);
         const int bpa = morton_bits == 63 ? 21 : 10;
         for (int64_t t = 0; t < nT; ++t)
-            keys[t] = wn_morton((cen[3 * t] - lo[0]) * inv, (cen[3 * t + 1] - lo[1]) * inv, (cen[3 * t + 2] - lo[2]) * inv, bpa);
+            keys[t] = wn_morton(wn_unit_coord(cen[3 * t], lo[0], inv), wn_unit_coord(cen[3 * t + 1], lo[1], inv),
+                                wn_unit_coord(cen[3 * t + 2], lo[2], inv), bpa);
         // K2: stable sort by key (what a stable LSD radix sort produces)
         std::vector<unsigned> idx(nT);
         std::iota(idx.begin(), idx.end(), 0u);
