@@ -91,8 +91,12 @@ typedef struct wn_info {
     int32_t order;
 } wn_info;
 
-/* Totals over one batch of queries; they define the algorithmic flops of a tree query:
- * flops = 10 * node_tests + 83 * far_field_evals + 75 * exact_triangles. */
+/* Work EXECUTED by one batch of tree queries, in the units of SURVEY.md section 8(d):
+ * flops = 10 * node_tests + 83 * far_field_evals + 75 * exact_triangles.
+ * With WN_QUERY_NO_TILING these are the per-point counts of the reference algorithm (every point tests / expands /
+ * descends exactly like UT_SolidAngle::computeSolidAngle does on the same tree). The tiled path accepts the same
+ * records per point but executes less: records that are far for a whole tile are evaluated at 64 sample points per
+ * tile (counted in far_field_evals) and records that are near for a whole tile are not tested at all. */
 typedef struct wn_query_stats {
     uint64_t node_tests;
     uint64_t far_field_evals;
@@ -130,6 +134,7 @@ WN_API wn_status wn_get_info(const wn_engine* e, wn_info* info);
  * beta <= 0 selects the engine default. `flags`: see WN_QUERY_*. */
 #define WN_QUERY_DEFAULT 0u
 #define WN_QUERY_PRESORTED 1u /* points are already spatially coherent: skip the Morton sort of the queries (K9) */
+#define WN_QUERY_NO_TILING 2u /* always run the generic per-point traversal (no tile plan, no far-field interpolation) */
 
 /* out_omega[i] = solid angle at q_i, in (-4pi k, 4pi k): what FastWindingNumber::solid_angle returns (:69-76). */
 WN_API wn_status wn_solid_angle(const wn_engine* e, const float* q_xyz, int64_t n, float beta, uint32_t flags,
@@ -143,13 +148,14 @@ WN_API wn_status wn_is_inside(const wn_engine* e, const float* q_xyz, int64_t n,
  * Only the z-slab [z_begin, z_end) is evaluated (multi-GPU sharding); the output holds dims[0]*dims[1]*(z_end-z_begin)
  * values starting at the slab's first point. Either output may be NULL (not both). */
 WN_API wn_status wn_query_grid(const wn_engine* e, const float origin[3], const float spacing[3], const int64_t dims[3],
-                               int64_t z_begin, int64_t z_end, float beta, float* out_omega, uint8_t* out_inside, void* stream);
+                               int64_t z_begin, int64_t z_end, float beta, uint32_t flags, float* out_omega, uint8_t* out_inside,
+                               void* stream);
 
 /* Counters of the traversal for a batch of points (same traversal as wn_solid_angle, results discarded). */
 WN_API wn_status wn_query_stats_points(const wn_engine* e, const float* q_xyz, int64_t n, float beta, uint32_t flags,
                                        wn_query_stats* stats, void* stream);
 WN_API wn_status wn_query_stats_grid(const wn_engine* e, const float origin[3], const float spacing[3], const int64_t dims[3],
-                                     int64_t z_begin, int64_t z_end, float beta, wn_query_stats* stats, void* stream);
+                                     int64_t z_begin, int64_t z_end, float beta, uint32_t flags, wn_query_stats* stats, void* stream);
 
 /* ---- exact brute-force mode (K7) ----------------------------------------------------------------------------
  * Sum of exact Van Oosterom-Strackee triangle solid angles over ALL triangles (UTsignedSolidAngleTri):

@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libwn_b200.so")
 WN_OK = 0
 WN_QUERY_DEFAULT = 0
 WN_QUERY_PRESORTED = 1
+WN_QUERY_NO_TILING = 2
 WN_RADIUS_BOX_CORNER = 0
 WN_RADIUS_VERTEX = 1
 
@@ -65,9 +66,9 @@ SIGNATURES = {
     "wn_get_info": (ctypes.c_int, [_vp, ctypes.POINTER(wn_info)]),
     "wn_solid_angle": (ctypes.c_int, [_vp, _vp, _i64, _f, _u32, _vp, _vp]),
     "wn_is_inside": (ctypes.c_int, [_vp, _vp, _i64, _f, _u32, _vp, _vp]),
-    "wn_query_grid": (ctypes.c_int, [_vp, _f3, _f3, _l3, _i64, _i64, _f, _vp, _vp, _vp]),
+    "wn_query_grid": (ctypes.c_int, [_vp, _f3, _f3, _l3, _i64, _i64, _f, _u32, _vp, _vp, _vp]),
     "wn_query_stats_points": (ctypes.c_int, [_vp, _vp, _i64, _f, _u32, ctypes.POINTER(wn_query_stats), _vp]),
-    "wn_query_stats_grid": (ctypes.c_int, [_vp, _f3, _f3, _l3, _i64, _i64, _f, ctypes.POINTER(wn_query_stats), _vp]),
+    "wn_query_stats_grid": (ctypes.c_int, [_vp, _f3, _f3, _l3, _i64, _i64, _f, _u32, ctypes.POINTER(wn_query_stats), _vp]),
     "wn_exact": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "wn_exact_grid": (ctypes.c_int, [_vp, _f3, _f3, _l3, _i64, _i64, _vp, _vp, _vp]),
     "wn_tree_packed_size": (ctypes.c_int, [_vp, ctypes.POINTER(_i64)]),

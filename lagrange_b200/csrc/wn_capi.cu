@@ -187,7 +187,7 @@ struct wn_engine
     int kept_nI = 0, kept_nL = 0, kept_W = 0;
     // per-engine query scratch, guarded by mu
     mutable std::mutex mu;
-    mutable DevBuf s_in, s_out_f, s_out_b, s_sort, s_stats, s_partial;
+    mutable DevBuf s_in, s_out_f, s_out_b, s_sort, s_stats, s_partial, s_plan_hdr, s_plan_items, s_plan_samples;
     mutable PinnedBuf p_small;
 };
 
@@ -640,6 +640,96 @@ int pick_qpl(int64_t n)
     return n >= (1 << 20) ? 2 : 1;
 }
 
+// The tiled path (k_tile_plan + k_tile_query) pays off when a tile's 512 queries are spatial neighbours: lattices
+// always, point sets when they are Morton-sorted (by us) or declared presorted by the caller.
+bool want_tiling(const wn_engine* e, int64_t n, uint32_t flags, bool coherent)
+{
+    const int forced = env_int("WN_TILE", -1);
+    if (forced == 0 || (flags & WN_QUERY_NO_TILING) || e->view.n_entries <= 1 || !coherent) return false;
+    return forced == 1 || n >= env_int("WN_TILE_MIN", 1 << 15);
+}
+
+float tile_kappa()
+{
+    const char* s = getenv("WN_KAPPA");
+    const float k = s && *s ? (float)atof(s) : 4.0f;
+    return k >= 1.5f ? k : 1.5f;
+}
+
+// Runs one batch of queries described by `a` (grid or points), generic or tiled, with optional executed-work counters.
+// grid_layers = z1 - z0 for lattices; ignored for points.
+template <bool GRID>
+wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_t grid_layers, bool tiled, wn_query_stats* stats,
+                         cudaStream_t st)
+{
+    if (stats) {
+        WN_CUDA(e->s_stats.reserve(4 * sizeof(unsigned long long)));
+        WN_CUDA(cudaMemsetAsync(e->s_stats.p, 0, 4 * sizeof(unsigned long long), st));
+        a.stats = (unsigned long long*)e->s_stats.p;
+    }
+    if (!tiled) {
+        const int qpl = pick_qpl(n);
+        int64_t blocks64;
+        if (GRID) {
+            const int tz = (int)((grid_layers + 4 * qpl - 1) / (4 * qpl));
+            blocks64 = (int64_t)a.tiles_x * a.tiles_y * tz;
+        } else {
+            const int per_block = wn::kQueryWarps * 32 * qpl;
+            blocks64 = (n + per_block - 1) / per_block;
+        }
+        if (blocks64 > INT_MAX) return fail(WN_ERR_UNSUPPORTED, "batch too large for one launch; split it");
+        if (stats)
+            launch_query<GRID, true>(qpl, (int)blocks64, a, st);
+        else
+            launch_query<GRID, false>(qpl, (int)blocks64, a, st);
+    } else {
+        // batches of tiles so that the plan scratch (16.7 KB per tile) stays around 1 GB
+        const int64_t max_tiles = std::max(1, env_int("WN_TILE_BATCH", 1 << 16));
+        int64_t units, tiles_per_unit; // grid: unit = one z layer of tiles; points: unit = one tile
+        if (GRID) {
+            units = (grid_layers + 7) / 8;
+            tiles_per_unit = (int64_t)a.tiles_x * a.tiles_y;
+        } else {
+            units = (n + wn::kTileQueries - 1) / wn::kTileQueries;
+            tiles_per_unit = 1;
+        }
+        const int64_t units_per_launch = std::max<int64_t>(1, max_tiles / tiles_per_unit);
+        const int64_t launch_tiles = std::min(units, units_per_launch) * tiles_per_unit;
+        if (launch_tiles > INT_MAX / 2 || launch_tiles * (int64_t)wn::kTileItemCap * 8 > ((int64_t)8 << 30))
+            return fail(WN_ERR_UNSUPPORTED, "lattice layer too large for the tiled path; pass WN_QUERY_NO_TILING or split it");
+        WN_CUDA(e->s_plan_hdr.reserve((size_t)launch_tiles * sizeof(wn::TileHeader)));
+        WN_CUDA(e->s_plan_items.reserve((size_t)launch_tiles * wn::kTileItemCap * sizeof(int2)));
+        WN_CUDA(e->s_plan_samples.reserve((size_t)launch_tiles * wn::kTileSampleStride * sizeof(float)));
+        a.plan_hdr = (wn::TileHeader*)e->s_plan_hdr.p;
+        a.plan_items = (int2*)e->s_plan_items.p;
+        a.plan_samples = (float*)e->s_plan_samples.p;
+        a.kappa = tile_kappa();
+        for (int64_t u0 = 0; u0 < units; u0 += units_per_launch) {
+            const int blocks = (int)(std::min(units_per_launch, units - u0) * tiles_per_unit);
+            if (GRID)
+                a.tile_z0 = (int)u0;
+            else
+                a.tile_base = u0;
+            wn::k_tile_plan<GRID><<<blocks, wn::kQueryThreads, 0, st>>>(a);
+            if (stats)
+                wn::k_tile_query<GRID, true><<<blocks, wn::kQueryThreads, 0, st>>>(a);
+            else
+                wn::k_tile_query<GRID, false><<<blocks, wn::kQueryThreads, 0, st>>>(a);
+        }
+    }
+    WN_CUDA(cudaGetLastError());
+    if (stats) {
+        unsigned long long h[4];
+        WN_CUDA(cudaMemcpyAsync(h, e->s_stats.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+        WN_CUDA(cudaStreamSynchronize(st));
+        stats->node_tests = h[0];
+        stats->far_field_evals = h[1];
+        stats->exact_triangles = h[2];
+        stats->lane_slots = h[3];
+    }
+    return WN_OK;
+}
+
 wn_status points_impl(const wn_engine* e, const float* q_xyz, int64_t n, float beta, uint32_t flags, float* out_omega,
                       uint8_t* out_inside, wn_query_stats* stats, void* stream)
 {
@@ -693,27 +783,9 @@ wn_status points_impl(const wn_engine* e, const float* q_xyz, int64_t n, float b
     a.q_aligned16 = (((uintptr_t)d_q) & 15) == 0;
     a.out_omega = ob.d_omega;
     a.out_inside = ob.d_inside;
-    const int qpl = pick_qpl(n);
-    const int per_block = (wn::kQueryThreads / 32) * 32 * qpl;
-    const int blocks = (int)((n + per_block - 1) / per_block);
-    if (stats) {
-        WN_CUDA(e->s_stats.reserve(4 * sizeof(unsigned long long)));
-        WN_CUDA(cudaMemsetAsync(e->s_stats.p, 0, 4 * sizeof(unsigned long long), st));
-        a.stats = (unsigned long long*)e->s_stats.p;
-        launch_query<false, true>(qpl, blocks, a, st);
-    } else {
-        launch_query<false, false>(qpl, blocks, a, st);
-    }
-    WN_CUDA(cudaGetLastError());
-    if (stats) {
-        unsigned long long h[4];
-        WN_CUDA(cudaMemcpyAsync(h, e->s_stats.p, sizeof(h), cudaMemcpyDeviceToHost, st));
-        WN_CUDA(cudaStreamSynchronize(st));
-        stats->node_tests = h[0];
-        stats->far_field_evals = h[1];
-        stats->exact_triangles = h[2];
-        stats->lane_slots = h[3];
-    }
+    const bool coherent = perm != nullptr || (flags & WN_QUERY_PRESORTED) != 0;
+    s = dispatch_query<false>(e, a, n, 0, want_tiling(e, n, flags, coherent), stats, st);
+    if (s != WN_OK) return s;
     return finish_outputs(n, ob, st);
 }
 
@@ -739,7 +811,7 @@ wn_status check_grid(const float* origin, const float* spacing, const int64_t* d
 }
 
 wn_status grid_impl(const wn_engine* e, const float* origin, const float* spacing, const int64_t* dims, int64_t z0, int64_t z1, float beta,
-                    float* out_omega, uint8_t* out_inside, wn_query_stats* stats, void* stream)
+                    uint32_t flags, float* out_omega, uint8_t* out_inside, wn_query_stats* stats, void* stream)
 {
     if (!e) return fail(WN_ERR_INVALID_ARGUMENT, "engine is null");
     if (!out_omega && !out_inside && !stats) return fail(WN_ERR_INVALID_ARGUMENT, "no output requested");
@@ -764,31 +836,10 @@ wn_status grid_impl(const wn_engine* e, const float* origin, const float* spacin
     a.g = g;
     a.out_omega = ob.d_omega;
     a.out_inside = ob.d_inside;
-    const int qpl = pick_qpl(n);
     a.tiles_x = (g.nx + 7) / 8;
     a.tiles_y = (g.ny + 7) / 8;
-    const int tz = (int)((z1 - z0 + 4 * qpl - 1) / (4 * qpl));
-    const int64_t blocks64 = (int64_t)a.tiles_x * a.tiles_y * tz;
-    if (blocks64 > INT_MAX) return fail(WN_ERR_UNSUPPORTED, "grid slab too large for one launch; split the z range");
-    const int blocks = (int)blocks64;
-    if (stats) {
-        WN_CUDA(e->s_stats.reserve(4 * sizeof(unsigned long long)));
-        WN_CUDA(cudaMemsetAsync(e->s_stats.p, 0, 4 * sizeof(unsigned long long), st));
-        a.stats = (unsigned long long*)e->s_stats.p;
-        launch_query<true, true>(qpl, blocks, a, st);
-    } else {
-        launch_query<true, false>(qpl, blocks, a, st);
-    }
-    WN_CUDA(cudaGetLastError());
-    if (stats) {
-        unsigned long long h[4];
-        WN_CUDA(cudaMemcpyAsync(h, e->s_stats.p, sizeof(h), cudaMemcpyDeviceToHost, st));
-        WN_CUDA(cudaStreamSynchronize(st));
-        stats->node_tests = h[0];
-        stats->far_field_evals = h[1];
-        stats->exact_triangles = h[2];
-        stats->lane_slots = h[3];
-    }
+    s = dispatch_query<true>(e, a, n, z1 - z0, want_tiling(e, n, flags, true), stats, st);
+    if (s != WN_OK) return s;
     return finish_outputs(n, ob, st);
 }
 
@@ -942,6 +993,9 @@ wn_status wn_destroy(wn_engine* e)
         e->s_sort.release();
         e->s_stats.release();
         e->s_partial.release();
+        e->s_plan_hdr.release();
+        e->s_plan_items.release();
+        e->s_plan_samples.release();
         e->p_small.release();
     }
     delete e;
@@ -968,9 +1022,9 @@ wn_status wn_is_inside(const wn_engine* e, const float* q_xyz, int64_t n, float 
 }
 
 wn_status wn_query_grid(const wn_engine* e, const float origin[3], const float spacing[3], const int64_t dims[3], int64_t z_begin,
-                        int64_t z_end, float beta, float* out_omega, uint8_t* out_inside, void* stream)
+                        int64_t z_end, float beta, uint32_t flags, float* out_omega, uint8_t* out_inside, void* stream)
 {
-    return grid_impl(e, origin, spacing, dims, z_begin, z_end, beta, out_omega, out_inside, nullptr, stream);
+    return grid_impl(e, origin, spacing, dims, z_begin, z_end, beta, flags, out_omega, out_inside, nullptr, stream);
 }
 
 wn_status wn_query_stats_points(const wn_engine* e, const float* q_xyz, int64_t n, float beta, uint32_t flags, wn_query_stats* stats, void* stream)
@@ -980,10 +1034,10 @@ wn_status wn_query_stats_points(const wn_engine* e, const float* q_xyz, int64_t 
 }
 
 wn_status wn_query_stats_grid(const wn_engine* e, const float origin[3], const float spacing[3], const int64_t dims[3], int64_t z_begin,
-                              int64_t z_end, float beta, wn_query_stats* stats, void* stream)
+                              int64_t z_end, float beta, uint32_t flags, wn_query_stats* stats, void* stream)
 {
     if (!stats) return fail(WN_ERR_INVALID_ARGUMENT, "stats is null");
-    return grid_impl(e, origin, spacing, dims, z_begin, z_end, beta, nullptr, nullptr, stats, stream);
+    return grid_impl(e, origin, spacing, dims, z_begin, z_end, beta, flags, nullptr, nullptr, stats, stream);
 }
 
 wn_status wn_exact(const wn_engine* e, const float* q_xyz, int64_t n, float* out_omega, uint8_t* out_inside, void* stream)

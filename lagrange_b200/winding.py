@@ -191,21 +191,25 @@ class FastWindingNumber:
         n = 1 if single else shape[0]
         return buf, n, single
 
-    def solid_angle(self, pos, accuracy_scale=None, presorted=False, out=None):
+    @staticmethod
+    def _flags(presorted=False, tiling=True):
+        return (_capi.WN_QUERY_PRESORTED if presorted else 0) | (0 if tiling else _capi.WN_QUERY_NO_TILING)
+
+    def solid_angle(self, pos, accuracy_scale=None, presorted=False, out=None, tiling=True):
         """Solid angle at the query point(s). ``pos``: (3,) -> float, or (n,3) -> float32 array (numpy or torch CUDA)."""
         buf, n, single = self._points(pos)
         res = _alloc_like(buf, n, np.float32) if out is None else out
         ob = _Buf(res, np.float32, writable=True)
-        flags = _capi.WN_QUERY_PRESORTED if presorted else 0
+        flags = self._flags(presorted, tiling)
         self._check(self._lib.wn_solid_angle(self._handle(), buf.ptr, n, float(accuracy_scale or 0.0), flags, ob.ptr, _current_stream_ptr()))
         return float(res[0]) if single else res
 
-    def is_inside(self, pos, accuracy_scale=None, presorted=False, out=None):
+    def is_inside(self, pos, accuracy_scale=None, presorted=False, out=None, tiling=True):
         """True iff (double)solid_angle / (4 pi) > 0.5 (FastWindingNumber.cpp:66). (3,) -> bool, (n,3) -> uint8 array."""
         buf, n, single = self._points(pos)
         res = _alloc_like(buf, n, np.uint8) if out is None else out
         ob = _Buf(res, np.uint8, writable=True)
-        flags = _capi.WN_QUERY_PRESORTED if presorted else 0
+        flags = self._flags(presorted, tiling)
         self._check(self._lib.wn_is_inside(self._handle(), buf.ptr, n, float(accuracy_scale or 0.0), flags, ob.ptr, _current_stream_ptr()))
         return bool(res[0]) if single else res
 
@@ -220,7 +224,7 @@ class FastWindingNumber:
         return o, s, d, z0, z1, n
 
     def query_grid(self, origin, spacing, dims, z_range=None, accuracy_scale=None, want_omega=False, want_inside=True, device_output=False,
-                   out_omega=None, out_inside=None):
+                   out_omega=None, out_inside=None, tiling=True):
         """Evaluate the cell-centred lattice p = origin + spacing*(ijk+0.5), x fastest; returns (omega, inside) (None if not wanted).
 
         ``device_output`` allocates torch CUDA outputs (results stay in HBM); otherwise numpy (copied to the host)."""
@@ -239,7 +243,8 @@ class FastWindingNumber:
         ins = mk(np.uint8, out_inside, want_inside)
         pom = _Buf(om, np.float32, writable=True).ptr if om is not None else None
         pin = _Buf(ins, np.uint8, writable=True).ptr if ins is not None else None
-        self._check(self._lib.wn_query_grid(self._handle(), o, s, d, z0, z1, float(accuracy_scale or 0.0), pom, pin, _current_stream_ptr()))
+        self._check(self._lib.wn_query_grid(self._handle(), o, s, d, z0, z1, float(accuracy_scale or 0.0), self._flags(False, tiling), pom, pin,
+                                            _current_stream_ptr()))
         return om, ins
 
     def is_inside_grid(self, origin, spacing, dims, **kw):
@@ -273,19 +278,20 @@ class FastWindingNumber:
         return om, ins
 
     # -- counters ------------------------------------------------------------------------------------------------------
-    def query_stats(self, pos, accuracy_scale=None, presorted=False) -> dict:
+    def query_stats(self, pos, accuracy_scale=None, presorted=False, tiling=False) -> dict:
+        """Executed-work counters. tiling=False (default): the reference algorithm's per-point counts."""
         buf, n, _ = self._points(pos)
         st = _capi.wn_query_stats()
-        flags = _capi.WN_QUERY_PRESORTED if presorted else 0
+        flags = self._flags(presorted, tiling)
         self._check(self._lib.wn_query_stats_points(self._handle(), buf.ptr, n, float(accuracy_scale or 0.0), flags, ctypes.byref(st),
                                                     _current_stream_ptr()))
         return self._stats_dict(st, n)
 
-    def query_stats_grid(self, origin, spacing, dims, z_range=None, accuracy_scale=None) -> dict:
+    def query_stats_grid(self, origin, spacing, dims, z_range=None, accuracy_scale=None, tiling=False) -> dict:
         o, s, d, z0, z1, n = self._grid_args(origin, spacing, dims, z_range)
         st = _capi.wn_query_stats()
-        self._check(self._lib.wn_query_stats_grid(self._handle(), o, s, d, z0, z1, float(accuracy_scale or 0.0), ctypes.byref(st),
-                                                  _current_stream_ptr()))
+        self._check(self._lib.wn_query_stats_grid(self._handle(), o, s, d, z0, z1, float(accuracy_scale or 0.0), self._flags(False, tiling),
+                                                  ctypes.byref(st), _current_stream_ptr()))
         return self._stats_dict(st, n)
 
     @staticmethod

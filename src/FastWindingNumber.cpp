@@ -110,15 +110,15 @@ void FastWindingNumber::solid_angle(const float* xyz, size_t n, float* out) cons
 void FastWindingNumber::is_inside(const Lattice& l, uint8_t* out, int64_t z_begin, int64_t z_end) const
 {
     const wn_engine* e = engine();
-    check(wn_query_grid(e, l.origin.data(), l.spacing.data(), l.dims.data(), z_begin, z_end < 0 ? l.dims[2] : z_end, m_impl->beta, nullptr, out,
-                        nullptr));
+    check(wn_query_grid(e, l.origin.data(), l.spacing.data(), l.dims.data(), z_begin, z_end < 0 ? l.dims[2] : z_end, m_impl->beta, WN_QUERY_DEFAULT, nullptr,
+                        out, nullptr));
 }
 
 void FastWindingNumber::solid_angle(const Lattice& l, float* out, int64_t z_begin, int64_t z_end) const
 {
     const wn_engine* e = engine();
-    check(wn_query_grid(e, l.origin.data(), l.spacing.data(), l.dims.data(), z_begin, z_end < 0 ? l.dims[2] : z_end, m_impl->beta, out, nullptr,
-                        nullptr));
+    check(wn_query_grid(e, l.origin.data(), l.spacing.data(), l.dims.data(), z_begin, z_end < 0 ? l.dims[2] : z_end, m_impl->beta, WN_QUERY_DEFAULT, out,
+                        nullptr, nullptr));
 }
 
 void FastWindingNumber::exact_solid_angle(const float* xyz, size_t n, float* out) const

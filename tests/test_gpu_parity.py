@@ -82,8 +82,8 @@ def test_oracle_tree_mode_matches_the_reference_algorithm(lb, oracle_mod, prim, 
     assert np.array_equal(ins_gpu[m], ins_ref[m])
     assert np.mean(ins_gpu != ins_ref) < 1e-3
     if lattice is not None:
-        om_g, ins_g = eng.query_grid(*lattice, want_omega=True, want_inside=True)
-        assert np.array_equal(om_g, eng.solid_angle(q)) and np.array_equal(ins_g, ins_gpu)
+        om_g, ins_g = eng.query_grid(*lattice, want_omega=True, want_inside=True, tiling=False)
+        assert np.array_equal(om_g, eng.solid_angle(q, tiling=False)) and np.array_equal(ins_g, eng.is_inside(q, tiling=False))
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
@@ -152,27 +152,34 @@ def test_lbvh_options_match_host_emulation(lb, emul_mod, prim, opts):
 
 
 # ---- batching must not change per-point results ------------------------------------------------------------------------------
+TOL_TILE = 3e-5 * FOUR_PI  # far-field interpolation of the tiled path (measured ~1e-5 * 4 pi), on top of which nothing else moves
+
+
 def test_results_do_not_depend_on_batch_composition(lb, prim):
+    """Generic traversal: a point's result is bit-identical whatever else is in its warp / batch."""
     V, F = prim.generate_torus(5, 1, 60, 30)
     eng = lb.FastWindingNumber(V, F)
     q = prim.uniform_points_in_bbox(*prim.mesh_bbox(V), 50000, seed=11)
-    base = eng.solid_angle(q)  # Morton-sorted internally
-    assert np.array_equal(eng.solid_angle(q, presorted=True), base)  # original (incoherent) order, no sort
+    base = eng.solid_angle(q, tiling=False)  # Morton-sorted internally
+    assert np.array_equal(eng.solid_angle(q, presorted=True, tiling=False), base)  # original (incoherent) order, no sort
     perm = np.random.Generator(np.random.PCG64(1)).permutation(len(q))
-    assert np.array_equal(eng.solid_angle(q[perm])[np.argsort(perm)], base)
+    assert np.array_equal(eng.solid_angle(q[perm], tiling=False)[np.argsort(perm)], base)
     for i in (0, 17, 49999):  # the reference's single-point signature
         assert eng.solid_angle(q[i]) == base[i]
         assert eng.is_inside(q[i]) == bool(base[i] >= np.float32(6.2831854820251465))
-    assert np.array_equal(eng.solid_angle(q[:1000]), base[:1000])  # QPL=1 path vs QPL=2 path? (size dependent)
-    os.environ["WN_QPL"] = "1"
-    try:
-        assert np.array_equal(eng.solid_angle(q), base)
-    finally:
-        os.environ["WN_QPL"] = "2"
-    try:
-        assert np.array_equal(eng.solid_angle(q), base)
-    finally:
-        del os.environ["WN_QPL"]
+    assert np.array_equal(eng.solid_angle(q[:1000]), base[:1000])
+    for qpl in ("1", "2"):
+        os.environ["WN_QPL"] = qpl
+        try:
+            assert np.array_equal(eng.solid_angle(q, tiling=False), base)
+        finally:
+            del os.environ["WN_QPL"]
+    # tiled path (sorted points grouped in tiles of 512): same accepted records, far field interpolated per tile
+    tiled = eng.solid_angle(q)
+    assert np.abs(tiled - base).max() < TOL_TILE
+    assert np.array_equal(eng.is_inside(q), eng.is_inside(q, tiling=False)) or np.mean(eng.is_inside(q) != eng.is_inside(q, tiling=False)) < 1e-4
+    # a caller that lies about coherence still gets correct answers (tiles overflow and fall back)
+    assert np.abs(eng.solid_angle(q, presorted=True) - base).max() < TOL_TILE
 
 
 def test_grid_overload_equals_points_and_slabs_tile(lb, prim):
@@ -180,9 +187,9 @@ def test_grid_overload_equals_points_and_slabs_tile(lb, prim):
     eng = lb.FastWindingNumber(V, F)
     o, s, d = prim.lattice_for_bbox(*prim.mesh_bbox(V), (37, 11, 29))
     P = prim.lattice_points(o, s, d)
-    om, ins = eng.query_grid(o, s, d, want_omega=True, want_inside=True)
-    assert np.array_equal(om, eng.solid_angle(P)) and np.array_equal(ins, eng.is_inside(P))
-    parts = [eng.query_grid(o, s, d, z_range=(a, b), want_omega=True)[0] for a, b in ((0, 5), (5, 6), (6, 29))]
+    om, ins = eng.query_grid(o, s, d, want_omega=True, want_inside=True, tiling=False)
+    assert np.array_equal(om, eng.solid_angle(P, tiling=False)) and np.array_equal(ins, eng.is_inside(P, tiling=False))
+    parts = [eng.query_grid(o, s, d, z_range=(a, b), want_omega=True, tiling=False)[0] for a, b in ((0, 5), (5, 6), (6, 29))]
     assert np.array_equal(np.concatenate(parts), om)
     assert eng.query_grid(o, s, d, z_range=(4, 4))[1].size == 0
     ex_om, ex_ins = eng.exact_grid(o, s, d, want_omega=True, want_inside=True)
@@ -190,6 +197,81 @@ def test_grid_overload_equals_points_and_slabs_tile(lb, prim):
     st_g = eng.query_stats_grid(o, s, d)
     st_p = eng.query_stats(P)
     assert [st_g[k] for k in ("node_tests", "far_field_evals", "exact_triangles")] == [st_p[k] for k in ("node_tests", "far_field_evals", "exact_triangles")]
+    # tiled lattice: whole lattice and z-slabs (slab cuts move the tile boundaries)
+    os.environ["WN_TILE"] = "1"
+    try:
+        om_t, ins_t = eng.query_grid(o, s, d, want_omega=True, want_inside=True)
+        assert np.abs(om_t - om).max() < TOL_TILE
+        parts = [eng.query_grid(o, s, d, z_range=(a, b), want_omega=True)[0] for a, b in ((0, 5), (5, 6), (6, 29))]
+        assert np.abs(np.concatenate(parts) - om).max() < TOL_TILE
+        m = band_mask(om / FOUR_PI)
+        assert np.array_equal(ins_t[m], ins[m])
+        st_t = eng.query_stats_grid(o, s, d, tiling=True)
+        assert st_t["far_field_evals"] < st_g["far_field_evals"] and st_t["node_tests"] < st_g["node_tests"]
+        assert st_t["exact_triangles"] == st_g["exact_triangles"]  # near field is untouched by the tiling
+    finally:
+        del os.environ["WN_TILE"]
+
+
+@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("tree", ["lbvh", "oracle", "lbvh_leaf8"])
+def test_tiled_path_matches_generic_traversal(lb, oracle_mod, prim, cfg, tree):
+    """The tile plan may only change where the far field is summed, never which records a point accepts."""
+    V, F, q, lattice = small_config(prim, cfg)
+    if tree == "oracle":
+        eng = lb.FastWindingNumber(V, F, topology=oracle_mod.RefEngine(V, F).topology())
+    else:
+        eng = lb.FastWindingNumber(V, F, leaf_size=8 if tree == "lbvh_leaf8" else 1)
+    os.environ["WN_TILE"] = "1"
+    try:
+        for beta in (2.0, 3.5):
+            if lattice is not None:
+                ref_om, ref_in = eng.query_grid(*lattice, want_omega=True, accuracy_scale=beta, tiling=False)
+                om, ins = eng.query_grid(*lattice, want_omega=True, accuracy_scale=beta)
+            else:
+                ref_om, ref_in = eng.solid_angle(q, accuracy_scale=beta, tiling=False), eng.is_inside(q, accuracy_scale=beta, tiling=False)
+                om, ins = eng.solid_angle(q, accuracy_scale=beta), eng.is_inside(q, accuracy_scale=beta)
+            assert np.abs(om - ref_om).max() < TOL_TILE, np.abs(om - ref_om).max() / FOUR_PI
+            m = band_mask(ref_om / FOUR_PI, band=1e-4)
+            assert np.array_equal(ins[m], ref_in[m])
+        for kappa in ("2", "16"):  # far-set distance criterion: accuracy must hold across the useful range
+            os.environ["WN_KAPPA"] = kappa
+            try:
+                om = eng.query_grid(*lattice, want_omega=True)[0] if lattice is not None else eng.solid_angle(q)
+                ref = eng.query_grid(*lattice, want_omega=True, tiling=False)[0] if lattice is not None else eng.solid_angle(q, tiling=False)
+                assert np.abs(om - ref).max() < (1e-4 if kappa == "2" else 3e-5) * FOUR_PI
+            finally:
+                del os.environ["WN_KAPPA"]
+    finally:
+        del os.environ["WN_TILE"]
+
+
+def test_tiled_path_survives_degenerate_tiles(lb, prim):
+    V, F = prim.generate_torus(5, 1, 40, 20)
+    eng = lb.FastWindingNumber(V, F)
+    os.environ["WN_TILE"] = "1"
+    try:
+        # all points identical / collinear / containing NaN / a single point / exactly one tile + 1
+        one = np.tile(np.array([[5.0, 0.1, 0.2]], np.float32), (1000, 1))
+        assert np.abs(eng.solid_angle(one) - eng.solid_angle(one, tiling=False)).max() < TOL_TILE
+        line = np.stack([np.linspace(-7, 7, 3000), np.zeros(3000), np.zeros(3000)], 1).astype(np.float32)
+        assert np.abs(eng.solid_angle(line) - eng.solid_angle(line, tiling=False)).max() < TOL_TILE
+        bad = prim.uniform_points_in_bbox(*prim.mesh_bbox(V), 513, seed=3)
+        bad[100] = np.nan
+        bad[200, 1] = np.inf
+        a, b = eng.solid_angle(bad), eng.solid_angle(bad, tiling=False)
+        ok = np.isfinite(b)
+        assert ok.sum() >= 511 and np.abs(a[ok] - b[ok]).max() < TOL_TILE
+        # a lattice much coarser than the mesh (tiles span the whole torus) and one much finer (tiles inside one triangle)
+        for n, scale in ((16, 1.0), (64, 0.01)):
+            lo, hi = prim.mesh_bbox(V)
+            c = 0.5 * (lo + hi) + np.array([5.0, 0, 0]) * (scale < 1)
+            o, s, d = prim.lattice_for_bbox(c - scale * (hi - lo), c + scale * (hi - lo), n)
+            x = eng.query_grid(o, s, d, want_omega=True)[0]
+            y = eng.query_grid(o, s, d, want_omega=True, tiling=False)[0]
+            assert np.abs(x - y).max() < TOL_TILE
+    finally:
+        del os.environ["WN_TILE"]
 
 
 # ---- K7 exact mode -----------------------------------------------------------------------------------------------------------
