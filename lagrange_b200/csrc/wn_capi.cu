@@ -652,7 +652,7 @@ bool want_tiling(const wn_engine* e, int64_t n, uint32_t flags, bool coherent)
 float tile_kappa()
 {
     const char* s = getenv("WN_KAPPA");
-    const float k = s && *s ? (float)atof(s) : 4.0f;
+    const float k = s && *s ? (float)atof(s) : 6.0f;
     return k >= 1.5f ? k : 1.5f;
 }
 

@@ -459,7 +459,9 @@ __global__ void __launch_bounds__(kQueryThreads) k_tile_plan(const QueryArgs a)
             const bool allfar = dm > 0.0f && dm * dm > thr * 1.0001f;
             const bool allnear = dp * dp <= thr * 0.9999f;
             if (allfar) {
-                if (!manc && D >= a.kappa * ra) {
+                // far set: the record's field must be smooth across the tile, i.e. the tile is small against its distance
+                // both to the expansion centre and to the nearest possible source point (bounding sphere of radius R)
+                if (!manc && D >= a.kappa * ra && D - sqrtf(fabsf(f0.w)) >= 0.5f * a.kappa * ra) {
                     const int pos = atomicAdd(&s_cnt[3], 1);
                     if (pos < kTileFarCap)
                         s_far[pos] = e;

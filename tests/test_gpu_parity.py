@@ -234,12 +234,12 @@ def test_tiled_path_matches_generic_traversal(lb, oracle_mod, prim, cfg, tree):
             assert np.abs(om - ref_om).max() < TOL_TILE, np.abs(om - ref_om).max() / FOUR_PI
             m = band_mask(ref_om / FOUR_PI, band=1e-4)
             assert np.array_equal(ins[m], ref_in[m])
-        for kappa in ("2", "16"):  # far-set distance criterion: accuracy must hold across the useful range
+        for kappa in ("3", "16"):  # far-set distance criterion: accuracy must hold across the useful range
             os.environ["WN_KAPPA"] = kappa
             try:
                 om = eng.query_grid(*lattice, want_omega=True)[0] if lattice is not None else eng.solid_angle(q)
                 ref = eng.query_grid(*lattice, want_omega=True, tiling=False)[0] if lattice is not None else eng.solid_angle(q, tiling=False)
-                assert np.abs(om - ref).max() < (1e-4 if kappa == "2" else 3e-5) * FOUR_PI
+                assert np.abs(om - ref).max() < (1e-4 if kappa == "3" else 3e-5) * FOUR_PI
             finally:
                 del os.environ["WN_KAPPA"]
     finally:

@@ -12,7 +12,7 @@ V, F = prim.generate_torus(5, 1, 40, 20)
 os.environ["WN_TILE"] = "1"
 for kw in ({}, {"leaf_size": 4}):
     eng = lb.FastWindingNumber(V, F, **kw)
-    o, s, d = prim.lattice_for_bbox(*prim.mesh_bbox(V), (19, 9, 21))
+    o, s, d = prim.lattice_for_bbox(*prim.mesh_bbox(V), (50, 17, 45))
     a = eng.query_grid(o, s, d, want_omega=True)[0]
     b = eng.query_grid(o, s, d, want_omega=True, tiling=False)[0]
     q = prim.uniform_points_in_bbox(*prim.mesh_bbox(V), 5000, seed=1)
