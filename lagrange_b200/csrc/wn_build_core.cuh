@@ -74,6 +74,7 @@ struct WnBuild
     // packed output
     float4* rec[6];      // [n_entries]
     int* link;           // [n_entries]
+    int4* kids;          // [n_entries] child entry indices of internal entries
     float4* tris;        // [nT*3]
     unsigned* tri_order; // [nT] triangle id at each depth-first position
 };
@@ -282,4 +283,15 @@ WN_HD void wn_pack_node(const WnBuild& b, int node)
 #pragma unroll
     for (int k = 0; k < 6; ++k) b.rec[k][idx] = rec[k];
     b.link[idx] = leaf_entry ? wn_leaf_link(tf, b.ntri[node]) : idx + b.size[node];
+    int kid[WN_MAX_WIDTH] = {-1, -1, -1, -1};
+    if (!leaf_entry) {
+        int cidx = idx + 1, n = 0;
+        for (int s = 0; s < b.W; ++s) {
+            const int c = b.child[(int64_t)node * b.W + s];
+            if (c < 0) continue;
+            kid[n++] = cidx;
+            cidx += b.size[c];
+        }
+    }
+    b.kids[idx] = make_int4(kid[0], kid[1], kid[2], kid[3]);
 }

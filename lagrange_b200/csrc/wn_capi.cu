@@ -129,12 +129,13 @@ size_t align_up(size_t v, size_t a)
 // Position independent packed tree: one device allocation, header first.
 struct PackedHeader
 {
-    uint64_t magic; // 'WNB200T1'
+    uint64_t magic; // 'WNB200T2'
     int64_t total_bytes;
     int64_t n_entries;
     int64_t n_tris;
     int64_t off_rec[6];
     int64_t off_link;
+    int64_t off_kids;
     int64_t off_tris;
     int64_t off_tri_order;
     int32_t width;
@@ -144,9 +145,9 @@ struct PackedHeader
     int64_t n_leaf_entries;
     int64_t num_vertices;
     int64_t num_tree_nodes;
-    int64_t reserved[4];
+    int64_t reserved[3];
 };
-constexpr uint64_t kMagic = 0x3154303032424e57ull;
+constexpr uint64_t kMagic = 0x3254303032424e57ull; // 'WNB200T2'
 
 PackedHeader make_header(int64_t n_entries, int64_t n_tris)
 {
@@ -160,6 +161,8 @@ PackedHeader make_header(int64_t n_entries, int64_t n_tris)
     }
     h.off_link = (int64_t)off;
     off = align_up(off + (size_t)n_entries * sizeof(int), 256);
+    h.off_kids = (int64_t)off;
+    off = align_up(off + (size_t)n_entries * sizeof(int4), 256);
     h.off_tris = (int64_t)off;
     off = align_up(off + (size_t)n_tris * 3 * sizeof(float4), 256);
     h.off_tri_order = (int64_t)off;
@@ -197,6 +200,7 @@ void set_view(wn_engine* e)
 {
     for (int k = 0; k < 6; ++k) e->view.rec[k] = (const float4*)(e->blob + e->hdr.off_rec[k]);
     e->view.link = (const int*)(e->blob + e->hdr.off_link);
+    e->view.kids = (const int4*)(e->blob + e->hdr.off_kids);
     e->view.tri = (const float4*)(e->blob + e->hdr.off_tris);
     e->view.n_entries = (int)e->hdr.n_entries;
     e->view.n_tris = (int)e->hdr.n_tris;
@@ -284,6 +288,7 @@ wn_status finish_build(wn_engine* e, WnBuild& b, std::vector<void*>& temps, size
     set_view(e);
     for (int k = 0; k < 6; ++k) b.rec[k] = (float4*)(e->blob + e->hdr.off_rec[k]);
     b.link = (int*)(e->blob + e->hdr.off_link);
+    b.kids = (int4*)(e->blob + e->hdr.off_kids);
     b.tris = (float4*)(e->blob + e->hdr.off_tris);
     b.tri_order = (unsigned*)(e->blob + e->hdr.off_tri_order);
     wn::k_pack<<<wn::grid_for(nN), wn::kBuildThreads, 0, st>>>(b);
@@ -695,13 +700,19 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
         }
         const int64_t units_per_launch = std::max<int64_t>(1, max_tiles / tiles_per_unit);
         const int64_t launch_tiles = std::min(units, units_per_launch) * tiles_per_unit;
-        if (launch_tiles > INT_MAX / 2 || launch_tiles * (int64_t)wn::kTileItemCap * 8 > ((int64_t)8 << 30))
+        if (launch_tiles > INT_MAX / 2)
             return fail(WN_ERR_UNSUPPORTED, "lattice layer too large for the tiled path; pass WN_QUERY_NO_TILING or split it");
-        WN_CUDA(e->s_plan_hdr.reserve((size_t)launch_tiles * sizeof(wn::TileHeader)));
-        WN_CUDA(e->s_plan_items.reserve((size_t)launch_tiles * wn::kTileItemCap * sizeof(int2)));
+        // Variable-size packets (conditional list + gathered direct records + gathered exact triangles) are bump-allocated
+        // from an arena sized for the average tile; a tile that does not fit falls back to the generic traversal.
+        const int64_t arena_bytes = std::min<int64_t>(std::max<int64_t>(launch_tiles * env_int("WN_TILE_ARENA_PER_TILE", 8192), (int64_t)64 << 20),
+                                                      (int64_t)4 << 30);
+        WN_CUDA(e->s_plan_hdr.reserve((size_t)launch_tiles * sizeof(wn::TileHeader) + 256));
+        WN_CUDA(e->s_plan_items.reserve((size_t)arena_bytes));
         WN_CUDA(e->s_plan_samples.reserve((size_t)launch_tiles * wn::kTileSampleStride * sizeof(float)));
-        a.plan_hdr = (wn::TileHeader*)e->s_plan_hdr.p;
-        a.plan_items = (int2*)e->s_plan_items.p;
+        a.plan_hdr = (wn::TileHeader*)((char*)e->s_plan_hdr.p + 256);
+        a.plan_cursor = (unsigned long long*)e->s_plan_hdr.p;
+        a.plan_arena = (char*)e->s_plan_items.p;
+        a.plan_arena_bytes = arena_bytes;
         a.plan_samples = (float*)e->s_plan_samples.p;
         a.kappa = tile_kappa();
         for (int64_t u0 = 0; u0 < units; u0 += units_per_launch) {
@@ -710,7 +721,8 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
                 a.tile_z0 = (int)u0;
             else
                 a.tile_base = u0;
-            wn::k_tile_plan<GRID><<<blocks, wn::kQueryThreads, 0, st>>>(a);
+            WN_CUDA(cudaMemsetAsync(a.plan_cursor, 0, sizeof(unsigned long long), st));
+            wn::k_tile_plan<GRID><<<blocks, wn::kPlanThreads, 0, st>>>(a);
             if (stats)
                 wn::k_tile_query<GRID, true><<<blocks, wn::kQueryThreads, 0, st>>>(a);
             else

@@ -35,6 +35,14 @@ static inline float4 make_float4(float x, float y, float z, float w)
 {
     return float4{x, y, z, w};
 }
+struct alignas(16) int4
+{
+    int x, y, z, w;
+};
+static inline int4 make_int4(int x, int y, int z, int w)
+{
+    return int4{x, y, z, w};
+}
 #endif
 
 struct WnV3
@@ -591,6 +599,8 @@ struct WnTreeView
 {
     const float4* rec[6];
     const int* link;
+    const int4* kids;  // entry indices of an internal entry's children (-1 = none); lets the tile planner expand a node
+                       // without walking the sibling chain through dependent link loads
     const float4* tri; // 3 float4 per triangle: a, b, c (w unused), depth-first order
     int n_entries;
     int n_tris;

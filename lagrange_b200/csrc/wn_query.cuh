@@ -1,27 +1,31 @@
 // wn_query.cuh — sm_100a tree query kernels (K6). Replace UT_SolidAngle::computeSolidAngle
 // (modules/winding/src/FastWindingNumber.cpp:66,75) for whole batches.
 //
-// warp_traverse  : the traversal every kernel shares. One warp owns 32*QPL spatially adjacent queries and walks a
-//                  depth-first sequence of records once for all of them (stackless: "descend" = next record, "skip
-//                  subtree" = the record's skip link). Each lane keeps the reference's per-point semantics through a
-//                  private resume index: a lane that accepted a far-field record ignores records until the end of that
-//                  subtree, lanes that must descend keep going; the warp leaves a subtree only when no lane needs it.
-//                  The accept test |q-P|^2 <= beta^2 R^2 is formed unfused, exactly like the reference, so every point
-//                  takes the same branches as in the CPU algorithm. Far field = folded order-2 Taylor record, leaves =
-//                  exact Van Oosterom-Strackee triangles. Record reads are warp-uniform float4 broadcasts.
+// warp_traverse  : the per-point traversal. One warp owns 32*QPL spatially adjacent queries and walks a depth-first
+//                  sequence of records once for all of them (stackless: "descend" = next record, "skip subtree" = the
+//                  record's skip link). Each lane keeps the reference's per-point semantics through a private resume
+//                  index: a lane that accepted a far-field record ignores records until the end of that subtree, lanes
+//                  that must descend keep going; the warp leaves a subtree only when no lane needs it. The accept test
+//                  |q-P|^2 <= beta^2 R^2 is formed unfused, exactly like the reference, so every point takes the same
+//                  branches as in the CPU algorithm. Far field = folded order-2 Taylor record, leaves = exact
+//                  Van Oosterom-Strackee triangles. Record reads are warp-uniform float4 broadcasts.
 // k_query        : generic kernel: the record sequence is the whole packed tree (small or incoherent batches, fallback).
 // k_tile_plan +  : tiled path for coherent batches (lattices, Morton-sorted point sets). A tile is 8x8x8 lattice points
 // k_tile_query     (or 512 consecutive sorted points). k_tile_plan classifies tree nodes against the tile's bounding
-//                  sphere, breadth first, with all 256 threads:
-//                    far for every point and no ancestor that some point accepted  -> "far set": its field is smooth over
-//                        the tile, so it is evaluated once per tile at 4^3 Chebyshev points instead of once per query
-//                    near for every point, internal                               -> dropped (nobody tests it), children expanded
-//                    anything else                                                 -> item of the tile's record list
-//                  then sorts the list back into depth-first order (bitonic, shared memory) and rebuilds skip links in
-//                  list coordinates. k_tile_query runs warp_traverse over that short list (staged in shared memory) and
-//                  adds the tensor-product Chebyshev interpolant of the far set. Which records a point accepts is
-//                  unchanged; only where their sum is evaluated differs (interpolation error ~1e-5 * 4 pi, measured in
-//                  tests). Executed work drops ~4x on the 512^3 / 1.3M-triangle configuration.
+//                  sphere, breadth first, and sorts the survivors back into depth-first order:
+//                    far set   : far for every point, no ancestor that some point accepted, and smooth over the tile ->
+//                                evaluated ONCE PER TILE at 4^3 Chebyshev points, interpolated per query
+//                    direct    : far for every point, no such ancestor, but too close to interpolate -> every point
+//                                evaluates it, nobody tests it; records gathered contiguously for the query kernel
+//                    exact     : leaf that is near for every point, no such ancestor -> every point evaluates its
+//                                triangles exactly, nobody tests it; triangles gathered contiguously
+//                    (near for every point, internal -> dropped, children expanded)
+//                    conditional: everything under a node that only some points accept -> short list with skip links in
+//                                list coordinates, walked by warp_traverse with the full per-point logic
+//                  k_tile_query streams the gathered records/triangles through tight loops (no tests, no votes, no
+//                  divergence), runs warp_traverse over the conditional list (staged in shared memory) and adds the
+//                  tensor-product Chebyshev interpolant of the far set. Which records a point accepts is unchanged; only
+//                  where their sum is evaluated differs (interpolation error ~1e-5 * 4 pi, bounded in tests).
 // All FP32 CUDA-core work (FMA pipe + MUFU rsqrt/atan): no tensor cores by design (BASELINE.json north_star).
 #pragma once
 
@@ -33,21 +37,28 @@ namespace wn {
 
 constexpr int kQueryThreads = 256;
 constexpr int kQueryWarps = kQueryThreads / 32;
-constexpr int kTileQPL = 2;                       // queries per lane in the tiled kernels: 8 warps * 32 * 2 = 512 = 8^3
+constexpr int kTileQPL = 2;                       // queries per lane in k_tile_query: 8 warps * 32 * 2 = 512 = 8^3
 constexpr int kTileQueries = kQueryThreads * kTileQPL;
-constexpr int kTileItemCap = 2048;                // records per tile list (shared memory: 16 KB as int2)
+constexpr int kPlanThreads = 128;                 // k_tile_plan: latency bound, small CTAs so that many are resident
+constexpr int kPlanWarps = kPlanThreads / 32;
+constexpr int kTileAllCap = 2048;                 // classified records per tile (conditional + direct + exact)
 constexpr int kTileFrontCap = 1024;               // breadth-first frontier
 constexpr int kTileFarCap = 512;                  // far set
 constexpr int kTileSamples = 64;                  // 4^3 Chebyshev points
 constexpr int kTileSampleStride = 72;             // 64 samples + centre(3) + 1/half-extent(3) + radius + pad
 constexpr int kTileFallback = 1;                  // header flag: tile must be processed by the generic traversal
 
+// record classes of the tile plan (low bits of a key = (entry << 3) | (leaf << 2) | class)
+constexpr int kClsCond = 0;       // tested per point
+constexpr int kClsCondFar = 1;    // far for every point of the tile, but under a node only some points accept: no test
+constexpr int kClsDirect = 2;     // far for every point, unconditional
+constexpr int kClsExact = 3;      // leaf, near for every point, unconditional
+
 struct TileHeader
 {
-    int n_items;
-    int n_far;
-    int flags;
-    int pad;
+    int n_cond, n_dir, n_tri, flags;
+    long long offset; // byte offset of the tile's packet in the arena: [cond int2 x n_cond | pad16 | dir 96 B x n_dir | tri 48 B x n_tri]
+    long long pad;
 };
 
 struct QueryArgs
@@ -69,9 +80,11 @@ struct QueryArgs
     // tiled path
     int64_t tile_base;        // points mode: first tile of this launch
     TileHeader* plan_hdr;     // [tiles in launch]
-    int2* plan_items;         // [tiles in launch][kTileItemCap]  (key, skip position)
     float* plan_samples;      // [tiles in launch][kTileSampleStride]
-    float kappa;              // far set needs |c - P| >= kappa * tile radius
+    char* plan_arena;         // variable-size packets
+    unsigned long long* plan_cursor; // bump allocator over the arena (reset before every k_tile_plan launch)
+    long long plan_arena_bytes;
+    float kappa;              // far set needs |c - P| >= kappa * tile radius and |c - P| - R >= kappa/2 * tile radius
 };
 
 struct TravCounters
@@ -96,16 +109,16 @@ __device__ __forceinline__ void cheb_weights(float u, float w[4])
     w[3] = d0 * d1 * d2 * (-1.0f / den0);
 }
 
-// list keys: (entry << 2) | (leaf << 1) | notest
-__device__ __forceinline__ int tile_key(int entry, bool leaf, bool notest)
+__device__ __forceinline__ int tile_key(int entry, bool leaf, int cls)
 {
-    return (entry << 2) | (leaf ? 2 : 0) | (notest ? 1 : 0);
+    return (entry << 3) | (leaf ? 4 : 0) | cls;
 }
 
 // ----------------------------------------------------------------------------------------------------------------
-// The shared traversal. LISTED = false: records are the packed tree itself. LISTED = true: records are the tile list in
-// shared memory (key, skip position). Returns true if a far-field value that the list cannot recover from was not
-// finite (the caller then redoes the tile generically; the reference descends in that case).
+// The per-point traversal. LISTED = false: records are the packed tree itself. LISTED = true: records are the tile's
+// conditional list in shared memory (key, skip position). Accumulates into acc. Returns true if a far-field value the
+// list cannot recover from was not finite (the caller then redoes the tile generically; the reference descends in
+// that case).
 // ----------------------------------------------------------------------------------------------------------------
 template <int QPL, bool STATS, bool LISTED>
 __device__ __forceinline__ bool warp_traverse(const WnTreeView& t, const float beta2, const float (&qx)[QPL], const float (&qy)[QPL],
@@ -124,10 +137,7 @@ __device__ __forceinline__ bool warp_traverse(const WnTreeView& t, const float b
     const int n = LISTED ? n_items : t.n_entries;
     int skip[QPL];
 #pragma unroll
-    for (int k = 0; k < QPL; ++k) {
-        skip[k] = valid[k] ? 0 : n;
-        acc[k] = 0.0f;
-    }
+    for (int k = 0; k < QPL; ++k) skip[k] = valid[k] ? 0 : n;
     bool bad = false;
     // entry 0 is the root, which is never approximated (A.5): start at its first child unless the root is itself a leaf
     int i = LISTED ? 0 : (n > 1 ? 1 : 0);
@@ -136,9 +146,9 @@ __device__ __forceinline__ bool warp_traverse(const WnTreeView& t, const float b
         bool leaf, notest = false;
         if (LISTED) {
             const int2 it = s_items[i];
-            e = it.x >> 2;
-            leaf = (it.x & 2) != 0;
-            notest = (it.x & 1) != 0;
+            e = it.x >> 3;
+            leaf = (it.x & 4) != 0;
+            notest = (it.x & 3) == kClsCondFar;
             after = it.y;
         }
         const float4 f0 = __ldg(r0 + e);
@@ -315,6 +325,8 @@ __global__ void __launch_bounds__(kQueryThreads) k_query(const QueryArgs a)
         grid_points<QPL>(a, qx, qy, qz, valid, oidx);
     else
         list_points<QPL>(a, blockIdx.x, stage + (threadIdx.x >> 5) * 24 * QPL, qx, qy, qz, valid, oidx);
+#pragma unroll
+    for (int k = 0; k < QPL; ++k) acc[k] = 0.0f;
     TravCounters cnt;
     warp_traverse<QPL, STATS, false>(a.tree, a.beta2, qx, qy, qz, valid, acc, nullptr, 0, cnt);
     write_results<QPL>(a, oidx, acc);
@@ -323,31 +335,79 @@ __global__ void __launch_bounds__(kQueryThreads) k_query(const QueryArgs a)
 
 // ---- tiled path: plan ------------------------------------------------------------------------------------------
 // frontier words: entry | (has_mixed_ancestor << 30)
-__device__ __forceinline__ void tile_push_children(const WnTreeView& t, int e, int flag, int* front, int* count, int* overflow)
+__device__ __forceinline__ void plan_push_kids(const int4 k4, int flag, int* front, int* count, int* overflow)
 {
-    const int end = __ldg(t.link + e);
-    int c = e + 1;
-    while (c < end) {
-        const int pos = atomicAdd(count, 1);
-        if (pos < kTileFrontCap)
-            front[pos] = c | (flag << 30);
-        else
-            *overflow = 1;
-        const bool leaf = __float_as_int(__ldg(&t.rec[0][c].w)) < 0;
-        c = leaf ? c + 1 : __ldg(t.link + c);
+    const int kid[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        if (kid[s] >= 0) {
+            const int pos = atomicAdd(count, 1);
+            if (pos < kTileFrontCap)
+                front[pos] = kid[s] | (flag << 30);
+            else
+                *overflow = 1;
+        }
     }
 }
 
+// in-place ascending bitonic sort of s[0..N), N a power of two, by the whole CTA
+__device__ __forceinline__ void plan_bitonic_sort(int* s, int N)
+{
+    for (int k = 2; k <= N; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < N; i += kPlanThreads) {
+                const int p = i ^ j;
+                if (p > i) {
+                    const int va = s[i], vb = s[p];
+                    const bool asc = (i & k) == 0;
+                    if ((va > vb) == asc) {
+                        s[i] = vb;
+                        s[p] = va;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// exclusive scan of one int per thread over the CTA (kPlanThreads threads); returns the exclusive prefix, total in `total`
+__device__ __forceinline__ int plan_block_scan(int v, int* s_warp /* kPlanWarps + 1 */, int& total)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(kFull, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    int base = 0;
+    total = 0;
+#pragma unroll
+    for (int w = 0; w < kPlanWarps; ++w) {
+        const int x = s_warp[w];
+        if (w < wid) base += x;
+        total += x;
+    }
+    __syncthreads();
+    return base + inc - v;
+}
+
 template <bool GRID>
-__global__ void __launch_bounds__(kQueryThreads) k_tile_plan(const QueryArgs a)
+__global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
 {
     __shared__ int s_front[2][kTileFrontCap];
-    __shared__ int s_items[kTileItemCap];
+    __shared__ int s_all[kTileAllCap];
+    __shared__ unsigned short s_pre[kTileAllCap + 1]; // number of conditional records before each sorted position
     __shared__ int s_far[kTileFarCap];
-    __shared__ float s_samp[kQueryWarps][kTileSamples];
-    __shared__ int s_cnt[8]; // 0,1 frontier sizes; 2 items; 3 far; 4 overflow / bad
+    __shared__ float s_samp[kPlanWarps][kTileSamples];
+    __shared__ int s_cnt[8]; // 0,1 frontier sizes; 2 classified; 3 far; 4 overflow / bad
     __shared__ float s_geo[8];
-    __shared__ float s_red[kQueryWarps][6];
+    __shared__ float s_red[kPlanWarps][6];
+    __shared__ int s_scan[kPlanWarps + 1];
+    __shared__ long long s_off;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const WnTreeView& t = a.tree;
 
@@ -370,9 +430,8 @@ __global__ void __launch_bounds__(kQueryThreads) k_tile_plan(const QueryArgs a)
     } else {
         float lo[3] = {3.4e38f, 3.4e38f, 3.4e38f}, hi[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
         const int64_t base = ((int64_t)blockIdx.x + a.tile_base) * kTileQueries;
-#pragma unroll
-        for (int k = 0; k < kTileQPL; ++k) {
-            const int64_t s = base + k * kQueryThreads + tid;
+        for (int k = tid; k < kTileQueries; k += kPlanThreads) {
+            const int64_t s = base + k;
             if (s < a.n) {
                 const int64_t p = a.perm ? (int64_t)a.perm[s] : s;
 #pragma unroll
@@ -400,6 +459,7 @@ __global__ void __launch_bounds__(kQueryThreads) k_tile_plan(const QueryArgs a)
         }
     }
     if (tid < 8) s_cnt[tid] = 0;
+    if (tid == 0) s_off = 0;
     __syncthreads();
     if (tid == 0) {
         float lo[3], hi[3];
@@ -408,7 +468,7 @@ __global__ void __launch_bounds__(kQueryThreads) k_tile_plan(const QueryArgs a)
             lo[d] = s_red[0][d];
             hi[d] = s_red[0][3 + d];
             if (!GRID) {
-                for (int w = 1; w < kQueryWarps; ++w) {
+                for (int w = 1; w < kPlanWarps; ++w) {
                     lo[d] = fminf(lo[d], s_red[w][d]);
                     hi[d] = fmaxf(hi[d], s_red[w][3 + d]);
                 }
@@ -430,9 +490,9 @@ __global__ void __launch_bounds__(kQueryThreads) k_tile_plan(const QueryArgs a)
         if (!finite) s_cnt[4] = 1; // non-finite coordinates (or an empty tile): generic path
         const int n_entries = t.n_entries;
         if (n_entries > 1) {
-            tile_push_children(t, 0, 0, s_front[0], &s_cnt[0], &s_cnt[4]);
+            plan_push_kids(__ldg(t.kids), 0, s_front[0], &s_cnt[0], &s_cnt[4]);
         } else if (n_entries == 1) {
-            s_items[0] = tile_key(0, true, false);
+            s_all[0] = tile_key(0, true, kClsExact); // the root is a leaf: exact for everybody
             s_cnt[2] = 1;
         }
     }
@@ -447,10 +507,11 @@ __global__ void __launch_bounds__(kQueryThreads) k_tile_plan(const QueryArgs a)
         const int F = min(s_cnt[cur], kTileFrontCap);
         if (F == 0 || s_cnt[4]) break;
         int* nxt = s_front[cur ^ 1];
-        for (int idx = tid; idx < F; idx += kQueryThreads) {
+        for (int idx = tid; idx < F; idx += kPlanThreads) {
             const int word = s_front[cur][idx];
             const int e = word & 0x3fffffff, manc = (word >> 30) & 1;
             const float4 f0 = __ldg(t.rec[0] + e);
+            const int4 k4 = __ldg(t.kids + e);
             const bool leaf = __float_as_int(f0.w) < 0;
             const float thr = fabsf(f0.w) * a.beta2;
             const float dx = cx - f0.x, dy = cy - f0.y, dz = cz - f0.z;
@@ -458,6 +519,7 @@ __global__ void __launch_bounds__(kQueryThreads) k_tile_plan(const QueryArgs a)
             const float dm = D - ra, dp = D + ra;
             const bool allfar = dm > 0.0f && dm * dm > thr * 1.0001f;
             const bool allnear = dp * dp <= thr * 0.9999f;
+            int key = -1;
             if (allfar) {
                 // far set: the record's field must be smooth across the tile, i.e. the tile is small against its distance
                 // both to the expansion centre and to the nearest possible source point (bounding sphere of radius R)
@@ -468,21 +530,23 @@ __global__ void __launch_bounds__(kQueryThreads) k_tile_plan(const QueryArgs a)
                     else
                         s_cnt[4] = 1;
                 } else {
-                    const int pos = atomicAdd(&s_cnt[2], 1);
-                    if (pos < kTileItemCap)
-                        s_items[pos] = tile_key(e, leaf, true);
-                    else
-                        s_cnt[4] = 1;
+                    key = tile_key(e, leaf, manc ? kClsCondFar : kClsDirect);
                 }
-            } else if (allnear && !leaf) {
-                tile_push_children(t, e, manc, nxt, &s_cnt[cur ^ 1], &s_cnt[4]);
+            } else if (allnear) {
+                if (leaf)
+                    key = tile_key(e, true, manc ? kClsCond : kClsExact);
+                else
+                    plan_push_kids(k4, manc, nxt, &s_cnt[cur ^ 1], &s_cnt[4]);
             } else {
+                key = tile_key(e, leaf, kClsCond);
+                if (!leaf) plan_push_kids(k4, 1, nxt, &s_cnt[cur ^ 1], &s_cnt[4]);
+            }
+            if (key >= 0) {
                 const int pos = atomicAdd(&s_cnt[2], 1);
-                if (pos < kTileItemCap)
-                    s_items[pos] = tile_key(e, leaf, false);
+                if (pos < kTileAllCap)
+                    s_all[pos] = key;
                 else
                     s_cnt[4] = 1;
-                if (!leaf && !allnear) tile_push_children(t, e, 1, nxt, &s_cnt[cur ^ 1], &s_cnt[4]);
             }
         }
         __syncthreads();
@@ -491,46 +555,94 @@ __global__ void __launch_bounds__(kQueryThreads) k_tile_plan(const QueryArgs a)
         __syncthreads();
     }
     __syncthreads();
-    const int n_items = min(s_cnt[2], kTileItemCap), n_far = min(s_cnt[3], kTileFarCap);
+    const int n_all = min(s_cnt[2], kTileAllCap), n_far = min(s_cnt[3], kTileFarCap);
     bool fallback = s_cnt[4] != 0;
 
-    // ---- back to depth-first order: bitonic sort of the keys, then skip links in list coordinates -------------------
+    int n_cond = 0, n_dir = 0, n_tri = 0;
     if (!fallback) {
+        // ---- back to depth-first order (the atomics above appended in arbitrary order; sorting also makes every sum
+        //      deterministic) ----------------------------------------------------------------------------------------
         int N = 2;
-        while (N < n_items) N <<= 1;
-        for (int j = n_items + tid; j < N; j += kQueryThreads) s_items[j] = 0x7fffffff;
+        while (N < n_all) N <<= 1;
+        for (int j = n_all + tid; j < N; j += kPlanThreads) s_all[j] = 0x7fffffff;
+        int NF = 2;
+        while (NF < n_far) NF <<= 1;
+        for (int j = n_far + tid; j < NF; j += kPlanThreads) s_far[j] = 0x7fffffff;
         __syncthreads();
-        for (int k = 2; k <= N; k <<= 1) {
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int i = tid; i < N; i += kQueryThreads) {
-                    const int p = i ^ j;
-                    if (p > i) {
-                        const int va = s_items[i], vb = s_items[p];
-                        const bool asc = (i & k) == 0;
-                        if ((va > vb) == asc) {
-                            s_items[i] = vb;
-                            s_items[p] = va;
-                        }
+        plan_bitonic_sort(s_all, N);
+        if (n_far > 1) plan_bitonic_sort(s_far, NF);
+
+        // ---- ranks inside each class: every thread owns a contiguous chunk of the sorted array --------------------------
+        const int chunk = (n_all + kPlanThreads - 1) / kPlanThreads;
+        const int j0 = min(tid * chunk, n_all), j1 = min(j0 + chunk, n_all);
+        int c_cond = 0, c_dir = 0, c_tri = 0;
+        for (int j = j0; j < j1; ++j) {
+            const int key = s_all[j], cls = key & 3;
+            if (cls <= kClsCondFar)
+                ++c_cond;
+            else if (cls == kClsDirect)
+                ++c_dir;
+            else
+                c_tri += (__ldg(t.link + (key >> 3)) & (WN_MAX_LEAF_SIZE - 1)) + 1;
+        }
+        int p_cond = plan_block_scan(c_cond, s_scan, n_cond);
+        int p_dir = plan_block_scan(c_dir, s_scan, n_dir);
+        int p_tri = plan_block_scan(c_tri, s_scan, n_tri);
+        {
+            int r = p_cond;
+            for (int j = j0; j < j1; ++j) {
+                s_pre[j] = (unsigned short)r;
+                r += ((s_all[j] & 3) <= kClsCondFar) ? 1 : 0;
+            }
+            if (tid == 0) s_pre[n_all] = (unsigned short)n_cond;
+        }
+        // ---- packet allocation ----------------------------------------------------------------------------------------
+        const long long cond_bytes = ((long long)n_cond * 8 + 15) & ~15ll;
+        const long long bytes = cond_bytes + (long long)n_dir * 96 + (long long)n_tri * 48;
+        if (tid == 0) {
+            long long off = 0;
+            if (bytes > 0) {
+                off = (long long)atomicAdd(a.plan_cursor, (unsigned long long)bytes);
+                if (off + bytes > a.plan_arena_bytes) s_cnt[4] = 1; // arena exhausted: generic path for this tile
+            }
+            s_off = off;
+        }
+        __syncthreads();
+        fallback = s_cnt[4] != 0;
+        if (!fallback) {
+            char* pk = a.plan_arena + s_off;
+            int2* out_cond = reinterpret_cast<int2*>(pk);
+            float4* out_dir = reinterpret_cast<float4*>(pk + cond_bytes);
+            float4* out_tri = out_dir + (long long)n_dir * 6;
+            for (int j = j0; j < j1; ++j) {
+                const int key = s_all[j], cls = key & 3, e = key >> 3;
+                if (cls <= kClsCondFar) {
+                    // skip link in conditional-list coordinates: first conditional record at or after the end of e's subtree
+                    const int end = (key & 4) ? e + 1 : __ldg(t.link + e);
+                    const int target = end << 3;
+                    int lo = j + 1, hi = n_all;
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (s_all[mid] < target)
+                            lo = mid + 1;
+                        else
+                            hi = mid;
+                    }
+                    out_cond[p_cond++] = make_int2(key, (int)s_pre[lo]);
+                } else if (cls == kClsDirect) {
+#pragma unroll
+                    for (int r = 0; r < 6; ++r) out_dir[(long long)p_dir * 6 + r] = __ldg(t.rec[r] + e);
+                    ++p_dir;
+                } else {
+                    const int lk = __ldg(t.link + e);
+                    const int first = lk >> WN_LEAF_COUNT_BITS, count = (lk & (WN_MAX_LEAF_SIZE - 1)) + 1;
+                    for (int tt = 0; tt < count; ++tt) {
+#pragma unroll
+                        for (int r = 0; r < 3; ++r) out_tri[(long long)p_tri * 3 + r] = __ldg(t.tri + 3 * (int64_t)(first + tt) + r);
+                        ++p_tri;
                     }
                 }
-                __syncthreads();
             }
-        }
-        int2* out = a.plan_items + (int64_t)blockIdx.x * kTileItemCap;
-        for (int j = tid; j < n_items; j += kQueryThreads) {
-            const int key = s_items[j];
-            const int e = key >> 2;
-            const int end = (key & 2) ? e + 1 : __ldg(t.link + e);
-            const int target = end << 2;
-            int lo = j + 1, hi = n_items; // first position whose key >= target
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (s_items[mid] < target)
-                    lo = mid + 1;
-                else
-                    hi = mid;
-            }
-            out[j] = make_int2(key, lo);
         }
     }
 
@@ -546,7 +658,7 @@ __global__ void __launch_bounds__(kQueryThreads) k_tile_plan(const QueryArgs a)
             py[k] = cy + hy * cheb_node((s >> 2) & 3);
             pz[k] = cz + hz * cheb_node(s >> 4);
         }
-        for (int m = wid; m < n_far; m += kQueryWarps) {
+        for (int m = wid; m < n_far; m += kPlanWarps) {
             const int e = s_far[m];
             const float4 f0 = __ldg(t.rec[0] + e), f1 = __ldg(t.rec[1] + e), f2 = __ldg(t.rec[2] + e), f3 = __ldg(t.rec[3] + e),
                          f4 = __ldg(t.rec[4] + e), f5 = __ldg(t.rec[5] + e);
@@ -567,15 +679,17 @@ __global__ void __launch_bounds__(kQueryThreads) k_tile_plan(const QueryArgs a)
     if (!fallback && tid < kTileSamples) {
         float s = 0.0f;
 #pragma unroll
-        for (int w = 0; w < kQueryWarps; ++w) s += s_samp[w][tid];
+        for (int w = 0; w < kPlanWarps; ++w) s += s_samp[w][tid];
         sout[tid] = s;
     }
     if (tid < 8) sout[kTileSamples + tid] = s_geo[tid];
     if (tid == 0) {
         TileHeader h;
-        h.n_items = fallback ? 0 : n_items;
-        h.n_far = fallback ? 0 : n_far;
+        h.n_cond = fallback ? 0 : n_cond;
+        h.n_dir = fallback ? 0 : n_dir;
+        h.n_tri = fallback ? 0 : n_tri;
         h.flags = fallback ? kTileFallback : 0;
+        h.offset = s_off;
         h.pad = 0;
         a.plan_hdr[blockIdx.x] = h;
         if (a.stats) {
@@ -589,8 +703,8 @@ __global__ void __launch_bounds__(kQueryThreads) k_tile_plan(const QueryArgs a)
 template <bool GRID, bool STATS>
 __global__ void __launch_bounds__(kQueryThreads) k_tile_query(const QueryArgs a)
 {
-    __shared__ int2 s_items[kTileItemCap];
-    __shared__ float s_samp[kTileSampleStride];
+    __shared__ int2 s_items[kTileAllCap];
+    __shared__ __align__(16) float s_samp[kTileSampleStride];
     __shared__ float4 stage[GRID ? 1 : kQueryWarps * 24 * kTileQPL];
     constexpr int QPL = kTileQPL;
     float qx[QPL], qy[QPL], qz[QPL], acc[QPL];
@@ -602,17 +716,56 @@ __global__ void __launch_bounds__(kQueryThreads) k_tile_query(const QueryArgs a)
         list_points<QPL>(a, (int64_t)blockIdx.x + a.tile_base, stage + (threadIdx.x >> 5) * 24 * QPL, qx, qy, qz, valid, oidx);
     const TileHeader hdr = a.plan_hdr[blockIdx.x];
     const bool fallback = (hdr.flags & kTileFallback) != 0;
+    const char* pk = a.plan_arena + hdr.offset;
     if (!fallback) {
-        const int2* src = a.plan_items + (int64_t)blockIdx.x * kTileItemCap;
-        for (int j = threadIdx.x; j < hdr.n_items; j += kQueryThreads) s_items[j] = src[j];
+        const int2* src = reinterpret_cast<const int2*>(pk);
+        for (int j = threadIdx.x; j < hdr.n_cond; j += kQueryThreads) s_items[j] = src[j];
         if (threadIdx.x < kTileSampleStride) s_samp[threadIdx.x] = a.plan_samples[(int64_t)blockIdx.x * kTileSampleStride + threadIdx.x];
     }
     __syncthreads();
     TravCounters cnt;
     bool bad = false;
-    if (!fallback) bad = warp_traverse<QPL, STATS, true>(a.tree, a.beta2, qx, qy, qz, valid, acc, s_items, hdr.n_items, cnt);
+#pragma unroll
+    for (int k = 0; k < QPL; ++k) acc[k] = 0.0f;
+    if (!fallback) {
+        // ---- direct records: far for every point of the tile; gathered contiguously by the plan ---------------------
+        const float4* __restrict__ dr = reinterpret_cast<const float4*>(pk + (((long long)hdr.n_cond * 8 + 15) & ~15ll));
+        for (int j = 0; j < hdr.n_dir; ++j) {
+            const float4 f0 = __ldg(dr + 0), f1 = __ldg(dr + 1), f2 = __ldg(dr + 2), f3 = __ldg(dr + 3), f4 = __ldg(dr + 4), f5 = __ldg(dr + 5);
+            dr += 6;
+#pragma unroll
+            for (int k = 0; k < QPL; ++k) {
+                const float rx = qx[k] - f0.x, ry = qy[k] - f0.y, rz = qz[k] - f0.z;
+                const float l2 = __fadd_rn(__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)), __fmul_rn(rz, rz)); // as in warp_traverse
+                const float om = wn_eval_record(rx, ry, rz, l2, f1, f2, f3, f4, f5);
+                bad = bad || (valid[k] && !(fabsf(om) <= 3.402823466e38f));
+                acc[k] += om;
+            }
+        }
+        // ---- exact triangles: leaves that are near for every point of the tile ------------------------------------------
+        const float4* __restrict__ tr = dr; // triangles follow the direct records in the packet
+        for (int j = 0; j < hdr.n_tri; ++j) {
+            const float4 ta = __ldg(tr + 0), tb = __ldg(tr + 1), tc = __ldg(tr + 2);
+            tr += 3;
+#pragma unroll
+            for (int k = 0; k < QPL; ++k) acc[k] += wn_tri_solid_angle(qx[k], qy[k], qz[k], ta, tb, tc);
+        }
+        if (STATS) {
+#pragma unroll
+            for (int k = 0; k < QPL; ++k) {
+                if (valid[k]) {
+                    cnt.A += hdr.n_dir;
+                    cnt.E += hdr.n_tri;
+                }
+            }
+        }
+        // ---- conditional records ------------------------------------------------------------------------------------
+        bad = warp_traverse<QPL, STATS, true>(a.tree, a.beta2, qx, qy, qz, valid, acc, s_items, hdr.n_cond, cnt) || bad;
+    }
     if (__syncthreads_or((int)(bad || fallback))) {
         // generic traversal of the whole tree for this tile (list overflow, non-finite far field, degenerate tile)
+#pragma unroll
+        for (int k = 0; k < QPL; ++k) acc[k] = 0.0f;
         warp_traverse<QPL, STATS, false>(a.tree, a.beta2, qx, qy, qz, valid, acc, nullptr, 0, cnt);
     } else {
         const float cx = s_samp[64], cy = s_samp[65], cz = s_samp[66];

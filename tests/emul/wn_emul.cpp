@@ -21,6 +21,7 @@ struct Emul
     std::vector<unsigned char> slot, collapsed;
     std::vector<unsigned> prim, r2v, tri_order;
     std::vector<float4> local, rec[6], tris;
+    std::vector<int4> kids;
     WnBuild b;
     WnTreeView view;
     int err = 0, max_depth = 0;
@@ -133,6 +134,8 @@ void* emul_build(const float* v, int64_t nV, const int32_t* tri, int64_t nT, con
         b.rec[k] = e->rec[k].data();
     }
     e->link.resize(n_entries);
+    e->kids.resize(n_entries);
+    b.kids = e->kids.data();
     e->tris.resize((size_t)nT * 3);
     e->tri_order.resize(nT);
     b.link = e->link.data();
@@ -144,6 +147,7 @@ void* emul_build(const float* v, int64_t nV, const int32_t* tri, int64_t nT, con
         e->err = WN_ERR_TOPOLOGY_BAD_CHILD;
     for (int k = 0; k < 6; ++k) e->view.rec[k] = e->rec[k].data();
     e->view.link = e->link.data();
+    e->view.kids = e->kids.data();
     e->view.tri = e->tris.data();
     e->view.n_entries = n_entries;
     e->view.n_tris = (int)nT;
@@ -204,6 +208,12 @@ void emul_get_packed(void* h, float* rec, int32_t* link, float* tris, uint32_t* 
     memcpy(link, e->link.data(), n * sizeof(int));
     memcpy(tris, e->tris.data(), e->tris.size() * sizeof(float4));
     memcpy(tri_order, e->tri_order.data(), e->tri_order.size() * sizeof(unsigned));
+}
+
+void emul_get_kids(void* h, int32_t* out)
+{
+    Emul* e = static_cast<Emul*>(h);
+    memcpy(out, e->kids.data(), e->kids.size() * sizeof(int4));
 }
 
 void emul_query(void* h, const float* q, int64_t n, float beta, float* out, uint64_t* counters)
