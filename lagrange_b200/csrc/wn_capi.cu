@@ -133,8 +133,8 @@ struct PackedHeader
     int64_t total_bytes;
     int64_t n_entries;
     int64_t n_tris;
-    int64_t off_rec[6];
-    int64_t off_link;
+    int64_t off_hot;  // float4[2 * n_entries]: (P, R2 | leaf), (N, link bits)
+    int64_t off_cold; // float4[4 * n_entries]: quadratic + cubic form
     int64_t off_kids;
     int64_t off_tris;
     int64_t off_tri_order;
@@ -155,12 +155,10 @@ PackedHeader make_header(int64_t n_entries, int64_t n_tris)
     memset(&h, 0, sizeof(h));
     h.magic = kMagic;
     size_t off = align_up(sizeof(PackedHeader), 256);
-    for (int k = 0; k < 6; ++k) {
-        h.off_rec[k] = (int64_t)off;
-        off = align_up(off + (size_t)n_entries * sizeof(float4), 256);
-    }
-    h.off_link = (int64_t)off;
-    off = align_up(off + (size_t)n_entries * sizeof(int), 256);
+    h.off_hot = (int64_t)off;
+    off = align_up(off + (size_t)n_entries * 2 * sizeof(float4), 256);
+    h.off_cold = (int64_t)off;
+    off = align_up(off + (size_t)n_entries * 4 * sizeof(float4), 256);
     h.off_kids = (int64_t)off;
     off = align_up(off + (size_t)n_entries * sizeof(int4), 256);
     h.off_tris = (int64_t)off;
@@ -198,8 +196,8 @@ namespace {
 
 void set_view(wn_engine* e)
 {
-    for (int k = 0; k < 6; ++k) e->view.rec[k] = (const float4*)(e->blob + e->hdr.off_rec[k]);
-    e->view.link = (const int*)(e->blob + e->hdr.off_link);
+    e->view.hot = (const float4*)(e->blob + e->hdr.off_hot);
+    e->view.cold = (const float4*)(e->blob + e->hdr.off_cold);
     e->view.kids = (const int4*)(e->blob + e->hdr.off_kids);
     e->view.tri = (const float4*)(e->blob + e->hdr.off_tris);
     e->view.n_entries = (int)e->hdr.n_entries;
@@ -286,8 +284,8 @@ wn_status finish_build(wn_engine* e, WnBuild& b, std::vector<void*>& temps, size
     e->hdr = make_header(h_size, b.nL);
     WN_CUDA(cudaMalloc((void**)&e->blob, (size_t)e->hdr.total_bytes));
     set_view(e);
-    for (int k = 0; k < 6; ++k) b.rec[k] = (float4*)(e->blob + e->hdr.off_rec[k]);
-    b.link = (int*)(e->blob + e->hdr.off_link);
+    b.hot = (float4*)(e->blob + e->hdr.off_hot);
+    b.cold = (float4*)(e->blob + e->hdr.off_cold);
     b.kids = (int4*)(e->blob + e->hdr.off_kids);
     b.tris = (float4*)(e->blob + e->hdr.off_tris);
     b.tri_order = (unsigned*)(e->blob + e->hdr.off_tri_order);

@@ -133,7 +133,7 @@ WN_HD int wn_dec_tri(int c)
 
 // Packed depth-first record array ("entries"). For entry i:
 //   rec[0][i] = (Px, Py, Pz, R2)          R2's sign bit set <=> leaf entry (R2 itself is >= 0; may be +inf)
-//   rec[1][i] = (Nx, Ny, Nz, unused)
+//   rec[1][i] = (Nx, Ny, Nz, link[i] as raw bits)
 //   rec[2][i] = (qxx, qyy, qzz, qxy)      quadratic form  a1(r^) = sum q_ab r^_a r^_b
 //   rec[3][i] = (qyz, qzx, cxxx, cyyy)    cubic form      a2(r^) = sum c_abc r^_a r^_b r^_c
 //   rec[4][i] = (czzz, cxyz, cxxy, cxxz)
@@ -532,11 +532,24 @@ WN_HD float wn_rsqrt(float x)
 #endif
 }
 
+// One MUFU.RSQ, denormal inputs flushed to zero (-> +inf -> a non-finite expansion -> the caller descends, which is also
+// what the reference ends up doing when 1/|r|^2 overflows). Saves the 3-instruction denormal fix-up of rsqrtf().
+WN_HD float wn_rsqrt_ftz(float x)
+{
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return x < 1.17549435e-38f ? (x == x ? INFINITY : x) : 1.0f / sqrtf(x);
+#endif
+}
+
 // Far-field Taylor evaluation of one record at r = q - P with l2 = |r|^2 > 0 (A.5 folded, see wn_pack_record).
 WN_HD float wn_eval_record(float rx, float ry, float rz, float l2, const float4& f1, const float4& f2, const float4& f3,
                            const float4& f4, const float4& f5)
 {
-    const float m1 = wn_rsqrt(l2);
+    const float m1 = wn_rsqrt_ftz(l2);
     const float x = rx * m1, y = ry * m1, z = rz * m1;
     const float m2 = m1 * m1;
     const float a0 = -(x * f1.x + y * f1.y + z * f1.z);
@@ -595,10 +608,15 @@ WN_HD float wn_lattice_coord(float origin, float spacing, int i)
 
 // One query point against the packed tree, one lane, no warp cooperation: the definition of the per-point result.
 // (Used by the host emulation harness and mirrored lane-wise by the warp kernel.)
+// Memory layout of the packed tree: the six float4 of a record (see wn_pack_record) are split in a hot and a cold part,
+// each interleaved per entry, so that one address computation serves every load of a visit:
+//   hot [2*i + 0] = (Px, Py, Pz, R2 | leaf sign)     hot [2*i + 1] = (Nx, Ny, Nz, link bits)      32 B: one sector
+//   cold[4*i + k] = quadratic / cubic form coefficients (rec[2..5])                                  64 B: two sectors
+// A visit that only tests (the record is near for every lane) touches the hot sector alone.
 struct WnTreeView
 {
-    const float4* rec[6];
-    const int* link;
+    const float4* hot;
+    const float4* cold;
     const int4* kids;  // entry indices of an internal entry's children (-1 = none); lets the tile planner expand a node
                        // without walking the sibling chain through dependent link loads
     const float4* tri; // 3 float4 per triangle: a, b, c (w unused), depth-first order
@@ -612,7 +630,8 @@ WN_HD float wn_traverse_point(const WnTreeView& t, float qx, float qy, float qz,
     // entry 0 is the root, which is never approximated (A.5): start at its first child unless the root is itself a leaf
     int i = t.n_entries > 1 ? 1 : 0;
     while (i < t.n_entries) {
-        const float4 f0 = t.rec[0][i];
+        const float4 f0 = t.hot[2 * (int64_t)i], f1 = t.hot[2 * (int64_t)i + 1];
+        const int lk = wn_float_as_int(f1.w);
         const bool leaf = wn_float_as_int(f0.w) < 0;
         const float thr = WN_MUL(fabsf(f0.w), beta2);
         const float rx = qx - f0.x, ry = qy - f0.y, rz = qz - f0.z;
@@ -620,17 +639,17 @@ WN_HD float wn_traverse_point(const WnTreeView& t, float qx, float qy, float qz,
         bool near = l2 <= thr;
         if (cnt) cnt[0]++;
         if (!near) {
-            const float om = wn_eval_record(rx, ry, rz, l2, t.rec[1][i], t.rec[2][i], t.rec[3][i], t.rec[4][i], t.rec[5][i]);
+            const float4* c = t.cold + 4 * (int64_t)i;
+            const float om = wn_eval_record(rx, ry, rz, l2, f1, c[0], c[1], c[2], c[3]);
             if (fabsf(om) <= 3.402823466e38f) { // finite
                 acc += om;
                 if (cnt) cnt[1]++;
-                i = leaf ? i + 1 : t.link[i];
+                i = leaf ? i + 1 : lk;
                 continue;
             }
             near = true;
         }
         if (leaf) {
-            const int lk = t.link[i];
             const int first = lk >> WN_LEAF_COUNT_BITS, count = (lk & (WN_MAX_LEAF_SIZE - 1)) + 1;
             for (int k = 0; k < count; ++k) {
                 acc += wn_tri_solid_angle(qx, qy, qz, t.tri[3 * (first + k)], t.tri[3 * (first + k) + 1], t.tri[3 * (first + k) + 2]);

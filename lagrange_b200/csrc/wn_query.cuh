@@ -114,6 +114,20 @@ __device__ __forceinline__ int tile_key(int entry, bool leaf, int cls)
     return (entry << 3) | (leaf ? 4 : 0) | cls;
 }
 
+// accessors of the hot/cold record layout (wn_device.cuh, WnTreeView)
+__device__ __forceinline__ float4 rec_hot(const WnTreeView& t, int e, int k)
+{
+    return __ldg(t.hot + 2 * (int64_t)e + k);
+}
+__device__ __forceinline__ float4 rec_cold(const WnTreeView& t, int e, int k)
+{
+    return __ldg(t.cold + 4 * (int64_t)e + k);
+}
+__device__ __forceinline__ int rec_link(const WnTreeView& t, int e)
+{
+    return __float_as_int(__ldg(&t.hot[2 * (int64_t)e + 1].w));
+}
+
 // ----------------------------------------------------------------------------------------------------------------
 // The per-point traversal. LISTED = false: records are the packed tree itself. LISTED = true: records are the tile's
 // conditional list in shared memory (key, skip position). Accumulates into acc. Returns true if a far-field value the
@@ -126,13 +140,8 @@ __device__ __forceinline__ bool warp_traverse(const WnTreeView& t, const float b
                                               const int n_items, TravCounters& cnt)
 {
     const int lane = threadIdx.x & 31;
-    const float4* __restrict__ r0 = t.rec[0];
-    const float4* __restrict__ r1 = t.rec[1];
-    const float4* __restrict__ r2 = t.rec[2];
-    const float4* __restrict__ r3 = t.rec[3];
-    const float4* __restrict__ r4 = t.rec[4];
-    const float4* __restrict__ r5 = t.rec[5];
-    const int* __restrict__ link = t.link;
+    const float4* __restrict__ hot = t.hot;
+    const float4* __restrict__ cold = t.cold;
     const float4* __restrict__ tris = t.tri;
     const int n = LISTED ? n_items : t.n_entries;
     int skip[QPL];
@@ -142,7 +151,7 @@ __device__ __forceinline__ bool warp_traverse(const WnTreeView& t, const float b
     // entry 0 is the root, which is never approximated (A.5): start at its first child unless the root is itself a leaf
     int i = LISTED ? 0 : (n > 1 ? 1 : 0);
     while (i < n) {
-        int e = i, after = 0, lk = 0;
+        int e = i, after = 0;
         bool leaf, notest = false;
         if (LISTED) {
             const int2 it = s_items[i];
@@ -151,9 +160,11 @@ __device__ __forceinline__ bool warp_traverse(const WnTreeView& t, const float b
             notest = (it.x & 3) == kClsCondFar;
             after = it.y;
         }
-        const float4 f0 = __ldg(r0 + e);
+        // one address, one 32-byte sector: centre + radius, normal + link
+        const float4* __restrict__ hp = hot + 2 * (int64_t)e;
+        const float4 f0 = __ldg(hp), f1 = __ldg(hp + 1);
+        const int lk = __float_as_int(f1.w);
         if (!LISTED) {
-            lk = __ldg(link + e);
             leaf = __float_as_int(f0.w) < 0;
             after = leaf ? i + 1 : lk;
         }
@@ -178,7 +189,8 @@ __device__ __forceinline__ bool warp_traverse(const WnTreeView& t, const float b
         }
         if (STATS) cnt.V += (lane == 0) ? 32 * QPL : 0;
         if (__any_sync(kFull, anyfar)) {
-            const float4 f1 = __ldg(r1 + e), f2 = __ldg(r2 + e), f3 = __ldg(r3 + e), f4 = __ldg(r4 + e), f5 = __ldg(r5 + e);
+            const float4* __restrict__ cp = cold + 4 * (int64_t)e;
+            const float4 f2 = __ldg(cp), f3 = __ldg(cp + 1), f4 = __ldg(cp + 2), f5 = __ldg(cp + 3);
 #pragma unroll
             for (int k = 0; k < QPL; ++k) {
                 if (farq[k]) {
@@ -200,7 +212,6 @@ __device__ __forceinline__ bool warp_traverse(const WnTreeView& t, const float b
         anynear = __any_sync(kFull, anynear);
         if (leaf) {
             if (anynear) {
-                if (LISTED) lk = __ldg(link + e);
                 const int first = lk >> WN_LEAF_COUNT_BITS, count = (lk & (WN_MAX_LEAF_SIZE - 1)) + 1;
                 for (int tt = 0; tt < count; ++tt) {
                     const float4 ta = __ldg(tris + 3 * (int64_t)(first + tt));
@@ -510,7 +521,7 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
         for (int idx = tid; idx < F; idx += kPlanThreads) {
             const int word = s_front[cur][idx];
             const int e = word & 0x3fffffff, manc = (word >> 30) & 1;
-            const float4 f0 = __ldg(t.rec[0] + e);
+            const float4 f0 = rec_hot(t, e, 0);
             const int4 k4 = __ldg(t.kids + e);
             const bool leaf = __float_as_int(f0.w) < 0;
             const float thr = fabsf(f0.w) * a.beta2;
@@ -583,7 +594,7 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
             else if (cls == kClsDirect)
                 ++c_dir;
             else
-                c_tri += (__ldg(t.link + (key >> 3)) & (WN_MAX_LEAF_SIZE - 1)) + 1;
+                c_tri += (rec_link(t, key >> 3) & (WN_MAX_LEAF_SIZE - 1)) + 1;
         }
         int p_cond = plan_block_scan(c_cond, s_scan, n_cond);
         int p_dir = plan_block_scan(c_dir, s_scan, n_dir);
@@ -618,7 +629,7 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
                 const int key = s_all[j], cls = key & 3, e = key >> 3;
                 if (cls <= kClsCondFar) {
                     // skip link in conditional-list coordinates: first conditional record at or after the end of e's subtree
-                    const int end = (key & 4) ? e + 1 : __ldg(t.link + e);
+                    const int end = (key & 4) ? e + 1 : rec_link(t, e);
                     const int target = end << 3;
                     int lo = j + 1, hi = n_all;
                     while (lo < hi) {
@@ -631,10 +642,10 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
                     out_cond[p_cond++] = make_int2(key, (int)s_pre[lo]);
                 } else if (cls == kClsDirect) {
 #pragma unroll
-                    for (int r = 0; r < 6; ++r) out_dir[(long long)p_dir * 6 + r] = __ldg(t.rec[r] + e);
+                    for (int r = 0; r < 6; ++r) out_dir[(long long)p_dir * 6 + r] = r < 2 ? rec_hot(t, e, r) : rec_cold(t, e, r - 2);
                     ++p_dir;
                 } else {
-                    const int lk = __ldg(t.link + e);
+                    const int lk = rec_link(t, e);
                     const int first = lk >> WN_LEAF_COUNT_BITS, count = (lk & (WN_MAX_LEAF_SIZE - 1)) + 1;
                     for (int tt = 0; tt < count; ++tt) {
 #pragma unroll
@@ -660,8 +671,8 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
         }
         for (int m = wid; m < n_far; m += kPlanWarps) {
             const int e = s_far[m];
-            const float4 f0 = __ldg(t.rec[0] + e), f1 = __ldg(t.rec[1] + e), f2 = __ldg(t.rec[2] + e), f3 = __ldg(t.rec[3] + e),
-                         f4 = __ldg(t.rec[4] + e), f5 = __ldg(t.rec[5] + e);
+            const float4 f0 = rec_hot(t, e, 0), f1 = rec_hot(t, e, 1), f2 = rec_cold(t, e, 0), f3 = rec_cold(t, e, 1),
+                         f4 = rec_cold(t, e, 2), f5 = rec_cold(t, e, 3);
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const float rx = px[k] - f0.x, ry = py[k] - f0.y, rz = pz[k] - f0.z;

@@ -17,10 +17,10 @@ struct Emul
 {
     std::vector<float> v;
     std::vector<int> tri;
-    std::vector<int> child, parent, arrive, ntri, size, link;
+    std::vector<int> child, parent, arrive, ntri, size;
     std::vector<unsigned char> slot, collapsed;
     std::vector<unsigned> prim, r2v, tri_order;
-    std::vector<float4> local, rec[6], tris;
+    std::vector<float4> local, hot, cold, tris;
     std::vector<int4> kids;
     WnBuild b;
     WnTreeView view;
@@ -129,24 +129,22 @@ void* emul_build(const float* v, int64_t nV, const int32_t* tri, int64_t nT, con
             for (int l = 0; l < b.nL; ++l) wn_vertex_radius_leaf(b, l);
     }
     const int n_entries = (e->err == 0 && nT > 0) ? e->size[0] : 0;
-    for (int k = 0; k < 6; ++k) {
-        e->rec[k].resize(n_entries);
-        b.rec[k] = e->rec[k].data();
-    }
-    e->link.resize(n_entries);
+    e->hot.resize((size_t)n_entries * 2);
+    e->cold.resize((size_t)n_entries * 4);
+    b.hot = e->hot.data();
+    b.cold = e->cold.data();
     e->kids.resize(n_entries);
     b.kids = e->kids.data();
     e->tris.resize((size_t)nT * 3);
     e->tri_order.resize(nT);
-    b.link = e->link.data();
     b.tris = e->tris.data();
     b.tri_order = e->tri_order.data();
     if (e->err == 0 && nT > 0 && e->ntri[0] == b.nL)
         for (int node = 0; node < (int)nN; ++node) wn_pack_node(b, node);
     else if (nT > 0 && e->err == 0)
         e->err = WN_ERR_TOPOLOGY_BAD_CHILD;
-    for (int k = 0; k < 6; ++k) e->view.rec[k] = e->rec[k].data();
-    e->view.link = e->link.data();
+    e->view.hot = e->hot.data();
+    e->view.cold = e->cold.data();
     e->view.kids = e->kids.data();
     e->view.tri = e->tris.data();
     e->view.n_entries = n_entries;
@@ -203,9 +201,14 @@ void emul_get_ref23(void* h, int64_t first, int64_t count, float* out)
 void emul_get_packed(void* h, float* rec, int32_t* link, float* tris, uint32_t* tri_order)
 {
     Emul* e = static_cast<Emul*>(h);
-    const size_t n = e->link.size();
-    for (int k = 0; k < 6; ++k) memcpy(rec + k * n * 4, e->rec[k].data(), n * sizeof(float4));
-    memcpy(link, e->link.data(), n * sizeof(int));
+    // de-interleave the hot/cold layout back into the six logical float4 arrays + link
+    const size_t n = e->kids.size();
+    for (size_t i = 0; i < n; ++i) {
+        memcpy(rec + (0 * n + i) * 4, &e->hot[2 * i], sizeof(float4));
+        memcpy(rec + (1 * n + i) * 4, &e->hot[2 * i + 1], sizeof(float4));
+        for (int k = 0; k < 4; ++k) memcpy(rec + ((2 + k) * n + i) * 4, &e->cold[4 * i + k], sizeof(float4));
+        link[i] = wn_float_as_int(e->hot[2 * i + 1].w);
+    }
     memcpy(tris, e->tris.data(), e->tris.size() * sizeof(float4));
     memcpy(tri_order, e->tri_order.data(), e->tri_order.size() * sizeof(unsigned));
 }
