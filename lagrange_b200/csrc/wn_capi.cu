@@ -190,6 +190,7 @@ struct wn_engine
     mutable std::mutex mu;
     mutable DevBuf s_in, s_out_f, s_out_b, s_sort, s_stats, s_partial, s_plan_hdr, s_plan_items, s_plan_samples;
     mutable PinnedBuf p_small;
+    mutable cudaStream_t copy_stream = nullptr; // D2H of finished batches while the next batch computes
 };
 
 namespace {
@@ -661,10 +662,13 @@ float tile_kappa()
 
 // Runs one batch of queries described by `a` (grid or points), generic or tiled, with optional executed-work counters.
 // grid_layers = z1 - z0 for lattices; ignored for points.
+// If `ob` has host outputs and the work is split in batches (tiled lattice), each batch's results are copied to the host
+// on a second stream while the next batch computes; *copied tells the caller that nothing is left to copy.
 template <bool GRID>
 wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_t grid_layers, bool tiled, wn_query_stats* stats,
-                         cudaStream_t st)
+                         cudaStream_t st, const OutBufs* ob = nullptr, bool* copied = nullptr)
 {
+    if (copied) *copied = false;
     if (stats) {
         WN_CUDA(e->s_stats.reserve(4 * sizeof(unsigned long long)));
         WN_CUDA(cudaMemsetAsync(e->s_stats.p, 0, 4 * sizeof(unsigned long long), st));
@@ -687,7 +691,9 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
             launch_query<GRID, false>(qpl, (int)blocks64, a, st);
     } else {
         // batches of tiles so that the plan scratch (16.7 KB per tile) stays around 1 GB
-        const int64_t max_tiles = std::max(1, env_int("WN_TILE_BATCH", 1 << 16));
+        // (host outputs: smaller batches, so that less of the device-to-host copy is left exposed after the last one)
+        const bool host_out = ob && (ob->h_omega || ob->h_inside);
+        const int64_t max_tiles = std::max(1, env_int("WN_TILE_BATCH", host_out ? 1 << 15 : 1 << 16));
         int64_t units, tiles_per_unit; // grid: unit = one z layer of tiles; points: unit = one tile
         if (GRID) {
             units = (grid_layers + 7) / 8;
@@ -713,8 +719,11 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
         a.plan_arena_bytes = arena_bytes;
         a.plan_samples = (float*)e->s_plan_samples.p;
         a.kappa = tile_kappa();
+        const bool overlap = GRID && ob && (ob->h_omega || ob->h_inside) && units > units_per_launch;
+        if (overlap && !e->copy_stream) WN_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
         for (int64_t u0 = 0; u0 < units; u0 += units_per_launch) {
-            const int blocks = (int)(std::min(units_per_launch, units - u0) * tiles_per_unit);
+            const int64_t nunits = std::min(units_per_launch, units - u0);
+            const int blocks = (int)(nunits * tiles_per_unit);
             if (GRID)
                 a.tile_z0 = (int)u0;
             else
@@ -725,6 +734,27 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
                 wn::k_tile_query<GRID, true><<<blocks, wn::kQueryThreads, 0, st>>>(a);
             else
                 wn::k_tile_query<GRID, false><<<blocks, wn::kQueryThreads, 0, st>>>(a);
+            if (overlap) {
+                // results of z layers [8*u0, 8*(u0+nunits)) of the slab are final: ship them while the next batch runs
+                const int64_t per_layer = (int64_t)a.g.nx * a.g.ny;
+                const int64_t first = 8 * u0 * per_layer;
+                const int64_t count = std::min<int64_t>(8 * nunits, grid_layers - 8 * u0) * per_layer;
+                cudaEvent_t ev;
+                WN_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                WN_CUDA(cudaEventRecord(ev, st));
+                WN_CUDA(cudaStreamWaitEvent(e->copy_stream, ev, 0));
+                WN_CUDA(cudaEventDestroy(ev)); // released by the runtime once it has completed
+                if (ob->h_omega)
+                    WN_CUDA(cudaMemcpyAsync(ob->h_omega + first, ob->d_omega + first, (size_t)count * sizeof(float), cudaMemcpyDeviceToHost,
+                                            e->copy_stream));
+                if (ob->h_inside)
+                    WN_CUDA(cudaMemcpyAsync(ob->h_inside + first, ob->d_inside + first, (size_t)count, cudaMemcpyDeviceToHost, e->copy_stream));
+            }
+        }
+        if (overlap) {
+            WN_CUDA(cudaGetLastError());
+            WN_CUDA(cudaStreamSynchronize(e->copy_stream));
+            if (copied) *copied = true;
         }
     }
     WN_CUDA(cudaGetLastError());
@@ -848,9 +878,10 @@ wn_status grid_impl(const wn_engine* e, const float* origin, const float* spacin
     a.out_inside = ob.d_inside;
     a.tiles_x = (g.nx + 7) / 8;
     a.tiles_y = (g.ny + 7) / 8;
-    s = dispatch_query<true>(e, a, n, z1 - z0, want_tiling(e, n, flags, true), stats, st);
+    bool copied = false;
+    s = dispatch_query<true>(e, a, n, z1 - z0, want_tiling(e, n, flags, true), stats, st, &ob, &copied);
     if (s != WN_OK) return s;
-    return finish_outputs(n, ob, st);
+    return copied ? WN_OK : finish_outputs(n, ob, st);
 }
 
 wn_status exact_impl(const wn_engine* e, bool grid, const float* q_xyz, int64_t n, const wn::GridDesc* g, float* out_omega,
@@ -1007,6 +1038,7 @@ wn_status wn_destroy(wn_engine* e)
         e->s_plan_items.release();
         e->s_plan_samples.release();
         e->p_small.release();
+        if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     }
     delete e;
     return WN_OK;
