@@ -44,6 +44,8 @@ constexpr int kPlanWarps = kPlanThreads / 32;
 constexpr int kTileAllCap = 2048;                 // classified records per tile (conditional + direct + exact)
 constexpr int kTileFrontCap = 1024;               // breadth-first frontier
 constexpr int kTileFarCap = 512;                  // far set
+constexpr int kTileDirCap = 512;                  // direct records
+constexpr int kTileExactCap = 1024;               // exact leaves (also bounded by the frontier buffer reused for offsets)
 constexpr int kTileSamples = 64;                  // 4^3 Chebyshev points
 constexpr int kTileSampleStride = 72;             // 64 samples + centre(3) + 1/half-extent(3) + radius + pad
 constexpr int kTileFallback = 1;                  // header flag: tile must be processed by the generic traversal
@@ -361,7 +363,16 @@ __device__ __forceinline__ void plan_push_kids(const int4 k4, int flag, int* fro
     }
 }
 
-// in-place ascending bitonic sort of s[0..N), N a power of two, by the whole CTA
+__device__ __forceinline__ void plan_append(int* list, int* count, int cap, int value, int* overflow)
+{
+    const int pos = atomicAdd(count, 1);
+    if (pos < cap)
+        list[pos] = value;
+    else
+        *overflow = 1;
+}
+
+// in-place ascending bitonic sort of s[0..N), N a power of two, by the whole CTA (lists longer than 64)
 __device__ __forceinline__ void plan_bitonic_sort(int* s, int N)
 {
     for (int k = 2; k <= N; k <<= 1) {
@@ -382,42 +393,47 @@ __device__ __forceinline__ void plan_bitonic_sort(int* s, int N)
     }
 }
 
-// exclusive scan of one int per thread over the CTA (kPlanThreads threads); returns the exclusive prefix, total in `total`
-__device__ __forceinline__ int plan_block_scan(int v, int* s_warp /* kPlanWarps + 1 */, int& total)
+// ascending sort of s[0..n), n <= 64, by ONE warp: two keys per lane (elements lane and lane + 32), bitonic network with
+// shuffles, no shared-memory traffic and no block barrier
+__device__ __forceinline__ void plan_warp_sort64(int* s, int n)
 {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    int inc = v;
+    const int lane = threadIdx.x & 31;
+    int a = lane < n ? s[lane] : 0x7fffffff;
+    int b = lane + 32 < n ? s[lane + 32] : 0x7fffffff;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(kFull, inc, o);
-        if (lane >= o) inc += t;
-    }
-    if (lane == 31) s_warp[wid] = inc;
-    __syncthreads();
-    int base = 0;
-    total = 0;
+    for (int k = 2; k <= 64; k <<= 1) {
 #pragma unroll
-    for (int w = 0; w < kPlanWarps; ++w) {
-        const int x = s_warp[w];
-        if (w < wid) base += x;
-        total += x;
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j == 32) { // k == 64: partner is the other key of the same lane, direction ascending
+                const int lo = min(a, b), hi = max(a, b);
+                a = lo;
+                b = hi;
+            } else {
+                const int pa = __shfl_xor_sync(kFull, a, j), pb = __shfl_xor_sync(kFull, b, j);
+                const bool lower = (lane & j) == 0;
+                const bool asc_a = (lane & k) == 0;        // element index = lane
+                const bool asc_b = ((lane + 32) & k) == 0; // element index = lane + 32
+                a = (lower == asc_a) ? min(a, pa) : max(a, pa);
+                b = (lower == asc_b) ? min(b, pb) : max(b, pb);
+            }
+        }
     }
-    __syncthreads();
-    return base + inc - v;
+    if (lane < n) s[lane] = a;
+    if (lane + 32 < n) s[lane + 32] = b;
 }
 
 template <bool GRID>
 __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
 {
     __shared__ int s_front[2][kTileFrontCap];
-    __shared__ int s_all[kTileAllCap];
-    __shared__ unsigned short s_pre[kTileAllCap + 1]; // number of conditional records before each sorted position
+    __shared__ int s_cond[kTileAllCap];
+    __shared__ int s_dir[kTileDirCap];
+    __shared__ int s_exact[kTileExactCap];
     __shared__ int s_far[kTileFarCap];
     __shared__ float s_samp[kPlanWarps][kTileSamples];
-    __shared__ int s_cnt[8]; // 0,1 frontier sizes; 2 classified; 3 far; 4 overflow / bad
+    __shared__ int s_cnt[8]; // 0,1 frontier sizes; 2 cond; 3 far; 4 overflow / bad; 5 dir; 6 exact; 7 triangles
     __shared__ float s_geo[8];
     __shared__ float s_red[kPlanWarps][6];
-    __shared__ int s_scan[kPlanWarps + 1];
     __shared__ long long s_off;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const WnTreeView& t = a.tree;
@@ -503,8 +519,8 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
         if (n_entries > 1) {
             plan_push_kids(__ldg(t.kids), 0, s_front[0], &s_cnt[0], &s_cnt[4]);
         } else if (n_entries == 1) {
-            s_all[0] = tile_key(0, true, kClsExact); // the root is a leaf: exact for everybody
-            s_cnt[2] = 1;
+            s_exact[0] = 0; // the root is a leaf: exact for everybody
+            s_cnt[6] = 1;
         }
     }
     __syncthreads();
@@ -530,34 +546,25 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
             const float dm = D - ra, dp = D + ra;
             const bool allfar = dm > 0.0f && dm * dm > thr * 1.0001f;
             const bool allnear = dp * dp <= thr * 0.9999f;
-            int key = -1;
             if (allfar) {
                 // far set: the record's field must be smooth across the tile, i.e. the tile is small against its distance
                 // both to the expansion centre and to the nearest possible source point (bounding sphere of radius R)
-                if (!manc && D >= a.kappa * ra && D - sqrtf(fabsf(f0.w)) >= 0.5f * a.kappa * ra) {
-                    const int pos = atomicAdd(&s_cnt[3], 1);
-                    if (pos < kTileFarCap)
-                        s_far[pos] = e;
-                    else
-                        s_cnt[4] = 1;
-                } else {
-                    key = tile_key(e, leaf, manc ? kClsCondFar : kClsDirect);
-                }
+                if (manc)
+                    plan_append(s_cond, &s_cnt[2], kTileAllCap, tile_key(e, leaf, kClsCondFar), &s_cnt[4]);
+                else if (D >= a.kappa * ra && D - sqrtf(fabsf(f0.w)) >= 0.5f * a.kappa * ra)
+                    plan_append(s_far, &s_cnt[3], kTileFarCap, e, &s_cnt[4]);
+                else
+                    plan_append(s_dir, &s_cnt[5], kTileDirCap, e, &s_cnt[4]);
             } else if (allnear) {
-                if (leaf)
-                    key = tile_key(e, true, manc ? kClsCond : kClsExact);
-                else
+                if (!leaf)
                     plan_push_kids(k4, manc, nxt, &s_cnt[cur ^ 1], &s_cnt[4]);
-            } else {
-                key = tile_key(e, leaf, kClsCond);
-                if (!leaf) plan_push_kids(k4, 1, nxt, &s_cnt[cur ^ 1], &s_cnt[4]);
-            }
-            if (key >= 0) {
-                const int pos = atomicAdd(&s_cnt[2], 1);
-                if (pos < kTileAllCap)
-                    s_all[pos] = key;
+                else if (manc)
+                    plan_append(s_cond, &s_cnt[2], kTileAllCap, tile_key(e, true, kClsCond), &s_cnt[4]);
                 else
-                    s_cnt[4] = 1;
+                    plan_append(s_exact, &s_cnt[6], kTileExactCap, e, &s_cnt[4]);
+            } else {
+                plan_append(s_cond, &s_cnt[2], kTileAllCap, tile_key(e, leaf, kClsCond), &s_cnt[4]);
+                if (!leaf) plan_push_kids(k4, 1, nxt, &s_cnt[cur ^ 1], &s_cnt[4]);
             }
         }
         __syncthreads();
@@ -566,94 +573,87 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
         __syncthreads();
     }
     __syncthreads();
-    const int n_all = min(s_cnt[2], kTileAllCap), n_far = min(s_cnt[3], kTileFarCap);
     bool fallback = s_cnt[4] != 0;
+    const int n_cond = fallback ? 0 : s_cnt[2], n_far = fallback ? 0 : s_cnt[3], n_dir = fallback ? 0 : s_cnt[5], n_ex = fallback ? 0 : s_cnt[6];
 
-    int n_cond = 0, n_dir = 0, n_tri = 0;
+    // ---- back to depth-first order. The atomics above appended in arbitrary order; sorting restores the order the skip
+    //      links need and makes every sum deterministic. Short lists (the usual case) are sorted by one warp each, in
+    //      parallel, with shuffles; long ones by the whole CTA. -------------------------------------------------------
+    int* const lists[4] = {s_cond, s_far, s_dir, s_exact};
+    const int lens[4] = {n_cond, n_far, n_dir, n_ex};
+    if (lens[wid] > 1 && lens[wid] <= 64) plan_warp_sort64(lists[wid], lens[wid]);
+    __syncthreads();
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+        if (lens[l] > 64) { // uniform over the CTA
+            int N = 128;
+            while (N < lens[l]) N <<= 1;
+            for (int j = lens[l] + tid; j < N; j += kPlanThreads) lists[l][j] = 0x7fffffff;
+            __syncthreads();
+            plan_bitonic_sort(lists[l], N);
+        }
+    }
+
+    // ---- triangles of the exact class: exclusive prefix of the leaf sizes (warp 0) --------------------------------------
+    int* s_exoff = s_front[0]; // the frontier is done; reuse it for the triangle offsets of the exact leaves
+    if (wid == 0) {
+        int run = 0;
+        for (int base = 0; base < n_ex; base += 32) {
+            const int j = base + lane;
+            const int c = j < n_ex ? (rec_link(t, s_exact[j]) & (WN_MAX_LEAF_SIZE - 1)) + 1 : 0;
+            int inc = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(kFull, inc, o);
+                if (lane >= o) inc += v;
+            }
+            if (j < n_ex) s_exoff[j] = run + inc - c;
+            run += __shfl_sync(kFull, inc, 31);
+        }
+        if (lane == 0) s_cnt[7] = run;
+    }
+    __syncthreads();
+    const int n_tri = s_cnt[7];
+
+    // ---- packet allocation and contents ---------------------------------------------------------------------------------
+    const long long cond_bytes = ((long long)n_cond * 8 + 15) & ~15ll;
+    const long long bytes = cond_bytes + (long long)n_dir * 96 + (long long)n_tri * 48;
+    if (tid == 0 && !fallback && bytes > 0) {
+        const long long off = (long long)atomicAdd(a.plan_cursor, (unsigned long long)bytes);
+        if (off + bytes > a.plan_arena_bytes) s_cnt[4] = 1; // arena exhausted: generic path for this tile
+        s_off = off;
+    }
+    __syncthreads();
+    fallback = s_cnt[4] != 0;
     if (!fallback) {
-        // ---- back to depth-first order (the atomics above appended in arbitrary order; sorting also makes every sum
-        //      deterministic) ----------------------------------------------------------------------------------------
-        int N = 2;
-        while (N < n_all) N <<= 1;
-        for (int j = n_all + tid; j < N; j += kPlanThreads) s_all[j] = 0x7fffffff;
-        int NF = 2;
-        while (NF < n_far) NF <<= 1;
-        for (int j = n_far + tid; j < NF; j += kPlanThreads) s_far[j] = 0x7fffffff;
-        __syncthreads();
-        plan_bitonic_sort(s_all, N);
-        if (n_far > 1) plan_bitonic_sort(s_far, NF);
-
-        // ---- ranks inside each class: every thread owns a contiguous chunk of the sorted array --------------------------
-        const int chunk = (n_all + kPlanThreads - 1) / kPlanThreads;
-        const int j0 = min(tid * chunk, n_all), j1 = min(j0 + chunk, n_all);
-        int c_cond = 0, c_dir = 0, c_tri = 0;
-        for (int j = j0; j < j1; ++j) {
-            const int key = s_all[j], cls = key & 3;
-            if (cls <= kClsCondFar)
-                ++c_cond;
-            else if (cls == kClsDirect)
-                ++c_dir;
-            else
-                c_tri += (rec_link(t, key >> 3) & (WN_MAX_LEAF_SIZE - 1)) + 1;
-        }
-        int p_cond = plan_block_scan(c_cond, s_scan, n_cond);
-        int p_dir = plan_block_scan(c_dir, s_scan, n_dir);
-        int p_tri = plan_block_scan(c_tri, s_scan, n_tri);
-        {
-            int r = p_cond;
-            for (int j = j0; j < j1; ++j) {
-                s_pre[j] = (unsigned short)r;
-                r += ((s_all[j] & 3) <= kClsCondFar) ? 1 : 0;
+        char* pk = a.plan_arena + s_off;
+        int2* out_cond = reinterpret_cast<int2*>(pk);
+        float4* out_dir = reinterpret_cast<float4*>(pk + cond_bytes);
+        float4* out_tri = out_dir + (long long)n_dir * 6;
+        for (int j = tid; j < n_cond; j += kPlanThreads) {
+            // skip link in list coordinates: first conditional record at or after the end of this record's subtree
+            const int key = s_cond[j], e = key >> 3;
+            const int end = (key & 4) ? e + 1 : rec_link(t, e);
+            const int target = end << 3;
+            int lo = j + 1, hi = n_cond;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (s_cond[mid] < target)
+                    lo = mid + 1;
+                else
+                    hi = mid;
             }
-            if (tid == 0) s_pre[n_all] = (unsigned short)n_cond;
+            out_cond[j] = make_int2(key, lo);
         }
-        // ---- packet allocation ----------------------------------------------------------------------------------------
-        const long long cond_bytes = ((long long)n_cond * 8 + 15) & ~15ll;
-        const long long bytes = cond_bytes + (long long)n_dir * 96 + (long long)n_tri * 48;
-        if (tid == 0) {
-            long long off = 0;
-            if (bytes > 0) {
-                off = (long long)atomicAdd(a.plan_cursor, (unsigned long long)bytes);
-                if (off + bytes > a.plan_arena_bytes) s_cnt[4] = 1; // arena exhausted: generic path for this tile
-            }
-            s_off = off;
+        for (int j = tid; j < n_dir * 6; j += kPlanThreads) {
+            const int e = s_dir[j / 6], r = j % 6;
+            out_dir[j] = r < 2 ? rec_hot(t, e, r) : rec_cold(t, e, r - 2);
         }
-        __syncthreads();
-        fallback = s_cnt[4] != 0;
-        if (!fallback) {
-            char* pk = a.plan_arena + s_off;
-            int2* out_cond = reinterpret_cast<int2*>(pk);
-            float4* out_dir = reinterpret_cast<float4*>(pk + cond_bytes);
-            float4* out_tri = out_dir + (long long)n_dir * 6;
-            for (int j = j0; j < j1; ++j) {
-                const int key = s_all[j], cls = key & 3, e = key >> 3;
-                if (cls <= kClsCondFar) {
-                    // skip link in conditional-list coordinates: first conditional record at or after the end of e's subtree
-                    const int end = (key & 4) ? e + 1 : rec_link(t, e);
-                    const int target = end << 3;
-                    int lo = j + 1, hi = n_all;
-                    while (lo < hi) {
-                        const int mid = (lo + hi) >> 1;
-                        if (s_all[mid] < target)
-                            lo = mid + 1;
-                        else
-                            hi = mid;
-                    }
-                    out_cond[p_cond++] = make_int2(key, (int)s_pre[lo]);
-                } else if (cls == kClsDirect) {
-#pragma unroll
-                    for (int r = 0; r < 6; ++r) out_dir[(long long)p_dir * 6 + r] = r < 2 ? rec_hot(t, e, r) : rec_cold(t, e, r - 2);
-                    ++p_dir;
-                } else {
-                    const int lk = rec_link(t, e);
-                    const int first = lk >> WN_LEAF_COUNT_BITS, count = (lk & (WN_MAX_LEAF_SIZE - 1)) + 1;
-                    for (int tt = 0; tt < count; ++tt) {
-#pragma unroll
-                        for (int r = 0; r < 3; ++r) out_tri[(long long)p_tri * 3 + r] = __ldg(t.tri + 3 * (int64_t)(first + tt) + r);
-                        ++p_tri;
-                    }
-                }
-            }
+        for (int j = tid; j < n_ex; j += kPlanThreads) {
+            const int lk = rec_link(t, s_exact[j]);
+            const int first = lk >> WN_LEAF_COUNT_BITS, count = (lk & (WN_MAX_LEAF_SIZE - 1)) + 1;
+            float4* dst = out_tri + (long long)s_exoff[j] * 3;
+            for (int r = 0; r < 3 * count; ++r) dst[r] = __ldg(t.tri + 3 * (int64_t)first + r);
         }
     }
 
