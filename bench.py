@@ -219,6 +219,9 @@ def main():
     build_info = {}
     if rank == 0:
         V, F, (origin, spacing, dims), name = workload(args)
+        # warm-up build on a small mesh: loads the build kernels (CUDA lazy module loading) so that build_ms is kernel time
+        lb.FastWindingNumber(*lb.primitive.generate_subdivided_sphere("icosahedron", 4), leaf_size=args.leaf_size).close()
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
         eng = lb.FastWindingNumber(V, F, leaf_size=args.leaf_size)
         torch.cuda.synchronize()

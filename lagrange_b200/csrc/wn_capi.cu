@@ -186,6 +186,7 @@ struct wn_engine
     int* kept_child = nullptr;
     unsigned* kept_prim = nullptr;
     int kept_nI = 0, kept_nL = 0, kept_W = 0;
+    std::vector<void*> kept_allocs; // device allocations that back the kept arrays
     // per-engine query scratch, guarded by mu
     mutable std::mutex mu;
     mutable DevBuf s_in, s_out_f, s_out_b, s_sort, s_stats, s_partial, s_plan_hdr, s_plan_items, s_plan_samples;
@@ -243,18 +244,33 @@ struct Timer
     }
 };
 
+// Build scratch comes out of ONE device allocation made before the timed region (cudaMalloc inside it would be what the
+// build time measures); anything that does not fit falls back to its own cudaMalloc.
+struct BuildArena
+{
+    char* base = nullptr;
+    size_t cap = 0, off = 0, used = 0;
+    std::vector<void*>* extra = nullptr;
+    cudaError_t take(void** p, size_t bytes)
+    {
+        const size_t need = align_up(bytes ? bytes : 1, 256);
+        used += bytes;
+        if (base && off + need <= cap) {
+            *p = base + off;
+            off += need;
+            return cudaSuccess;
+        }
+        cudaError_t r = cudaMalloc(p, need);
+        if (r == cudaSuccess) extra->push_back(*p);
+        return r;
+    }
+};
+
 // Everything after the topology exists: moments, radii, packing. `b` has mesh + topology + options filled in.
-wn_status finish_build(wn_engine* e, WnBuild& b, std::vector<void*>& temps, size_t& scratch_bytes, Timer& tm, cudaStream_t st)
+wn_status finish_build(wn_engine* e, WnBuild& b, BuildArena& arena, size_t blob_cap, Timer& tm, cudaStream_t st)
 {
     const int64_t nN = (int64_t)b.nI + b.nL;
-    auto dalloc = [&](void** p, size_t bytes) -> cudaError_t {
-        cudaError_t r = cudaMalloc(p, bytes ? bytes : 1);
-        if (r == cudaSuccess) {
-            temps.push_back(*p);
-            scratch_bytes += bytes;
-        }
-        return r;
-    };
+    auto dalloc = [&](void** p, size_t bytes) -> cudaError_t { return arena.take(p, bytes); };
     int* small = nullptr; // err, max_depth
     WN_CUDA(dalloc((void**)&b.local, (size_t)nN * 9 * sizeof(float4)));
     WN_CUDA(dalloc((void**)&b.arrive, (size_t)b.nI * sizeof(int)));
@@ -283,7 +299,11 @@ wn_status finish_build(wn_engine* e, WnBuild& b, std::vector<void*>& temps, size
         return fail(WN_ERR_INVALID_ARGUMENT, "malformed hierarchy topology (error %d, %d of %d triangles reachable from the root)",
                     h_small[0], h_ntri, b.nL);
     e->hdr = make_header(h_size, b.nL);
-    WN_CUDA(cudaMalloc((void**)&e->blob, (size_t)e->hdr.total_bytes));
+    if (!e->blob || blob_cap < (size_t)e->hdr.total_bytes) { // normally pre-allocated for the worst case before the timed region
+        if (e->blob) cudaFree(e->blob);
+        e->blob = nullptr;
+        WN_CUDA(cudaMalloc((void**)&e->blob, (size_t)e->hdr.total_bytes));
+    }
     set_view(e);
     b.hot = (float4*)(e->blob + e->hdr.off_hot);
     b.cold = (float4*)(e->blob + e->hdr.off_cold);
@@ -368,25 +388,22 @@ wn_status create_impl(const float* v_xyz, int64_t nV, const int32_t* tri, int64_
     memset(&e->view, 0, sizeof(e->view));
 
     std::vector<void*> temps;
-    size_t scratch_bytes = 0;
+    BuildArena arena;
+    arena.extra = &temps;
+    size_t blob_cap = 0;
+    bool keep_arena = false;
     cudaStream_t st = nullptr; // legacy default stream: build is synchronous for the caller
     auto cleanup = [&](wn_status r) {
         for (void* p : temps) cudaFree(p);
         temps.clear();
+        if (arena.base && !(keep_arena && r == WN_OK)) cudaFree(arena.base);
         if (r != WN_OK) {
             wn_destroy(e);
             e = nullptr;
         }
         return r;
     };
-    auto dalloc = [&](void** p, size_t bytes) -> cudaError_t {
-        cudaError_t r = cudaMalloc(p, bytes ? bytes : 1);
-        if (r == cudaSuccess) {
-            temps.push_back(*p);
-            scratch_bytes += bytes;
-        }
-        return r;
-    };
+    auto dalloc = [&](void** p, size_t bytes) -> cudaError_t { return arena.take(p, bytes); };
 #define WN_TRY(expr)                          \
     do {                                      \
         wn_status s__ = (expr);               \
@@ -427,6 +444,49 @@ wn_status create_impl(const float* v_xyz, int64_t nV, const int32_t* tri, int64_
     b.order = opt.order;
     b.radius_mode = opt.radius_mode;
     b.approx_single = opt.approximate_single_triangles;
+
+    // One allocation for all build scratch and one (worst-case sized) for the packed tree, both before the first event.
+    {
+        const int64_t nI_max = imported ? num_nodes : std::max<int64_t>(1, nT - 1);
+        const int64_t nN_max = nI_max + nT;
+        const int64_t W = imported ? width : 2;
+        size_t need = 0;
+        auto add = [&](size_t bytes) { need += align_up(bytes ? bytes : 1, 256); };
+        add((size_t)nV * 12);
+        add((size_t)nT * 12);
+        add(64);
+        if (!imported) {
+            add((size_t)nT * 8);
+            add((size_t)nT * 8);
+            add((size_t)nT * 4);
+            add((size_t)nT * 4);
+            add((size_t)wn::sort_scratch_bytes(nT));
+        } else {
+            add((size_t)nI_max * W * 4);
+            add((size_t)nN_max * 4);
+            add((size_t)nT * 4);
+        }
+        add((size_t)nI_max * W * 4); // child
+        add((size_t)nN_max * 4);     // parent
+        add((size_t)nN_max);         // slot
+        add((size_t)nN_max * 9 * sizeof(float4));
+        add((size_t)nI_max * 4);
+        add((size_t)nN_max * 4);
+        add((size_t)nN_max * 4);
+        add((size_t)nI_max);
+        add((size_t)nN_max * 4);
+        add(64);
+        need += 4096;
+        if (cudaMalloc((void**)&arena.base, need) == cudaSuccess)
+            arena.cap = need;
+        else
+            cudaGetLastError(); // fall back to piecemeal allocations
+        const PackedHeader worst = make_header(nN_max, nT);
+        if (cudaMalloc((void**)&e->blob, (size_t)worst.total_bytes) == cudaSuccess)
+            blob_cap = (size_t)worst.total_bytes;
+        else
+            cudaGetLastError();
+    }
 
     // mesh on the device (copied: the caller may free its buffers when we return)
     float* d_v = nullptr;
@@ -526,10 +586,10 @@ wn_status create_impl(const float* v_xyz, int64_t nV, const int32_t* tri, int64_
         tm.mark(); // 3
     }
     b.prim = d_prim;
-    WN_TRY(finish_build(e, b, temps, scratch_bytes, tm, st)); // marks 4 (moments) and 5 (pack)
+    WN_TRY(finish_build(e, b, arena, blob_cap, tm, st)); // marks 4 (moments) and 5 (pack)
 
     fill_info(e);
-    e->info.build_scratch_bytes = (int64_t)scratch_bytes;
+    e->info.build_scratch_bytes = (int64_t)arena.used;
     e->info.build_ms = tm.ms(0, 5);
     e->info.build_ms_morton = tm.ms(0, 1);
     e->info.build_ms_sort = tm.ms(1, 2);
@@ -541,20 +601,17 @@ wn_status create_impl(const float* v_xyz, int64_t nV, const int32_t* tri, int64_
     e->info.num_leaf_entries = opt.leaf_size == 1 ? nT : -1;
 
     if (opt.keep_build_data) {
-        const int64_t nN = (int64_t)b.nI + b.nL;
-        auto keep = [&](void* p) {
-            temps.erase(std::remove(temps.begin(), temps.end(), p), temps.end());
-        };
+        // the kept arrays live in the build arena (or in fallback allocations): keep all of it alive with the engine
         e->kept_local = b.local;
-        keep(b.local);
         e->kept_child = b.child;
-        keep(b.child);
         e->kept_prim = d_prim;
-        keep(d_prim);
         e->kept_nI = b.nI;
         e->kept_nL = b.nL;
         e->kept_W = b.W;
-        (void)nN;
+        e->kept_allocs = temps;
+        temps.clear();
+        if (arena.base) e->kept_allocs.push_back(arena.base);
+        keep_arena = true;
     }
     *out = e;
     return cleanup(WN_OK);
@@ -1025,9 +1082,7 @@ wn_status wn_destroy(wn_engine* e)
     {
         DeviceGuard guard(e->device);
         if (e->blob) cudaFree(e->blob);
-        if (e->kept_local) cudaFree(e->kept_local);
-        if (e->kept_child) cudaFree(e->kept_child);
-        if (e->kept_prim) cudaFree(e->kept_prim);
+        for (void* p : e->kept_allocs) cudaFree(p);
         e->s_in.release();
         e->s_out_f.release();
         e->s_out_b.release();
