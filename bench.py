@@ -356,8 +356,9 @@ def main():
                    "leaf_size": args.leaf_size, "tiled": tiled},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 60, "d2h_bytes_per_step": n_total, "ms_per_step": e2e_ms,
                 "api": "FastWindingNumber.query_grid -> wn_query_grid with a pinned HOST output buffer (lattice is implicit: 60-byte descriptor in)"},
-        # per step and rank: tiled = (k_tile_plan + k_tile_query) per batch of <= 65536 tiles; generic = one k_query
-        "gpu_launches": args.steps * (2 * max(1, -(-((-(-(z1 - z0) // 8)) * (-(-int(dims[0]) // 8)) * (-(-int(dims[1]) // 8))) // 65536)) if tiled else 1),
+        # per step and rank: tiled = 1 probe launch of k_tile_plan + (k_tile_plan + k_tile_query) per batch of <= 65536 tiles;
+        # generic = one k_query
+        "gpu_launches": args.steps * (1 + 2 * max(1, -(-((-(-(z1 - z0) // 8)) * (-(-int(dims[0]) // 8)) * (-(-int(dims[1]) // 8))) // 65536)) if tiled else 1),
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         "build": {k: build_info.get(k) for k in ("build_ms", "build_ms_morton", "build_ms_sort", "build_ms_hierarchy", "build_ms_moments",
                                                  "build_ms_pack", "build_wall_ms", "num_entries", "tree_bytes", "max_depth")},

@@ -192,6 +192,7 @@ struct wn_engine
     mutable DevBuf s_in, s_out_f, s_out_b, s_sort, s_stats, s_partial, s_plan_hdr, s_plan_items, s_plan_samples;
     mutable PinnedBuf p_small;
     mutable cudaStream_t copy_stream = nullptr; // D2H of finished batches while the next batch computes
+    mutable float last_probe_share = -1.0f;     // far-set share measured by the last tiling probe (diagnostics)
 };
 
 namespace {
@@ -703,11 +704,13 @@ int pick_qpl(int64_t n)
 
 // The tiled path (k_tile_plan + k_tile_query) pays off when a tile's 512 queries are spatial neighbours: lattices
 // always, point sets when they are Morton-sorted (by us) or declared presorted by the caller.
-bool want_tiling(const wn_engine* e, int64_t n, uint32_t flags, bool coherent)
+// 0 = generic traversal, 1 = tiled, 2 = decide by probing (sampled tile classification, see dispatch_query)
+int want_tiling(const wn_engine* e, int64_t n, uint32_t flags, bool coherent)
 {
     const int forced = env_int("WN_TILE", -1);
-    if (forced == 0 || (flags & WN_QUERY_NO_TILING) || e->view.n_entries <= 1 || !coherent) return false;
-    return forced == 1 || n >= env_int("WN_TILE_MIN", 1 << 15);
+    if (forced == 0 || (flags & WN_QUERY_NO_TILING) || e->view.n_entries <= 1 || !coherent) return 0;
+    if (forced == 1) return 1;
+    return n >= env_int("WN_TILE_MIN", 1 << 15) ? 2 : 0;
 }
 
 float tile_kappa()
@@ -722,10 +725,41 @@ float tile_kappa()
 // If `ob` has host outputs and the work is split in batches (tiled lattice), each batch's results are copied to the host
 // on a second stream while the next batch computes; *copied tells the caller that nothing is left to copy.
 template <bool GRID>
-wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_t grid_layers, bool tiled, wn_query_stats* stats,
+wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_t grid_layers, int tile_mode, wn_query_stats* stats,
                          cudaStream_t st, const OutBufs* ob = nullptr, bool* copied = nullptr)
 {
     if (copied) *copied = false;
+    bool tiled = tile_mode == 1;
+    if (tile_mode == 2) {
+        // Probe: classify ~1000 tiles spread over the batch (breadth-first part of k_tile_plan only) and estimate the share of
+        // far-field evaluations the tiled path would take off every query: far / (far + direct + ~half the conditional ones).
+        // Tiling pays off when that share is large (measured: cfg2 0.6 -> 1.33x faster; shares below ~0.4 -> slower).
+        const int64_t total_tiles = GRID ? (int64_t)a.tiles_x * a.tiles_y * ((grid_layers + 7) / 8) : (n + wn::kTileQueries - 1) / wn::kTileQueries;
+        const int stride = (int)std::max<int64_t>(1, total_tiles / 1024);
+        const int blocks = (int)((total_tiles + stride - 1) / stride);
+        WN_CUDA(e->s_stats.reserve(16 * sizeof(unsigned long long)));
+        unsigned long long* d_probe = (unsigned long long*)e->s_stats.p + 8;
+        WN_CUDA(cudaMemsetAsync(d_probe, 0, 5 * sizeof(unsigned long long), st));
+        wn::QueryArgs p = a;
+        p.probe_stride = stride;
+        p.probe = d_probe;
+        p.tile_z0 = 0;
+        p.tile_base = 0;
+        p.kappa = tile_kappa();
+        p.stats = nullptr;
+        wn::k_tile_plan<GRID><<<blocks, wn::kPlanThreads, 0, st>>>(p);
+        unsigned long long h[5];
+        WN_CUDA(cudaMemcpyAsync(h, d_probe, sizeof(h), cudaMemcpyDeviceToHost, st));
+        WN_CUDA(cudaStreamSynchronize(st));
+        const double far = (double)h[0], cond = (double)h[1], dir = (double)h[2];
+        const double share = far / (far + dir + 0.5 * cond + 1e-9);
+        const char* thr = getenv("WN_TILE_MIN_SHARE");
+        tiled = share >= (thr && *thr ? atof(thr) : 0.45) && (double)h[4] < 0.5 * blocks;
+        e->last_probe_share = (float)share;
+        if (env_int("WN_VERBOSE", 0))
+            fprintf(stderr, "[wn_b200] tiling probe: %d tiles, far %.0f cond %.0f direct %.0f exact %.0f fallback %.0f -> share %.3f -> %s\n", blocks,
+                    far, cond, dir, (double)h[3], (double)h[4], share, tiled ? "tiled" : "generic");
+    }
     if (stats) {
         WN_CUDA(e->s_stats.reserve(4 * sizeof(unsigned long long)));
         WN_CUDA(cudaMemsetAsync(e->s_stats.p, 0, 4 * sizeof(unsigned long long), st));

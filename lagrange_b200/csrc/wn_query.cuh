@@ -87,6 +87,8 @@ struct QueryArgs
     unsigned long long* plan_cursor; // bump allocator over the arena (reset before every k_tile_plan launch)
     long long plan_arena_bytes;
     float kappa;              // far set needs |c - P| >= kappa * tile radius and |c - P| - R >= kappa/2 * tile radius
+    int probe_stride;         // > 0: k_tile_plan only classifies every probe_stride-th tile and adds the class sizes to `probe`
+    unsigned long long* probe; // [5] far, conditional, direct, exact records, fallback tiles
 };
 
 struct TravCounters
@@ -437,13 +439,16 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
     __shared__ long long s_off;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const WnTreeView& t = a.tree;
+    // probe mode (probe_stride > 0): classify every probe_stride-th tile only and add up the class sizes, so that the host
+    // can decide whether the tiled path pays off for this batch (it does when the far set is a large share of the work)
+    const int tile = a.probe_stride > 0 ? (int)blockIdx.x * a.probe_stride : (int)blockIdx.x;
 
     // ---- tile bounding sphere ------------------------------------------------------------------------------------
     if (GRID) {
         if (tid == 0) {
-            const int bx = blockIdx.x % a.tiles_x;
-            const int by = (blockIdx.x / a.tiles_x) % a.tiles_y;
-            const int bz = blockIdx.x / (a.tiles_x * a.tiles_y) + a.tile_z0;
+            const int bx = tile % a.tiles_x;
+            const int by = (tile / a.tiles_x) % a.tiles_y;
+            const int bz = tile / (a.tiles_x * a.tiles_y) + a.tile_z0;
             const float lx = wn_lattice_coord(a.g.ox, a.g.sx, bx * 8), hx = wn_lattice_coord(a.g.ox, a.g.sx, bx * 8 + 7);
             const float ly = wn_lattice_coord(a.g.oy, a.g.sy, by * 8), hy = wn_lattice_coord(a.g.oy, a.g.sy, by * 8 + 7);
             const float lz = wn_lattice_coord(a.g.oz, a.g.sz, a.g.z0 + bz * 8), hz = wn_lattice_coord(a.g.oz, a.g.sz, a.g.z0 + bz * 8 + 7);
@@ -456,7 +461,7 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
         }
     } else {
         float lo[3] = {3.4e38f, 3.4e38f, 3.4e38f}, hi[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
-        const int64_t base = ((int64_t)blockIdx.x + a.tile_base) * kTileQueries;
+        const int64_t base = ((int64_t)tile + a.tile_base) * kTileQueries;
         for (int k = tid; k < kTileQueries; k += kPlanThreads) {
             const int64_t s = base + k;
             if (s < a.n) {
@@ -575,6 +580,16 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
     __syncthreads();
     bool fallback = s_cnt[4] != 0;
     const int n_cond = fallback ? 0 : s_cnt[2], n_far = fallback ? 0 : s_cnt[3], n_dir = fallback ? 0 : s_cnt[5], n_ex = fallback ? 0 : s_cnt[6];
+    if (a.probe_stride > 0) {
+        if (tid == 0) {
+            atomicAdd(a.probe + 0, (unsigned long long)n_far);
+            atomicAdd(a.probe + 1, (unsigned long long)n_cond);
+            atomicAdd(a.probe + 2, (unsigned long long)n_dir);
+            atomicAdd(a.probe + 3, (unsigned long long)n_ex);
+            atomicAdd(a.probe + 4, (unsigned long long)(fallback ? 1 : 0));
+        }
+        return;
+    }
 
     // ---- back to depth-first order. The atomics above appended in arbitrary order; sorting restores the order the skip
     //      links need and makes every sum deterministic. Short lists (the usual case) are sorted by one warp each, in
