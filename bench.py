@@ -195,7 +195,7 @@ def main():
     import torch
 
     import lagrange_b200 as lb
-    from lagrange_b200.distributed import replicate_engine, slab_range
+    from lagrange_b200.distributed import interleaved_layers, replicate_engine
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -239,14 +239,18 @@ def main():
         bcast_ms = 1e3 * (time.perf_counter() - t0)
 
     nz = int(dims[2])
-    z0, z1 = slab_range(nz, rank, world, align=8)
-    n_local = int(dims[0] * dims[1]) * (z1 - z0)
+    # rank r classifies the tile layers r, r+N, r+2N, ... (8 z-planes each): same mix of work on every rank
+    ranges = interleaved_layers(nz, rank, world, depth=8)
+    per_layer = int(dims[0] * dims[1])
+    offsets = np.concatenate([[0], np.cumsum([(b - a) * per_layer for a, b in ranges])]).astype(np.int64)
+    n_local = int(offsets[-1])
     n_total = int(dims[0] * dims[1] * dims[2])
     out_dev = torch.empty(max(n_local, 1), dtype=torch.uint8, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     def step_device():
-        eng.query_grid(origin, spacing, dims, z_range=(z0, z1), want_inside=True, out_inside=out_dev)
+        for (za, zb), off in zip(ranges, offsets):
+            eng.query_grid(origin, spacing, dims, z_range=(za, zb), want_inside=True, out_inside=out_dev[off:off + (zb - za) * per_layer])
 
     def barrier():
         torch.cuda.synchronize()
@@ -278,15 +282,19 @@ def main():
 
     # ---- e2e: the public API with a HOST output buffer (pinned), D2H inside the timed region --------------------------------
     out_host = torch.empty(max(n_local, 1), dtype=torch.uint8).pin_memory().numpy()
+    def step_host():
+        for (za, zb), off in zip(ranges, offsets):
+            eng.query_grid(origin, spacing, dims, z_range=(za, zb), want_inside=True, out_inside=out_host[off:off + (zb - za) * per_layer])
+
     for _ in range(2):
-        eng.query_grid(origin, spacing, dims, z_range=(z0, z1), want_inside=True, out_inside=out_host)
+        step_host()
     barrier()
     e2e_times = []
     for _ in range(max(3, min(args.steps, 5))):
         flush.fill_(1)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        eng.query_grid(origin, spacing, dims, z_range=(z0, z1), want_inside=True, out_inside=out_host)
+        step_host()
         checksum = int(out_host[::4097].sum())  # the caller reads the result
         e2e_times.append(time.perf_counter() - t0)
     t = torch.tensor([float(np.mean(e2e_times)) * 1e3], dtype=torch.float64, device="cuda")
@@ -306,8 +314,16 @@ def main():
 
     # ---- roofline (rank 0): flops EXECUTED by the timed kernels (their own counters), FMA peak measured live -----------------
     tiled = os.environ.get("WN_TILE", "1") != "0"
-    executed = eng.query_stats_grid(origin, spacing, dims, z_range=(z0, z1), tiling=tiled)
-    per_point = eng.query_stats_grid(origin, spacing, dims, z_range=(z0, z1), tiling=False)
+    def summed_stats(tiling):
+        tot = {}
+        for za, zb in ranges:
+            st = eng.query_stats_grid(origin, spacing, dims, z_range=(za, zb), tiling=tiling)
+            for k, v in st.items():
+                tot[k] = tot.get(k, 0) + v
+        return tot
+
+    executed = summed_stats(tiled)
+    per_point = summed_stats(False)
     nq = max(1, executed["queries"])
     # SURVEY.md 8(d) units (10 / 83 / 75 flop) + the far-field interpolation of the tiled path: 64 FMA + ~60 for the weights
     interp_flops = (2 * 64 + 60) if tiled else 0
@@ -351,14 +367,15 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": name, "queries_per_step": n_total, "sharding": f"{world} z-slab(s), tree built on rank 0 and broadcast",
+        "config": {"workload": name, "queries_per_step": n_total, "sharding": f"tile layers (8 z-planes) round-robin over {world} rank(s), tree built on rank 0 and broadcast",
                    "l2": "flushed between timed steps (256 MiB fill); tree %.0f MB" % (build_info.get("tree_bytes", 0) / 1e6),
                    "leaf_size": args.leaf_size, "tiled": tiled},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 60, "d2h_bytes_per_step": n_total, "ms_per_step": e2e_ms,
                 "api": "FastWindingNumber.query_grid -> wn_query_grid with a pinned HOST output buffer (lattice is implicit: 60-byte descriptor in)"},
-        # per step and rank: tiled = 1 probe launch of k_tile_plan + (k_tile_plan + k_tile_query) per batch of <= 65536 tiles;
-        # generic = one k_query
-        "gpu_launches": args.steps * (1 + 2 * max(1, -(-((-(-(z1 - z0) // 8)) * (-(-int(dims[0]) // 8)) * (-(-int(dims[1]) // 8))) // 65536)) if tiled else 1),
+        # per step and rank 0: tiled = (k_tile_plan + k_tile_query) per batch of <= 65536 tiles of every z range (the probe that
+        # picks the path runs once, in the warm-up, and is remembered); generic = one k_query per z range
+        "gpu_launches": args.steps * sum((2 * max(1, -(-((-(-(zb - za) // 8)) * (-(-int(dims[0]) // 8)) * (-(-int(dims[1]) // 8))) // 65536)) if tiled else 1)
+                                         for za, zb in ranges),
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         "build": {k: build_info.get(k) for k in ("build_ms", "build_ms_morton", "build_ms_sort", "build_ms_hierarchy", "build_ms_moments",
                                                  "build_ms_pack", "build_wall_ms", "num_entries", "tree_bytes", "max_depth")},

@@ -193,6 +193,9 @@ struct wn_engine
     mutable PinnedBuf p_small;
     mutable cudaStream_t copy_stream = nullptr; // D2H of finished batches while the next batch computes
     mutable float last_probe_share = -1.0f;     // far-set share measured by the last tiling probe (diagnostics)
+    mutable float probe_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    mutable int probe_dims[3] = {0, 0, 0};
+    mutable bool probe_cache_valid = false, probe_cache_tiled = false;
 };
 
 namespace {
@@ -730,6 +733,18 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
 {
     if (copied) *copied = false;
     bool tiled = tile_mode == 1;
+    // The decision for a lattice is remembered per engine (key: lattice descriptor + beta), so that a caller that walks the
+    // same lattice slab by slab (multi-GPU sharding, streaming) pays for the probe and its host synchronisation once.
+    float key[8] = {0, 0, 0, 0, 0, 0, a.beta2, tile_kappa()};
+    int kdims[3] = {0, 0, 0};
+    if (GRID) {
+        key[0] = a.g.ox, key[1] = a.g.oy, key[2] = a.g.oz, key[3] = a.g.sx, key[4] = a.g.sy, key[5] = a.g.sz;
+        kdims[0] = a.g.nx, kdims[1] = a.g.ny, kdims[2] = a.g.nz;
+        if (tile_mode == 2 && e->probe_cache_valid && memcmp(key, e->probe_key, sizeof(key)) == 0 && memcmp(kdims, e->probe_dims, sizeof(kdims)) == 0) {
+            tiled = e->probe_cache_tiled;
+            tile_mode = tiled ? 1 : 0;
+        }
+    }
     if (tile_mode == 2) {
         // Probe: classify ~1000 tiles spread over the batch (breadth-first part of k_tile_plan only) and estimate the share of
         // far-field evaluations the tiled path would take off every query: far / (far + direct + ~half the conditional ones).
@@ -756,6 +771,12 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
         const char* thr = getenv("WN_TILE_MIN_SHARE");
         tiled = share >= (thr && *thr ? atof(thr) : 0.45) && (double)h[4] < 0.5 * blocks;
         e->last_probe_share = (float)share;
+        if (GRID) {
+            memcpy(e->probe_key, key, sizeof(key));
+            memcpy(e->probe_dims, kdims, sizeof(kdims));
+            e->probe_cache_tiled = tiled;
+            e->probe_cache_valid = true;
+        }
         if (env_int("WN_VERBOSE", 0))
             fprintf(stderr, "[wn_b200] tiling probe: %d tiles, far %.0f cond %.0f direct %.0f exact %.0f fallback %.0f -> share %.3f -> %s\n", blocks,
                     far, cond, dir, (double)h[3], (double)h[4], share, tiled ? "tiled" : "generic");

@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from lagrange_b200.distributed import broadcast_packed, shard_range, slab_range
+from lagrange_b200.distributed import broadcast_packed, interleaved_layers, shard_range, slab_range
 
 
 def test_ranges_tile_exactly():
@@ -24,6 +24,23 @@ def test_ranges_tile_exactly():
             assert cuts[0][0] == 0 and cuts[-1][1] == nz
             assert all(cuts[i][1] == cuts[i + 1][0] for i in range(world - 1))
             assert all(a % 8 == 0 for a, _ in cuts)
+
+
+def test_interleaved_layers_tile_exactly_and_balance():
+    for nz in (512, 100, 37, 8, 1):
+        for world in (1, 2, 3, 4, 8):
+            covered = np.zeros(nz, dtype=int)
+            sizes = []
+            for r in range(world):
+                rs = interleaved_layers(nz, r, world, depth=8)
+                sizes.append(sum(b - a for a, b in rs))
+                for a, b in rs:
+                    assert 0 <= a < b <= nz and (a % 8 == 0)
+                    covered[a:b] += 1
+            assert np.all(covered == 1)
+            assert max(sizes) - min(sizes) <= 8
+    assert interleaved_layers(512, 0, 1) == [(0, 512)]
+    assert interleaved_layers(64, 1, 2) == [(8, 16), (24, 32), (40, 48), (56, 64)]
 
 
 def _free_port():
