@@ -151,6 +151,15 @@ WN_API wn_status wn_query_grid(const wn_engine* e, const float origin[3], const 
                                int64_t z_begin, int64_t z_end, float beta, uint32_t flags, float* out_omega, uint8_t* out_inside,
                                void* stream);
 
+/* Strided sharding of a lattice across GPUs: evaluates the tile layers (8 consecutive z-planes each, counted from z = 0)
+ * layer_first, layer_first + layer_step, layer_first + 2*layer_step, ... and stores them compactly in that order (each
+ * layer dims[0]*dims[1]*8 values, the lattice's last layer possibly fewer). With layer_step = number of ranks and
+ * layer_first = rank every rank gets the same mix of work in one call (contiguous z-slabs load-imbalance when the work is
+ * not uniform along z). */
+WN_API wn_status wn_query_grid_strided(const wn_engine* e, const float origin[3], const float spacing[3], const int64_t dims[3],
+                                       int64_t layer_first, int64_t layer_step, float beta, uint32_t flags, float* out_omega,
+                                       uint8_t* out_inside, void* stream);
+
 /* Counters of the traversal for a batch of points (same traversal as wn_solid_angle, results discarded). */
 WN_API wn_status wn_query_stats_points(const wn_engine* e, const float* q_xyz, int64_t n, float beta, uint32_t flags,
                                        wn_query_stats* stats, void* stream);

@@ -67,6 +67,7 @@ SIGNATURES = {
     "wn_solid_angle": (ctypes.c_int, [_vp, _vp, _i64, _f, _u32, _vp, _vp]),
     "wn_is_inside": (ctypes.c_int, [_vp, _vp, _i64, _f, _u32, _vp, _vp]),
     "wn_query_grid": (ctypes.c_int, [_vp, _f3, _f3, _l3, _i64, _i64, _f, _u32, _vp, _vp, _vp]),
+    "wn_query_grid_strided": (ctypes.c_int, [_vp, _f3, _f3, _l3, _i64, _i64, _f, _u32, _vp, _vp, _vp]),
     "wn_query_stats_points": (ctypes.c_int, [_vp, _vp, _i64, _f, _u32, ctypes.POINTER(wn_query_stats), _vp]),
     "wn_query_stats_grid": (ctypes.c_int, [_vp, _f3, _f3, _l3, _i64, _i64, _f, _u32, ctypes.POINTER(wn_query_stats), _vp]),
     "wn_exact": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),

@@ -758,7 +758,6 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
         wn::QueryArgs p = a;
         p.probe_stride = stride;
         p.probe = d_probe;
-        p.tile_z0 = 0;
         p.tile_base = 0;
         p.kappa = tile_kappa();
         p.stats = nullptr;
@@ -786,8 +785,9 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
         WN_CUDA(cudaMemsetAsync(e->s_stats.p, 0, 4 * sizeof(unsigned long long), st));
         a.stats = (unsigned long long*)e->s_stats.p;
     }
+    const int layer_first = a.tile_z0; // lattices: first tile layer (8 z-planes) of this call; 0 unless strided
     if (!tiled) {
-        const int qpl = pick_qpl(n);
+        const int qpl = (GRID && a.layer_step > 1) ? 2 : pick_qpl(n);
         int64_t blocks64;
         if (GRID) {
             const int tz = (int)((grid_layers + 4 * qpl - 1) / (4 * qpl));
@@ -836,10 +836,12 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
         for (int64_t u0 = 0; u0 < units; u0 += units_per_launch) {
             const int64_t nunits = std::min(units_per_launch, units - u0);
             const int blocks = (int)(nunits * tiles_per_unit);
-            if (GRID)
-                a.tile_z0 = (int)u0;
-            else
+            if (GRID) {
+                a.tile_z0 = layer_first + (int)u0 * a.layer_step;
+                a.out_layer0 = (int)u0;
+            } else {
                 a.tile_base = u0;
+            }
             WN_CUDA(cudaMemsetAsync(a.plan_cursor, 0, sizeof(unsigned long long), st));
             wn::k_tile_plan<GRID><<<blocks, wn::kPlanThreads, 0, st>>>(a);
             if (stats)
@@ -962,15 +964,29 @@ wn_status check_grid(const float* origin, const float* spacing, const int64_t* d
     return WN_OK;
 }
 
+// layer_step == 1: the z-slab [z0, z1). layer_step > 1: the tile layers (8 z-planes each, counted from z = 0) layer_first,
+// layer_first + layer_step, ... of the whole lattice, results stored compactly in that order (z0/z1 ignored).
 wn_status grid_impl(const wn_engine* e, const float* origin, const float* spacing, const int64_t* dims, int64_t z0, int64_t z1, float beta,
-                    uint32_t flags, float* out_omega, uint8_t* out_inside, wn_query_stats* stats, void* stream)
+                    uint32_t flags, float* out_omega, uint8_t* out_inside, wn_query_stats* stats, void* stream, int64_t layer_first = 0,
+                    int64_t layer_step = 1)
 {
     if (!e) return fail(WN_ERR_INVALID_ARGUMENT, "engine is null");
     if (!out_omega && !out_inside && !stats) return fail(WN_ERR_INVALID_ARGUMENT, "no output requested");
     wn::GridDesc g;
     int64_t n = 0;
+    if (layer_step > 1 && dims) {
+        z0 = 0;
+        z1 = dims[2];
+    }
     wn_status s = check_grid(origin, spacing, dims, z0, z1, g, n);
     if (s != WN_OK) return s;
+    int64_t local_planes = z1 - z0;
+    if (layer_step > 1) {
+        if (layer_first < 0 || layer_step > (1 << 20)) return fail(WN_ERR_INVALID_ARGUMENT, "bad layer_first / layer_step");
+        local_planes = 0;
+        for (int64_t L = layer_first; L * 8 < dims[2]; L += layer_step) local_planes += std::min<int64_t>(8, dims[2] - L * 8);
+        n = dims[0] * dims[1] * local_planes;
+    }
     if (stats) memset(stats, 0, sizeof(*stats));
     if (n == 0) return WN_OK;
     DeviceGuard guard(e->device);
@@ -990,8 +1006,11 @@ wn_status grid_impl(const wn_engine* e, const float* origin, const float* spacin
     a.out_inside = ob.d_inside;
     a.tiles_x = (g.nx + 7) / 8;
     a.tiles_y = (g.ny + 7) / 8;
+    a.layer_step = (int)std::max<int64_t>(1, layer_step);
+    a.tile_z0 = layer_step > 1 ? (int)layer_first : 0;
+    a.out_layer0 = 0;
     bool copied = false;
-    s = dispatch_query<true>(e, a, n, z1 - z0, want_tiling(e, n, flags, true), stats, st, &ob, &copied);
+    s = dispatch_query<true>(e, a, n, local_planes, want_tiling(e, n, flags, true), stats, st, &ob, &copied);
     if (s != WN_OK) return s;
     return copied ? WN_OK : finish_outputs(n, ob, st);
 }
@@ -1177,6 +1196,14 @@ wn_status wn_query_grid(const wn_engine* e, const float origin[3], const float s
                         int64_t z_end, float beta, uint32_t flags, float* out_omega, uint8_t* out_inside, void* stream)
 {
     return grid_impl(e, origin, spacing, dims, z_begin, z_end, beta, flags, out_omega, out_inside, nullptr, stream);
+}
+
+wn_status wn_query_grid_strided(const wn_engine* e, const float origin[3], const float spacing[3], const int64_t dims[3], int64_t layer_first,
+                                int64_t layer_step, float beta, uint32_t flags, float* out_omega, uint8_t* out_inside, void* stream)
+{
+    if (layer_step < 1) return fail(WN_ERR_INVALID_ARGUMENT, "layer_step must be >= 1");
+    if (layer_step == 1) return grid_impl(e, origin, spacing, dims, layer_first * 8, dims ? dims[2] : 0, beta, flags, out_omega, out_inside, nullptr, stream);
+    return grid_impl(e, origin, spacing, dims, 0, 0, beta, flags, out_omega, out_inside, nullptr, stream, layer_first, layer_step);
 }
 
 wn_status wn_query_stats_points(const wn_engine* e, const float* q_xyz, int64_t n, float beta, uint32_t flags, wn_query_stats* stats, void* stream)

@@ -75,6 +75,7 @@ struct QueryArgs
     // grid mode: block b covers lattice tile (b % tiles_x, (b / tiles_x) % tiles_y, b / (tiles_x*tiles_y) + tile_z0)
     GridDesc g;
     int tiles_x, tiles_y, tile_z0;
+    int layer_step, out_layer0; // strided layers: CTA layer l -> lattice layer tile_z0 + l*layer_step, output layer out_layer0 + l
     // outputs (either may be null)
     float* out_omega;
     uint8_t* out_inside;
@@ -248,17 +249,22 @@ __device__ __forceinline__ void grid_points(const QueryArgs& a, float (&qx)[QPL]
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int bx = blockIdx.x % a.tiles_x;
     const int by = (blockIdx.x / a.tiles_x) % a.tiles_y;
-    const int bz = blockIdx.x / (a.tiles_x * a.tiles_y) + a.tile_z0;
+    // CTA layer l of this launch covers the lattice layer tile_z0 + l * layer_step (strided sharding across GPUs: every
+    // layer_step-th layer, results stored compactly: local layer out_layer0 + l)
+    const int l = blockIdx.x / (a.tiles_x * a.tiles_y);
+    const int bz = a.tile_z0 + l * a.layer_step;
     const int x = bx * 8 + (wid & 1) * 4 + (lane & 3);
     const int y = by * 8 + ((wid >> 1) & 1) * 4 + ((lane >> 2) & 3);
 #pragma unroll
     for (int k = 0; k < QPL; ++k) {
-        const int z = a.g.z0 + bz * (4 * QPL) + (wid >> 2) * (2 * QPL) + 2 * k + (lane >> 4);
+        const int dz = (wid >> 2) * (2 * QPL) + 2 * k + (lane >> 4);
+        const int z = a.g.z0 + bz * (4 * QPL) + dz;
+        const int zl = (a.out_layer0 + l) * (4 * QPL) + dz;
         valid[k] = x < a.g.nx && y < a.g.ny && z < a.g.z1;
         qx[k] = wn_lattice_coord(a.g.ox, a.g.sx, x);
         qy[k] = wn_lattice_coord(a.g.oy, a.g.sy, y);
         qz[k] = wn_lattice_coord(a.g.oz, a.g.sz, z);
-        oidx[k] = valid[k] ? ((int64_t)(z - a.g.z0) * a.g.ny + y) * a.g.nx + x : -1;
+        oidx[k] = valid[k] ? ((int64_t)zl * a.g.ny + y) * a.g.nx + x : -1;
     }
 }
 
@@ -448,7 +454,7 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
         if (tid == 0) {
             const int bx = tile % a.tiles_x;
             const int by = (tile / a.tiles_x) % a.tiles_y;
-            const int bz = tile / (a.tiles_x * a.tiles_y) + a.tile_z0;
+            const int bz = a.tile_z0 + (tile / (a.tiles_x * a.tiles_y)) * a.layer_step;
             const float lx = wn_lattice_coord(a.g.ox, a.g.sx, bx * 8), hx = wn_lattice_coord(a.g.ox, a.g.sx, bx * 8 + 7);
             const float ly = wn_lattice_coord(a.g.oy, a.g.sy, by * 8), hy = wn_lattice_coord(a.g.oy, a.g.sy, by * 8 + 7);
             const float lz = wn_lattice_coord(a.g.oz, a.g.sz, a.g.z0 + bz * 8), hz = wn_lattice_coord(a.g.oz, a.g.sz, a.g.z0 + bz * 8 + 7);

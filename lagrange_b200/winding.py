@@ -224,11 +224,15 @@ class FastWindingNumber:
         return o, s, d, z0, z1, n
 
     def query_grid(self, origin, spacing, dims, z_range=None, accuracy_scale=None, want_omega=False, want_inside=True, device_output=False,
-                   out_omega=None, out_inside=None, tiling=True):
+                   out_omega=None, out_inside=None, tiling=True, layers=None):
         """Evaluate the cell-centred lattice p = origin + spacing*(ijk+0.5), x fastest; returns (omega, inside) (None if not wanted).
 
-        ``device_output`` allocates torch CUDA outputs (results stay in HBM); otherwise numpy (copied to the host)."""
+        ``device_output`` allocates torch CUDA outputs (results stay in HBM); otherwise numpy (copied to the host).
+        ``layers=(first, step)``: strided multi-GPU sharding -- only the tile layers (8 z-planes each) first, first+step, ...
+        are evaluated and returned compactly in that order (see ``strided_layer_planes``)."""
         o, s, d, z0, z1, n = self._grid_args(origin, spacing, dims, z_range)
+        if layers is not None:
+            n = int(dims[0]) * int(dims[1]) * len(self.strided_layer_planes(int(dims[2]), *layers))
         def mk(dtype, given, want):
             if given is not None:
                 return given
@@ -243,9 +247,21 @@ class FastWindingNumber:
         ins = mk(np.uint8, out_inside, want_inside)
         pom = _Buf(om, np.float32, writable=True).ptr if om is not None else None
         pin = _Buf(ins, np.uint8, writable=True).ptr if ins is not None else None
-        self._check(self._lib.wn_query_grid(self._handle(), o, s, d, z0, z1, float(accuracy_scale or 0.0), self._flags(False, tiling), pom, pin,
-                                            _current_stream_ptr()))
+        if layers is not None:
+            self._check(self._lib.wn_query_grid_strided(self._handle(), o, s, d, int(layers[0]), int(layers[1]), float(accuracy_scale or 0.0),
+                                                        self._flags(False, tiling), pom, pin, _current_stream_ptr()))
+        else:
+            self._check(self._lib.wn_query_grid(self._handle(), o, s, d, z0, z1, float(accuracy_scale or 0.0), self._flags(False, tiling), pom,
+                                                pin, _current_stream_ptr()))
         return om, ins
+
+    @staticmethod
+    def strided_layer_planes(nz, first, step):
+        """z indices, in output order, of the planes that ``query_grid(layers=(first, step))`` evaluates."""
+        out = []
+        for layer in range(int(first), (nz + 7) // 8, int(step)):
+            out.extend(range(layer * 8, min(nz, layer * 8 + 8)))
+        return out
 
     def is_inside_grid(self, origin, spacing, dims, **kw):
         return self.query_grid(origin, spacing, dims, want_inside=True, want_omega=False, **kw)[1]

@@ -213,6 +213,31 @@ def test_grid_overload_equals_points_and_slabs_tile(lb, prim):
         del os.environ["WN_TILE"]
 
 
+def test_strided_layers_tile_the_lattice(lb, prim):
+    """Multi-GPU sharding primitive: layers r, r+N, ... of every rank together are the whole lattice, bit for bit."""
+    V, F = prim.generate_subdivided_sphere("icosahedron", 4)
+    eng = lb.FastWindingNumber(V, F)
+    o, s, d = prim.lattice_for_bbox([-1.0] * 3, [1.0] * 3, (40, 24, 53))  # nz not a multiple of 8: partial last layer
+    per = 40 * 24
+    for tiling_env in ("0", "1"):
+        os.environ["WN_TILE"] = tiling_env
+        try:
+            full_om, full_in = eng.query_grid(o, s, d, want_omega=True)
+            for world in (2, 3, 8):
+                seen = np.zeros(53, dtype=int)
+                for rank in range(world):
+                    planes = eng.strided_layer_planes(53, rank, world)
+                    om, ins = eng.query_grid(o, s, d, want_omega=True, layers=(rank, world))
+                    assert om.shape == (per * len(planes),)
+                    for k, z in enumerate(planes):
+                        assert np.array_equal(om[k * per:(k + 1) * per], full_om[z * per:(z + 1) * per])
+                        assert np.array_equal(ins[k * per:(k + 1) * per], full_in[z * per:(z + 1) * per])
+                        seen[z] += 1
+                assert np.all(seen == 1)
+        finally:
+            del os.environ["WN_TILE"]
+
+
 @pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5])
 @pytest.mark.parametrize("tree", ["lbvh", "oracle", "lbvh_leaf8"])
 def test_tiled_path_matches_generic_traversal(lb, oracle_mod, prim, cfg, tree):
