@@ -72,8 +72,8 @@ struct WnBuild
     // options
     int leaf_size, order, radius_mode, approx_single;
     // packed output
-    float4* hot;         // [n_entries * WN_HOT_F4]   see wn_pack_record
-    float4* cold;        // [n_entries * WN_COLD_F4]
+    float4* hot;         // [n_entries * 2]  (P, R2 | leaf) , (N, link bits)
+    float4* cold;        // [n_entries * 4]  quadratic + cubic form
     int4* kids;          // [n_entries] child entry indices of internal entries
     float4* tris;        // [nT*3]
     unsigned* tri_order; // [nT] triangle id at each depth-first position
@@ -278,13 +278,14 @@ WN_HD void wn_pack_node(const WnBuild& b, int node)
     } else {
         r2 = wn_box_corner_r2(d);
     }
-    float4 rec[WN_REC_F4];
+    float4 rec[6];
+    wn_pack_record(d, r2, leaf_entry, b.order, rec);
     const int link = leaf_entry ? wn_leaf_link(tf, b.ntri[node]) : idx + b.size[node];
-    wn_pack_record(d, r2, leaf_entry, b.order, link, rec);
+    rec[1].w = wn_int_as_float(link); // raw bits, never used as a number
+    b.hot[2 * (int64_t)idx] = rec[0];
+    b.hot[2 * (int64_t)idx + 1] = rec[1];
 #pragma unroll
-    for (int k = 0; k < WN_HOT_F4; ++k) b.hot[WN_HOT_F4 * (int64_t)idx + k] = rec[k];
-#pragma unroll
-    for (int k = 0; k < WN_COLD_F4; ++k) b.cold[WN_COLD_F4 * (int64_t)idx + k] = rec[WN_HOT_F4 + k];
+    for (int k = 0; k < 4; ++k) b.cold[4 * (int64_t)idx + k] = rec[2 + k];
     int kid[WN_MAX_WIDTH] = {-1, -1, -1, -1};
     if (!leaf_entry) {
         int cidx = idx + 1, n = 0;

@@ -129,12 +129,12 @@ size_t align_up(size_t v, size_t a)
 // Position independent packed tree: one device allocation, header first.
 struct PackedHeader
 {
-    uint64_t magic; // 'WNB200T3'
+    uint64_t magic; // 'WNB200T2'
     int64_t total_bytes;
     int64_t n_entries;
     int64_t n_tris;
-    int64_t off_hot;  // float4[WN_HOT_F4 * n_entries]   (wn_pack_record)
-    int64_t off_cold; // float4[WN_COLD_F4 * n_entries]
+    int64_t off_hot;  // float4[2 * n_entries]: (P, R2 | leaf), (N, link bits)
+    int64_t off_cold; // float4[4 * n_entries]: quadratic + cubic form
     int64_t off_kids;
     int64_t off_tris;
     int64_t off_tri_order;
@@ -147,7 +147,7 @@ struct PackedHeader
     int64_t num_tree_nodes;
     int64_t reserved[3];
 };
-constexpr uint64_t kMagic = 0x3354303032424e57ull; // 'WNB200T3'
+constexpr uint64_t kMagic = 0x3254303032424e57ull; // 'WNB200T2'
 
 PackedHeader make_header(int64_t n_entries, int64_t n_tris)
 {
@@ -156,9 +156,9 @@ PackedHeader make_header(int64_t n_entries, int64_t n_tris)
     h.magic = kMagic;
     size_t off = align_up(sizeof(PackedHeader), 256);
     h.off_hot = (int64_t)off;
-    off = align_up(off + (size_t)n_entries * WN_HOT_F4 * sizeof(float4), 256);
+    off = align_up(off + (size_t)n_entries * 2 * sizeof(float4), 256);
     h.off_cold = (int64_t)off;
-    off = align_up(off + (size_t)n_entries * WN_COLD_F4 * sizeof(float4), 256);
+    off = align_up(off + (size_t)n_entries * 4 * sizeof(float4), 256);
     h.off_kids = (int64_t)off;
     off = align_up(off + (size_t)n_entries * sizeof(int4), 256);
     h.off_tris = (int64_t)off;

@@ -132,9 +132,12 @@ WN_HD int wn_dec_tri(int c)
 }
 
 // Packed depth-first record array ("entries"). For entry i:
-//   centre P, radius R2 (sign bit set <=> leaf entry; R2 itself is >= 0, may be +inf), normal sum N,
-//   quadratic form  a1(r^) = sum q_ab r^_a r^_b  (6 coefficients), cubic form a2(r^) = sum c_abc r^_a r^_b r^_c  (10);
-//   memory form: see wn_pack_record
+//   rec[0][i] = (Px, Py, Pz, R2)          R2's sign bit set <=> leaf entry (R2 itself is >= 0; may be +inf)
+//   rec[1][i] = (Nx, Ny, Nz, link[i] as raw bits)
+//   rec[2][i] = (qxx, qyy, qzz, qxy)      quadratic form  a1(r^) = sum q_ab r^_a r^_b
+//   rec[3][i] = (qyz, qzx, cxxx, cyyy)    cubic form      a2(r^) = sum c_abc r^_a r^_b r^_c
+//   rec[4][i] = (czzz, cxyz, cxxy, cxxz)
+//   rec[5][i] = (cyyz, cyyx, czzx, czzy)
 //   link[i]   = internal: index of the first entry after this subtree (skip link, > i)
 //               leaf:     (first_triangle << 4) | (num_triangles - 1)   into the depth-first ordered triangle array
 #define WN_LEAF_COUNT_BITS 4
@@ -491,23 +494,7 @@ WN_HD void wn_local_to_ref23(const WnLocal& d, float* o)
 //   a2 = 1.5 x.(3 D + t0) - 7.5 (cubic terms)      = sum c_abc x_a x_b x_c (linear part folded in through |x|^2 = 1)
 //   Omega ~= (a0 + (a1 + a2 / l) / l) / l^2
 // order < 2 zeroes the cubic form, order < 1 the quadratic form.
-//
-// Memory form ("pair-duplicated"): Blackwell's packed FP32 instructions (FFMA2 / FMUL2 / FADD2, sm_100) do two FMAs per
-// issue slot on 64-bit register pairs. The query kernels put two query points of a lane in the two halves, so every node
-// coefficient is needed as the pair (c, c); storing it that way lets a 128-bit load deliver two ready-made pairs with no
-// register shuffling. Centre and normal are stored negated so that r = q + (-P) and a0 = x.(-N) need no negation.
-//   hot [0] = (-Px,-Px,-Py,-Py)      hot [1] = (-Pz,-Pz, R2|leaf sign, link bits)
-//   cold[0] = (-Nx,-Nx,-Ny,-Ny)      cold[1] = (-Nz,-Nz, qxx,qxx)    cold[2] = (qyy,qyy,qzz,qzz)    cold[3] = (qxy,qxy,qyz,qyz)
-//   cold[4] = (qzx,qzx,cxxx,cxxx)    cold[5] = (cyyy,cyyy,czzz,czzz) cold[6] = (cxyz,cxyz,cxxy,cxxy) cold[7] = (cxxz,cxxz,cyyz,cyyz)
-//   cold[8] = (cyyx,cyyx,czzx,czzx)  cold[9] = (czzy,czzy,0,0)
-#define WN_HOT_F4 2
-#define WN_COLD_F4 10
-#define WN_REC_F4 (WN_HOT_F4 + WN_COLD_F4)
-WN_HD float4 wn_dup2(float a, float b)
-{
-    return make_float4(a, a, b, b);
-}
-WN_HD void wn_pack_record(const WnLocal& d, float r2, bool leaf, int order, int link, float4* rec /* WN_REC_F4: hot then cold */)
+WN_HD void wn_pack_record(const WnLocal& d, float r2, bool leaf, int order, float4* rec /* 6 */)
 {
     const float Nxx = d.Nd[0], Nyy = d.Nd[1], Nzz = d.Nd[2];
     const float Cxy = d.Nxy + d.Nyx, Cyz = d.Nyz + d.Nzy, Czx = d.Nzx + d.Nxz;
@@ -525,22 +512,16 @@ WN_HD void wn_pack_record(const WnLocal& d, float r2, bool leaf, int order, int 
     if (order < 2) cxxx = cyyy = czzz = cxyz = cxxy = cxxz = cyyz = cyyx = czzx = czzy = 0.0f;
     if (order < 1) qxx = qyy = qzz = qxy = qyz = qzx = 0.0f;
     const float r2s = leaf ? wn_int_as_float(wn_float_as_int(r2) | (int)0x80000000) : r2;
-    rec[0] = wn_dup2(-d.P[0], -d.P[1]);
-    rec[1] = make_float4(-d.P[2], -d.P[2], r2s, wn_int_as_float(link)); // link: raw bits, never used as a number
-    rec[2] = wn_dup2(-d.N[0], -d.N[1]);
-    rec[3] = wn_dup2(-d.N[2], qxx);
-    rec[4] = wn_dup2(qyy, qzz);
-    rec[5] = wn_dup2(qxy, qyz);
-    rec[6] = wn_dup2(qzx, cxxx);
-    rec[7] = wn_dup2(cyyy, czzz);
-    rec[8] = wn_dup2(cxyz, cxxy);
-    rec[9] = wn_dup2(cxxz, cyyz);
-    rec[10] = wn_dup2(cyyx, czzx);
-    rec[11] = wn_dup2(czzy, 0.0f);
+    rec[0] = make_float4(d.P[0], d.P[1], d.P[2], r2s);
+    rec[1] = make_float4(d.N[0], d.N[1], d.N[2], 0.0f);
+    rec[2] = make_float4(qxx, qyy, qzz, qxy);
+    rec[3] = make_float4(qyz, qzx, cxxx, cyyy);
+    rec[4] = make_float4(czzz, cxyz, cxxy, cxxz);
+    rec[5] = make_float4(cyyz, cyyx, czzx, czzy);
 }
 
 // ----------------------------------------------------------------------------------------------------------------
-// Query arithmetic
+// Query arithmetic (fused multiply-adds welcome here)
 // ----------------------------------------------------------------------------------------------------------------
 WN_HD float wn_rsqrt(float x)
 {
@@ -564,54 +545,22 @@ WN_HD float wn_rsqrt_ftz(float x)
 #endif
 }
 
-// Scalar operation set with explicit rounding points (no compiler contraction): the packed float2 kernels apply exactly the
-// same sequence per component, so a point's result does not depend on which kernel variant evaluated it.
-#if defined(__CUDA_ARCH__)
-#define WN_FMA(a, b, c) __fmaf_rn((a), (b), (c))
-#else
-#define WN_FMA(a, b, c) fmaf((a), (b), (c))
-#endif
-
 // Far-field Taylor evaluation of one record at r = q - P with l2 = |r|^2 > 0 (A.5 folded, see wn_pack_record).
-// c = the record's WN_COLD_F4 cold float4 (pair-duplicated: .x and .z are the coefficients).
-WN_HD float wn_eval_record(float rx, float ry, float rz, float l2, const float4* c)
+WN_HD float wn_eval_record(float rx, float ry, float rz, float l2, const float4& f1, const float4& f2, const float4& f3,
+                           const float4& f4, const float4& f5)
 {
     const float m1 = wn_rsqrt_ftz(l2);
-    const float x = WN_MUL(rx, m1), y = WN_MUL(ry, m1), z = WN_MUL(rz, m1);
-    const float m2 = WN_MUL(m1, m1);
-    float a0 = WN_MUL(x, c[0].x);
-    a0 = WN_FMA(y, c[0].z, a0);
-    a0 = WN_FMA(z, c[1].x, a0);
-    // quadratic form: x (x qxx + y qxy + z qzx) + y (y qyy + z qyz) + z (z qzz)
-    float t = WN_MUL(x, c[1].z);
-    t = WN_FMA(y, c[3].x, t);
-    t = WN_FMA(z, c[4].x, t);
-    float u = WN_MUL(y, c[2].x);
-    u = WN_FMA(z, c[3].z, u);
-    const float w = WN_MUL(z, c[2].z);
-    float a1 = WN_MUL(x, t);
-    a1 = WN_FMA(y, u, a1);
-    a1 = WN_FMA(z, w, a1);
-    // cubic form: x (x (x cxxx + y cxxy + z cxxz) + y (y cyyx + z cxyz) + z (z czzx)) + y (y (y cyyy + z cyyz) + z (z czzy)) + z (z (z czzz))
-    float p = WN_MUL(x, c[4].z);
-    p = WN_FMA(y, c[6].z, p);
-    p = WN_FMA(z, c[7].x, p);
-    float q = WN_MUL(y, c[8].x);
-    q = WN_FMA(z, c[6].x, q);
-    const float s = WN_MUL(z, c[8].z);
-    float cx = WN_MUL(x, p);
-    cx = WN_FMA(y, q, cx);
-    cx = WN_FMA(z, s, cx);
-    float g = WN_MUL(y, c[5].x);
-    g = WN_FMA(z, c[7].z, g);
-    const float h = WN_MUL(z, c[9].x);
-    float cy = WN_MUL(y, g);
-    cy = WN_FMA(z, h, cy);
-    const float cz = WN_MUL(z, WN_MUL(z, c[5].z));
-    float a2 = WN_MUL(x, cx);
-    a2 = WN_FMA(y, cy, a2);
-    a2 = WN_FMA(z, cz, a2);
-    return WN_MUL(m2, WN_FMA(m1, WN_FMA(m1, a2, a1), a0));
+    const float x = rx * m1, y = ry * m1, z = rz * m1;
+    const float m2 = m1 * m1;
+    const float a0 = -(x * f1.x + y * f1.y + z * f1.z);
+    // quadratic form: x (x qxx + y qxy + z qzx) + y (y qyy + z qyz) + z z qzz
+    const float a1 = x * (x * f2.x + y * f2.w + z * f3.y) + y * (y * f2.y + z * f3.x) + z * (z * f2.z);
+    // cubic form
+    const float cx = x * (x * f3.z + y * f4.z + z * f4.w) + y * (y * f5.y + z * f4.y) + z * (z * f5.z);
+    const float cy = y * (y * f3.w + z * f5.x) + z * (z * f5.w);
+    const float cz = z * (z * f4.x);
+    const float a2 = x * cx + y * cy + z * cz;
+    return m2 * (a0 + m1 * (a1 + m1 * a2));
 }
 
 // Exact signed solid angle of triangle (a,b,c) seen from q (A.1, reference formulation incl. its two zero rules).
@@ -659,10 +608,10 @@ WN_HD float wn_lattice_coord(float origin, float spacing, int i)
 
 // One query point against the packed tree, one lane, no warp cooperation: the definition of the per-point result.
 // (Used by the host emulation harness and mirrored lane-wise by the warp kernel.)
-// Memory layout of the packed tree: a record (see wn_pack_record) is split in a hot and a cold part, each interleaved per
-// entry, so that one address computation serves every load of a visit:
-//   hot [WN_HOT_F4  * i + k]   centre (negated, pair-duplicated), R2 | leaf sign, link                32 B: one sector
-//   cold[WN_COLD_F4 * i + k]   normal (negated) + quadratic + cubic form, pair-duplicated             160 B
+// Memory layout of the packed tree: the six float4 of a record (see wn_pack_record) are split in a hot and a cold part,
+// each interleaved per entry, so that one address computation serves every load of a visit:
+//   hot [2*i + 0] = (Px, Py, Pz, R2 | leaf sign)     hot [2*i + 1] = (Nx, Ny, Nz, link bits)      32 B: one sector
+//   cold[4*i + k] = quadratic / cubic form coefficients (rec[2..5])                                  64 B: two sectors
 // A visit that only tests (the record is near for every lane) touches the hot sector alone.
 struct WnTreeView
 {
@@ -681,16 +630,17 @@ WN_HD float wn_traverse_point(const WnTreeView& t, float qx, float qy, float qz,
     // entry 0 is the root, which is never approximated (A.5): start at its first child unless the root is itself a leaf
     int i = t.n_entries > 1 ? 1 : 0;
     while (i < t.n_entries) {
-        const float4 f0 = t.hot[WN_HOT_F4 * (int64_t)i], f1 = t.hot[WN_HOT_F4 * (int64_t)i + 1];
+        const float4 f0 = t.hot[2 * (int64_t)i], f1 = t.hot[2 * (int64_t)i + 1];
         const int lk = wn_float_as_int(f1.w);
-        const bool leaf = wn_float_as_int(f1.z) < 0;
-        const float thr = WN_MUL(fabsf(f1.z), beta2);
-        const float rx = WN_ADD(qx, f0.x), ry = WN_ADD(qy, f0.z), rz = WN_ADD(qz, f1.x); // the record stores -P
+        const bool leaf = wn_float_as_int(f0.w) < 0;
+        const float thr = WN_MUL(fabsf(f0.w), beta2);
+        const float rx = qx - f0.x, ry = qy - f0.y, rz = qz - f0.z;
         const float l2 = WN_ADD(WN_ADD(WN_MUL(rx, rx), WN_MUL(ry, ry)), WN_MUL(rz, rz)); // unfused, like the reference
         bool near = l2 <= thr;
         if (cnt) cnt[0]++;
         if (!near) {
-            const float om = wn_eval_record(rx, ry, rz, l2, t.cold + WN_COLD_F4 * (int64_t)i);
+            const float4* c = t.cold + 4 * (int64_t)i;
+            const float om = wn_eval_record(rx, ry, rz, l2, f1, c[0], c[1], c[2], c[3]);
             if (fabsf(om) <= 3.402823466e38f) { // finite
                 acc += om;
                 if (cnt) cnt[1]++;

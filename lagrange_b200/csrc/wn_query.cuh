@@ -119,94 +119,18 @@ __device__ __forceinline__ int tile_key(int entry, bool leaf, int cls)
     return (entry << 3) | (leaf ? 4 : 0) | cls;
 }
 
-// accessors of the hot/cold record layout (wn_device.cuh, wn_pack_record / WnTreeView)
+// accessors of the hot/cold record layout (wn_device.cuh, WnTreeView)
 __device__ __forceinline__ float4 rec_hot(const WnTreeView& t, int e, int k)
 {
-    return __ldg(t.hot + WN_HOT_F4 * (int64_t)e + k);
+    return __ldg(t.hot + 2 * (int64_t)e + k);
 }
 __device__ __forceinline__ float4 rec_cold(const WnTreeView& t, int e, int k)
 {
-    return __ldg(t.cold + WN_COLD_F4 * (int64_t)e + k);
+    return __ldg(t.cold + 4 * (int64_t)e + k);
 }
 __device__ __forceinline__ int rec_link(const WnTreeView& t, int e)
 {
-    return __float_as_int(__ldg(&t.hot[WN_HOT_F4 * (int64_t)e + 1].w));
-}
-__device__ __forceinline__ bool rec_is_leaf(const WnTreeView& t, int e)
-{
-    return __float_as_int(__ldg(&t.hot[WN_HOT_F4 * (int64_t)e + 1].z)) < 0;
-}
-
-// ----------------------------------------------------------------------------------------------------------------
-// Arithmetic on one query (float) or on the two queries of a lane at once (float2, packed FFMA2 / FMUL2 / FADD2 of
-// sm_100: one issue slot for two FMAs). Both spell out the same IEEE operations per component, so results are identical.
-// ----------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float vmul(float a, float b) { return __fmul_rn(a, b); }
-__device__ __forceinline__ float vadd(float a, float b) { return __fadd_rn(a, b); }
-__device__ __forceinline__ float vfma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
-__device__ __forceinline__ float2 vmul(float2 a, float2 b) { return __fmul2_rn(a, b); }
-__device__ __forceinline__ float2 vadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
-__device__ __forceinline__ float2 vfma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
-__device__ __forceinline__ float vrsqrt(float a) { return wn_rsqrt_ftz(a); }
-__device__ __forceinline__ float2 vrsqrt(float2 a) { return make_float2(wn_rsqrt_ftz(a.x), wn_rsqrt_ftz(a.y)); }
-__device__ __forceinline__ float vget(float v, int) { return v; }
-__device__ __forceinline__ float vget(float2 v, int k) { return k ? v.y : v.x; }
-template <class T> __device__ __forceinline__ T vlo(const float4& f);  // first pair-duplicated coefficient of a float4
-template <class T> __device__ __forceinline__ T vhi(const float4& f);  // second
-template <> __device__ __forceinline__ float vlo<float>(const float4& f) { return f.x; }
-template <> __device__ __forceinline__ float vhi<float>(const float4& f) { return f.z; }
-template <> __device__ __forceinline__ float2 vlo<float2>(const float4& f) { return make_float2(f.x, f.y); }
-template <> __device__ __forceinline__ float2 vhi<float2>(const float4& f) { return make_float2(f.z, f.w); }
-template <int QPL> struct VecOf { using type = float; };
-template <> struct VecOf<2> { using type = float2; };
-template <class T> __device__ __forceinline__ T vmake(const float* v);
-template <> __device__ __forceinline__ float vmake<float>(const float* v) { return v[0]; }
-template <> __device__ __forceinline__ float2 vmake<float2>(const float* v) { return make_float2(v[0], v[1]); }
-
-// Far-field Taylor evaluation (A.5 folded), same operation sequence as wn_eval_record. c = the record's 10 cold float4.
-template <class T>
-__device__ __forceinline__ T eval_cold(const T rx, const T ry, const T rz, const T l2, const float4 (&c)[WN_COLD_F4])
-{
-    const T m1 = vrsqrt(l2);
-    const T x = vmul(rx, m1), y = vmul(ry, m1), z = vmul(rz, m1);
-    const T m2 = vmul(m1, m1);
-    T a0 = vmul(x, vlo<T>(c[0]));
-    a0 = vfma(y, vhi<T>(c[0]), a0);
-    a0 = vfma(z, vlo<T>(c[1]), a0);
-    T t = vmul(x, vhi<T>(c[1]));
-    t = vfma(y, vlo<T>(c[3]), t);
-    t = vfma(z, vlo<T>(c[4]), t);
-    T u = vmul(y, vlo<T>(c[2]));
-    u = vfma(z, vhi<T>(c[3]), u);
-    const T w = vmul(z, vhi<T>(c[2]));
-    T a1 = vmul(x, t);
-    a1 = vfma(y, u, a1);
-    a1 = vfma(z, w, a1);
-    T p = vmul(x, vhi<T>(c[4]));
-    p = vfma(y, vhi<T>(c[6]), p);
-    p = vfma(z, vlo<T>(c[7]), p);
-    T q = vmul(y, vlo<T>(c[8]));
-    q = vfma(z, vlo<T>(c[6]), q);
-    const T s = vmul(z, vhi<T>(c[8]));
-    T cx = vmul(x, p);
-    cx = vfma(y, q, cx);
-    cx = vfma(z, s, cx);
-    T g = vmul(y, vlo<T>(c[5]));
-    g = vfma(z, vhi<T>(c[7]), g);
-    const T h = vmul(z, vlo<T>(c[9]));
-    T cy = vmul(y, g);
-    cy = vfma(z, h, cy);
-    const T cz = vmul(z, vmul(z, vhi<T>(c[5])));
-    T a2 = vmul(x, cx);
-    a2 = vfma(y, cy, a2);
-    a2 = vfma(z, cz, a2);
-    return vmul(m2, vfma(m1, vfma(m1, a2, a1), a0));
-}
-
-__device__ __forceinline__ void load_cold(const float4* __restrict__ cp, float4 (&c)[WN_COLD_F4])
-{
-#pragma unroll
-    for (int k = 0; k < WN_COLD_F4; ++k) c[k] = __ldg(cp + k);
+    return __float_as_int(__ldg(&t.hot[2 * (int64_t)e + 1].w));
 }
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -220,13 +144,11 @@ __device__ __forceinline__ bool warp_traverse(const WnTreeView& t, const float b
                                               const float (&qz)[QPL], const bool (&valid)[QPL], float (&acc)[QPL], const int2* s_items,
                                               const int n_items, TravCounters& cnt)
 {
-    using T = typename VecOf<QPL>::type;
     const int lane = threadIdx.x & 31;
     const float4* __restrict__ hot = t.hot;
     const float4* __restrict__ cold = t.cold;
     const float4* __restrict__ tris = t.tri;
     const int n = LISTED ? n_items : t.n_entries;
-    const T vqx = vmake<T>(qx), vqy = vmake<T>(qy), vqz = vmake<T>(qz);
     int skip[QPL];
 #pragma unroll
     for (int k = 0; k < QPL; ++k) skip[k] = valid[k] ? 0 : n;
@@ -243,25 +165,28 @@ __device__ __forceinline__ bool warp_traverse(const WnTreeView& t, const float b
             notest = (it.x & 3) == kClsCondFar;
             after = it.y;
         }
-        // one address, one 32-byte sector: centre (negated, pair-duplicated), radius | leaf, link
-        const float4* __restrict__ hp = hot + WN_HOT_F4 * (int64_t)e;
+        // one address, one 32-byte sector: centre + radius, normal + link
+        const float4* __restrict__ hp = hot + 2 * (int64_t)e;
         const float4 f0 = __ldg(hp), f1 = __ldg(hp + 1);
         const int lk = __float_as_int(f1.w);
         if (!LISTED) {
-            leaf = __float_as_int(f1.z) < 0;
+            leaf = __float_as_int(f0.w) < 0;
             after = leaf ? i + 1 : lk;
         }
         // Unfused, like the reference: a decision flipped by an FMA's single rounding would change Omega by that record's
         // whole truncation error (~1e-4 * 4 pi at beta = 2).
-        const float thr = __fmul_rn(fabsf(f1.z), beta2);
-        const T rx = vadd(vqx, vlo<T>(f0)), ry = vadd(vqy, vhi<T>(f0)), rz = vadd(vqz, vlo<T>(f1)); // q + (-P)
-        const T l2 = vadd(vadd(vmul(rx, rx), vmul(ry, ry)), vmul(rz, rz));
+        const float thr = __fmul_rn(fabsf(f0.w), beta2);
+        float rx[QPL], ry[QPL], rz[QPL], l2[QPL];
         bool nearq[QPL], farq[QPL];
         bool anyfar = false;
 #pragma unroll
         for (int k = 0; k < QPL; ++k) {
             const bool active = i >= skip[k];
-            const bool nr = (LISTED && notest) ? false : (vget(l2, k) <= thr);
+            rx[k] = qx[k] - f0.x;
+            ry[k] = qy[k] - f0.y;
+            rz[k] = qz[k] - f0.z;
+            l2[k] = __fadd_rn(__fadd_rn(__fmul_rn(rx[k], rx[k]), __fmul_rn(ry[k], ry[k])), __fmul_rn(rz[k], rz[k]));
+            const bool nr = (LISTED && notest) ? false : (l2[k] <= thr);
             nearq[k] = active && nr;
             farq[k] = active && !nr;
             anyfar |= farq[k];
@@ -269,15 +194,14 @@ __device__ __forceinline__ bool warp_traverse(const WnTreeView& t, const float b
         }
         if (STATS) cnt.V += (lane == 0) ? 32 * QPL : 0;
         if (__any_sync(kFull, anyfar)) {
-            float4 c[WN_COLD_F4];
-            load_cold(cold + WN_COLD_F4 * (int64_t)e, c);
-            const T om = eval_cold<T>(rx, ry, rz, l2, c);
+            const float4* __restrict__ cp = cold + 4 * (int64_t)e;
+            const float4 f2 = __ldg(cp), f3 = __ldg(cp + 1), f4 = __ldg(cp + 2), f5 = __ldg(cp + 3);
 #pragma unroll
             for (int k = 0; k < QPL; ++k) {
                 if (farq[k]) {
-                    const float o = vget(om, k);
-                    if (fabsf(o) <= 3.402823466e38f) {
-                        acc[k] += o;
+                    const float om = wn_eval_record(rx[k], ry[k], rz[k], l2[k], f1, f2, f3, f4, f5);
+                    if (fabsf(om) <= 3.402823466e38f) {
+                        acc[k] += om;
                         skip[k] = after;
                         if (STATS) ++cnt.A;
                     } else {
@@ -624,12 +548,11 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
         for (int idx = tid; idx < F; idx += kPlanThreads) {
             const int word = s_front[cur][idx];
             const int e = word & 0x3fffffff, manc = (word >> 30) & 1;
-            const float4 f0 = rec_hot(t, e, 0), f1 = rec_hot(t, e, 1);
+            const float4 f0 = rec_hot(t, e, 0);
             const int4 k4 = __ldg(t.kids + e);
-            const bool leaf = __float_as_int(f1.z) < 0;
-            const float R2 = fabsf(f1.z);
-            const float thr = R2 * a.beta2;
-            const float dx = cx + f0.x, dy = cy + f0.z, dz = cz + f1.x; // the record stores -P
+            const bool leaf = __float_as_int(f0.w) < 0;
+            const float thr = fabsf(f0.w) * a.beta2;
+            const float dx = cx - f0.x, dy = cy - f0.y, dz = cz - f0.z;
             const float D = sqrtf(dx * dx + dy * dy + dz * dz);
             const float dm = D - ra, dp = D + ra;
             const bool allfar = dm > 0.0f && dm * dm > thr * 1.0001f;
@@ -639,7 +562,7 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
                 // both to the expansion centre and to the nearest possible source point (bounding sphere of radius R)
                 if (manc)
                     plan_append(s_cond, &s_cnt[2], kTileAllCap, tile_key(e, leaf, kClsCondFar), &s_cnt[4]);
-                else if (D >= a.kappa * ra && D - sqrtf(R2) >= 0.5f * a.kappa * ra)
+                else if (D >= a.kappa * ra && D - sqrtf(fabsf(f0.w)) >= 0.5f * a.kappa * ra)
                     plan_append(s_far, &s_cnt[3], kTileFarCap, e, &s_cnt[4]);
                 else
                     plan_append(s_dir, &s_cnt[5], kTileDirCap, e, &s_cnt[4]);
@@ -715,7 +638,7 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
 
     // ---- packet allocation and contents ---------------------------------------------------------------------------------
     const long long cond_bytes = ((long long)n_cond * 8 + 15) & ~15ll;
-    const long long bytes = cond_bytes + (long long)n_dir * (WN_REC_F4 * 16) + (long long)n_tri * 48;
+    const long long bytes = cond_bytes + (long long)n_dir * 96 + (long long)n_tri * 48;
     if (tid == 0 && !fallback && bytes > 0) {
         const long long off = (long long)atomicAdd(a.plan_cursor, (unsigned long long)bytes);
         if (off + bytes > a.plan_arena_bytes) s_cnt[4] = 1; // arena exhausted: generic path for this tile
@@ -727,7 +650,7 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
         char* pk = a.plan_arena + s_off;
         int2* out_cond = reinterpret_cast<int2*>(pk);
         float4* out_dir = reinterpret_cast<float4*>(pk + cond_bytes);
-        float4* out_tri = out_dir + (long long)n_dir * WN_REC_F4;
+        float4* out_tri = out_dir + (long long)n_dir * 6;
         for (int j = tid; j < n_cond; j += kPlanThreads) {
             // skip link in list coordinates: first conditional record at or after the end of this record's subtree
             const int key = s_cond[j], e = key >> 3;
@@ -743,9 +666,9 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
             }
             out_cond[j] = make_int2(key, lo);
         }
-        for (int j = tid; j < n_dir * WN_REC_F4; j += kPlanThreads) {
-            const int e = s_dir[j / WN_REC_F4], r = j % WN_REC_F4;
-            out_dir[j] = r < WN_HOT_F4 ? rec_hot(t, e, r) : rec_cold(t, e, r - WN_HOT_F4);
+        for (int j = tid; j < n_dir * 6; j += kPlanThreads) {
+            const int e = s_dir[j / 6], r = j % 6;
+            out_dir[j] = r < 2 ? rec_hot(t, e, r) : rec_cold(t, e, r - 2);
         }
         for (int j = tid; j < n_ex; j += kPlanThreads) {
             const int lk = rec_link(t, s_exact[j]);
@@ -756,7 +679,7 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
     }
 
     // ---- far set: sample its field at the 4^3 Chebyshev points of the tile's box -----------------------------------
-    float2 sacc = make_float2(0.0f, 0.0f);
+    float sacc[2] = {0.0f, 0.0f};
     bool bad = false;
     if (!fallback) {
         float px[2], py[2], pz[2];
@@ -767,20 +690,21 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
             py[k] = cy + hy * cheb_node((s >> 2) & 3);
             pz[k] = cz + hz * cheb_node(s >> 4);
         }
-        const float2 vpx = make_float2(px[0], px[1]), vpy = make_float2(py[0], py[1]), vpz = make_float2(pz[0], pz[1]);
         for (int m = wid; m < n_far; m += kPlanWarps) {
             const int e = s_far[m];
-            const float4 f0 = rec_hot(t, e, 0), f1 = rec_hot(t, e, 1);
-            float4 c[WN_COLD_F4];
-            load_cold(t.cold + WN_COLD_F4 * (int64_t)e, c);
-            const float2 rx = vadd(vpx, vlo<float2>(f0)), ry = vadd(vpy, vhi<float2>(f0)), rz = vadd(vpz, vlo<float2>(f1));
-            const float2 l2 = vfma(rz, rz, vfma(ry, ry, vmul(rx, rx)));
-            const float2 om = eval_cold<float2>(rx, ry, rz, l2, c);
-            bad = bad || !(fabsf(om.x) <= 3.402823466e38f) || !(fabsf(om.y) <= 3.402823466e38f);
-            sacc = vadd(sacc, om);
+            const float4 f0 = rec_hot(t, e, 0), f1 = rec_hot(t, e, 1), f2 = rec_cold(t, e, 0), f3 = rec_cold(t, e, 1),
+                         f4 = rec_cold(t, e, 2), f5 = rec_cold(t, e, 3);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const float rx = px[k] - f0.x, ry = py[k] - f0.y, rz = pz[k] - f0.z;
+                const float l2 = rx * rx + ry * ry + rz * rz;
+                const float om = wn_eval_record(rx, ry, rz, l2, f1, f2, f3, f4, f5);
+                bad = bad || !(fabsf(om) <= 3.402823466e38f);
+                sacc[k] += om;
+            }
         }
-        s_samp[wid][lane] = sacc.x;
-        s_samp[wid][lane + 32] = sacc.y;
+        s_samp[wid][lane] = sacc[0];
+        s_samp[wid][lane + 32] = sacc[1];
     }
     fallback = __syncthreads_or((int)(bad || fallback)) != 0;
     float* sout = a.plan_samples + (int64_t)blockIdx.x * kTileSampleStride;
@@ -838,18 +762,17 @@ __global__ void __launch_bounds__(kQueryThreads) k_tile_query(const QueryArgs a)
     if (!fallback) {
         // ---- direct records: far for every point of the tile; gathered contiguously by the plan ---------------------
         const float4* __restrict__ dr = reinterpret_cast<const float4*>(pk + (((long long)hdr.n_cond * 8 + 15) & ~15ll));
-        const float2 vqx = make_float2(qx[0], qx[1]), vqy = make_float2(qy[0], qy[1]), vqz = make_float2(qz[0], qz[1]);
         for (int j = 0; j < hdr.n_dir; ++j) {
-            const float4 f0 = __ldg(dr + 0), f1 = __ldg(dr + 1);
-            float4 c[WN_COLD_F4];
-            load_cold(dr + WN_HOT_F4, c);
-            dr += WN_REC_F4;
-            const float2 rx = vadd(vqx, vlo<float2>(f0)), ry = vadd(vqy, vhi<float2>(f0)), rz = vadd(vqz, vlo<float2>(f1));
-            const float2 l2 = vadd(vadd(vmul(rx, rx), vmul(ry, ry)), vmul(rz, rz)); // as in warp_traverse
-            const float2 om = eval_cold<float2>(rx, ry, rz, l2, c);
-            bad = bad || (valid[0] && !(fabsf(om.x) <= 3.402823466e38f)) || (valid[1] && !(fabsf(om.y) <= 3.402823466e38f));
-            acc[0] += om.x;
-            acc[1] += om.y;
+            const float4 f0 = __ldg(dr + 0), f1 = __ldg(dr + 1), f2 = __ldg(dr + 2), f3 = __ldg(dr + 3), f4 = __ldg(dr + 4), f5 = __ldg(dr + 5);
+            dr += 6;
+#pragma unroll
+            for (int k = 0; k < QPL; ++k) {
+                const float rx = qx[k] - f0.x, ry = qy[k] - f0.y, rz = qz[k] - f0.z;
+                const float l2 = __fadd_rn(__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)), __fmul_rn(rz, rz)); // as in warp_traverse
+                const float om = wn_eval_record(rx, ry, rz, l2, f1, f2, f3, f4, f5);
+                bad = bad || (valid[k] && !(fabsf(om) <= 3.402823466e38f));
+                acc[k] += om;
+            }
         }
         // ---- exact triangles: leaves that are near for every point of the tile ------------------------------------------
         const float4* __restrict__ tr = dr; // triangles follow the direct records in the packet

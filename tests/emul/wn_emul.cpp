@@ -129,8 +129,8 @@ void* emul_build(const float* v, int64_t nV, const int32_t* tri, int64_t nT, con
             for (int l = 0; l < b.nL; ++l) wn_vertex_radius_leaf(b, l);
     }
     const int n_entries = (e->err == 0 && nT > 0) ? e->size[0] : 0;
-    e->hot.resize((size_t)n_entries * WN_HOT_F4);
-    e->cold.resize((size_t)n_entries * WN_COLD_F4);
+    e->hot.resize((size_t)n_entries * 2);
+    e->cold.resize((size_t)n_entries * 4);
     b.hot = e->hot.data();
     b.cold = e->cold.data();
     e->kids.resize(n_entries);
@@ -203,20 +203,11 @@ void emul_get_packed(void* h, float* rec, int32_t* link, float* tris, uint32_t* 
     Emul* e = static_cast<Emul*>(h);
     // de-interleave the hot/cold layout back into the six logical float4 arrays + link
     const size_t n = e->kids.size();
-    // logical view for the tests: rec[0] = (P, R2|leaf), rec[1] = (N, 0), rec[2..5] = the 16 form coefficients in the order
-    // qxx qyy qzz qxy | qyz qzx cxxx cyyy | czzz cxyz cxxy cxxz | cyyz cyyx czzx czzy
     for (size_t i = 0; i < n; ++i) {
-        const float4* h = &e->hot[WN_HOT_F4 * i];
-        const float4* c = &e->cold[WN_COLD_F4 * i];
-        const float r0[4] = {-h[0].x, -h[0].z, -h[1].x, h[1].z};
-        const float r1[4] = {-c[0].x, -c[0].z, -c[1].x, 0.0f};
-        const float r2[4] = {c[1].z, c[2].x, c[2].z, c[3].x};
-        const float r3[4] = {c[3].z, c[4].x, c[4].z, c[5].x};
-        const float r4[4] = {c[5].z, c[6].x, c[6].z, c[7].x};
-        const float r5[4] = {c[7].z, c[8].x, c[8].z, c[9].x};
-        const float* rows[6] = {r0, r1, r2, r3, r4, r5};
-        for (int k = 0; k < 6; ++k) memcpy(rec + (k * n + i) * 4, rows[k], sizeof(float4));
-        link[i] = wn_float_as_int(h[1].w);
+        memcpy(rec + (0 * n + i) * 4, &e->hot[2 * i], sizeof(float4));
+        memcpy(rec + (1 * n + i) * 4, &e->hot[2 * i + 1], sizeof(float4));
+        for (int k = 0; k < 4; ++k) memcpy(rec + ((2 + k) * n + i) * 4, &e->cold[4 * i + k], sizeof(float4));
+        link[i] = wn_float_as_int(e->hot[2 * i + 1].w);
     }
     memcpy(tris, e->tris.data(), e->tris.size() * sizeof(float4));
     memcpy(tri_order, e->tri_order.data(), e->tri_order.size() * sizeof(unsigned));
