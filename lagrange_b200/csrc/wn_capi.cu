@@ -147,7 +147,7 @@ struct PackedHeader
     int64_t num_tree_nodes;
     int64_t reserved[3];
 };
-constexpr uint64_t kMagic = 0x3254303032424e57ull; // 'WNB200T2'
+constexpr uint64_t kMagic = 0x3454303032424e57ull; // 'WNB200T4' (T4: paired coefficient order, wn_pack_record)
 
 PackedHeader make_header(int64_t n_entries, int64_t n_tris)
 {

@@ -67,12 +67,14 @@ WN_HD WnV3 wn_v3(float x, float y, float z)
 #define WN_SUB(a, b) __fsub_rn((a), (b))
 #define WN_DIV(a, b) __fdiv_rn((a), (b))
 #define WN_SQRT(a) __fsqrt_rn((a))
+#define WN_FMA(a, b, c) __fmaf_rn((a), (b), (c))
 #else
 #define WN_MUL(a, b) ((a) * (b))
 #define WN_ADD(a, b) ((a) + (b))
 #define WN_SUB(a, b) ((a) - (b))
 #define WN_DIV(a, b) ((a) / (b))
 #define WN_SQRT(a) sqrtf((a))
+#define WN_FMA(a, b, c) fmaf((a), (b), (c))
 #endif
 
 WN_HD float wn_min(float a, float b)
@@ -512,12 +514,24 @@ WN_HD void wn_pack_record(const WnLocal& d, float r2, bool leaf, int order, floa
     if (order < 2) cxxx = cyyy = czzz = cxyz = cxxy = cxxz = cyyz = cyyx = czzx = czzy = 0.0f;
     if (order < 1) qxx = qyy = qzz = qxy = qyz = qzx = 0.0f;
     const float r2s = leaf ? wn_int_as_float(wn_float_as_int(r2) | (int)0x80000000) : r2;
+    // Storage order = the operand pairs of the evaluation (wn_eval_record): two chains of the same shape advance together,
+    // (lo, hi) of one 64-bit register pair, so that sm_100's packed FFMA2/FMUL2 retire two of the record's FMAs per issue slot.
     rec[0] = make_float4(d.P[0], d.P[1], d.P[2], r2s);
-    rec[1] = make_float4(d.N[0], d.N[1], d.N[2], 0.0f);
-    rec[2] = make_float4(qxx, qyy, qzz, qxy);
-    rec[3] = make_float4(qyz, qzx, cxxx, cyyy);
-    rec[4] = make_float4(czzz, cxyz, cxxy, cxxz);
-    rec[5] = make_float4(cyyz, cyyx, czzx, czzy);
+    rec[1] = make_float4(czzy, czzz, d.N[0], 0.0f); // .w: link bits, written by the packer
+    rec[2] = make_float4(qxx, cxxx, qxy, cxxy);
+    rec[3] = make_float4(qzx, cxxz, qyy, cyyx);
+    rec[4] = make_float4(qyz, cxyz, qzz, czzx);
+    rec[5] = make_float4(d.N[1], cyyy, d.N[2], cyyz);
+}
+
+// The 19 expansion coefficients of a stored record in their logical order (tests, debugging):
+// N xyz | qxx qyy qzz qxy qyz qzx | cxxx cyyy czzz cxyz cxxy cxxz cyyz cyyx czzx czzy
+WN_HD void wn_unpack_record(const float4* rec /* 6 */, float* o /* 19 */)
+{
+    o[0] = rec[1].z, o[1] = rec[5].x, o[2] = rec[5].z;
+    o[3] = rec[2].x, o[4] = rec[3].z, o[5] = rec[4].z, o[6] = rec[2].z, o[7] = rec[4].x, o[8] = rec[3].x;
+    o[9] = rec[2].y, o[10] = rec[5].y, o[11] = rec[1].y, o[12] = rec[4].y, o[13] = rec[2].w, o[14] = rec[3].y;
+    o[15] = rec[5].w, o[16] = rec[3].w, o[17] = rec[4].w, o[18] = rec[1].x;
 }
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -546,21 +560,36 @@ WN_HD float wn_rsqrt_ftz(float x)
 }
 
 // Far-field Taylor evaluation of one record at r = q - P with l2 = |r|^2 > 0 (A.5 folded, see wn_pack_record).
-WN_HD float wn_eval_record(float rx, float ry, float rz, float l2, const float4& f1, const float4& f2, const float4& f3,
-                           const float4& f4, const float4& f5)
+// f1 = the record's second hot float4, c0..c3 its cold ones. The operation sequence is spelled out (no compiler-chosen
+// contraction): this is the definition every kernel variant (scalar here, packed pairs in wn_query.cuh) reproduces bit for bit.
+WN_HD float wn_eval_record(float rx, float ry, float rz, float l2, const float4& f1, const float4& c0, const float4& c1,
+                           const float4& c2, const float4& c3)
 {
     const float m1 = wn_rsqrt_ftz(l2);
-    const float x = rx * m1, y = ry * m1, z = rz * m1;
-    const float m2 = m1 * m1;
-    const float a0 = -(x * f1.x + y * f1.y + z * f1.z);
-    // quadratic form: x (x qxx + y qxy + z qzx) + y (y qyy + z qyz) + z z qzz
-    const float a1 = x * (x * f2.x + y * f2.w + z * f3.y) + y * (y * f2.y + z * f3.x) + z * (z * f2.z);
-    // cubic form
-    const float cx = x * (x * f3.z + y * f4.z + z * f4.w) + y * (y * f5.y + z * f4.y) + z * (z * f5.z);
-    const float cy = y * (y * f3.w + z * f5.x) + z * (z * f5.w);
-    const float cz = z * (z * f4.x);
-    const float a2 = x * cx + y * cy + z * cz;
-    return m2 * (a0 + m1 * (a1 + m1 * a2));
+    const float x = WN_MUL(rx, m1), y = WN_MUL(ry, m1), z = WN_MUL(rz, m1);
+    const float m2 = WN_MUL(m1, m1);
+    // (t, p) = x (qxx, cxxx) + y (qxy, cxxy) + z (qzx, cxxz)
+    const float t = WN_FMA(z, c1.x, WN_FMA(y, c0.z, WN_MUL(x, c0.x)));
+    const float p = WN_FMA(z, c1.y, WN_FMA(y, c0.w, WN_MUL(x, c0.y)));
+    // (u, q) = y (qyy, cyyx) + z (qyz, cxyz);  (w, s) = z (qzz, czzx)
+    const float u = WN_FMA(z, c2.x, WN_MUL(y, c1.z));
+    const float q = WN_FMA(z, c2.y, WN_MUL(y, c1.w));
+    const float w = WN_MUL(z, c2.z);
+    const float s = WN_MUL(z, c2.w);
+    // (a1, cx) = x (t, p) + y (u, q) + z (w, s): the quadratic form and the x-part of the cubic form
+    const float a1 = WN_FMA(z, w, WN_FMA(y, u, WN_MUL(x, t)));
+    const float cx = WN_FMA(z, s, WN_FMA(y, q, WN_MUL(x, p)));
+    // (n, g) = y (Ny, cyyy) + z (Nz, cyyz);  n += x Nx
+    const float n = WN_FMA(x, f1.z, WN_FMA(z, c3.z, WN_MUL(y, c3.x)));
+    const float g = WN_FMA(z, c3.w, WN_MUL(y, c3.y));
+    // (h, k) = z (czzy, czzz)
+    const float h = WN_MUL(z, f1.x);
+    const float k = WN_MUL(z, f1.y);
+    const float cy = WN_FMA(z, h, WN_MUL(y, g));
+    const float cz = WN_MUL(z, k);
+    const float a2 = WN_FMA(z, cz, WN_FMA(y, cy, WN_MUL(x, cx)));
+    // Omega ~= m2 (-x.N + m1 (a1 + m1 a2))
+    return WN_MUL(m2, WN_FMA(m1, WN_FMA(m1, a2, a1), -n));
 }
 
 // Exact signed solid angle of triangle (a,b,c) seen from q (A.1, reference formulation incl. its two zero rules).
@@ -610,8 +639,8 @@ WN_HD float wn_lattice_coord(float origin, float spacing, int i)
 // (Used by the host emulation harness and mirrored lane-wise by the warp kernel.)
 // Memory layout of the packed tree: the six float4 of a record (see wn_pack_record) are split in a hot and a cold part,
 // each interleaved per entry, so that one address computation serves every load of a visit:
-//   hot [2*i + 0] = (Px, Py, Pz, R2 | leaf sign)     hot [2*i + 1] = (Nx, Ny, Nz, link bits)      32 B: one sector
-//   cold[4*i + k] = quadratic / cubic form coefficients (rec[2..5])                                  64 B: two sectors
+//   hot [2*i + 0] = (Px, Py, Pz, R2 | leaf sign)     hot [2*i + 1] = (czzy, czzz, Nx, link bits)   32 B: one sector
+//   cold[4*i + k] = the paired form coefficients (rec[2..5])                                        64 B: two sectors
 // A visit that only tests (the record is near for every lane) touches the hot sector alone.
 struct WnTreeView
 {

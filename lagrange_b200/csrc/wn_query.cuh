@@ -133,6 +133,30 @@ __device__ __forceinline__ int rec_link(const WnTreeView& t, int e)
     return __float_as_int(__ldg(&t.hot[2 * (int64_t)e + 1].w));
 }
 
+// wn_eval_record (wn_device.cuh) with its same-shaped chains advanced two at a time by sm_100's packed FP32 instructions
+// (FMUL2 / FFMA2: one issue slot, two correctly rounded results, bit-identical to the scalar sequence). The record's storage
+// order already is the operand-pair order, so the pairs come straight out of the 128-bit loads; only the unit vector has to
+// be duplicated (3 MOV). 30 issue slots instead of 39 — these kernels are issue-bound, not FMA-pipe-bound.
+__device__ __forceinline__ float eval_record(float rx, float ry, float rz, float l2, const float4& f1, const float4& c0, const float4& c1,
+                                             const float4& c2, const float4& c3)
+{
+    const float m1 = wn_rsqrt_ftz(l2);
+    const float x = __fmul_rn(rx, m1), y = __fmul_rn(ry, m1), z = __fmul_rn(rz, m1);
+    const float m2 = __fmul_rn(m1, m1);
+    const float2 X = make_float2(x, x), Y = make_float2(y, y), Z = make_float2(z, z);
+    const float2 tp = __ffma2_rn(Z, make_float2(c1.x, c1.y), __ffma2_rn(Y, make_float2(c0.z, c0.w), __fmul2_rn(X, make_float2(c0.x, c0.y))));
+    const float2 uq = __ffma2_rn(Z, make_float2(c2.x, c2.y), __fmul2_rn(Y, make_float2(c1.z, c1.w)));
+    const float2 ws = __fmul2_rn(Z, make_float2(c2.z, c2.w));
+    const float2 a1cx = __ffma2_rn(Z, ws, __ffma2_rn(Y, uq, __fmul2_rn(X, tp)));
+    const float2 ng = __ffma2_rn(Z, make_float2(c3.z, c3.w), __fmul2_rn(Y, make_float2(c3.x, c3.y)));
+    const float n = __fmaf_rn(x, f1.z, ng.x);
+    const float2 hk = __fmul2_rn(Z, make_float2(f1.x, f1.y));
+    const float cy = __fmaf_rn(z, hk.x, __fmul_rn(y, ng.y));
+    const float cz = __fmul_rn(z, hk.y);
+    const float a2 = __fmaf_rn(z, cz, __fmaf_rn(y, cy, __fmul_rn(x, a1cx.y)));
+    return __fmul_rn(m2, __fmaf_rn(m1, __fmaf_rn(m1, a2, a1cx.x), -n));
+}
+
 // ----------------------------------------------------------------------------------------------------------------
 // The per-point traversal. LISTED = false: records are the packed tree itself. LISTED = true: records are the tile's
 // conditional list in shared memory (key, skip position). Accumulates into acc. Returns true if a far-field value the
@@ -199,7 +223,7 @@ __device__ __forceinline__ bool warp_traverse(const WnTreeView& t, const float b
 #pragma unroll
             for (int k = 0; k < QPL; ++k) {
                 if (farq[k]) {
-                    const float om = wn_eval_record(rx[k], ry[k], rz[k], l2[k], f1, f2, f3, f4, f5);
+                    const float om = eval_record(rx[k], ry[k], rz[k], l2[k], f1, f2, f3, f4, f5);
                     if (fabsf(om) <= 3.402823466e38f) {
                         acc[k] += om;
                         skip[k] = after;
@@ -698,7 +722,7 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
             for (int k = 0; k < 2; ++k) {
                 const float rx = px[k] - f0.x, ry = py[k] - f0.y, rz = pz[k] - f0.z;
                 const float l2 = rx * rx + ry * ry + rz * rz;
-                const float om = wn_eval_record(rx, ry, rz, l2, f1, f2, f3, f4, f5);
+                const float om = eval_record(rx, ry, rz, l2, f1, f2, f3, f4, f5);
                 bad = bad || !(fabsf(om) <= 3.402823466e38f);
                 sacc[k] += om;
             }
@@ -769,7 +793,7 @@ __global__ void __launch_bounds__(kQueryThreads) k_tile_query(const QueryArgs a)
             for (int k = 0; k < QPL; ++k) {
                 const float rx = qx[k] - f0.x, ry = qy[k] - f0.y, rz = qz[k] - f0.z;
                 const float l2 = __fadd_rn(__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)), __fmul_rn(rz, rz)); // as in warp_traverse
-                const float om = wn_eval_record(rx, ry, rz, l2, f1, f2, f3, f4, f5);
+                const float om = eval_record(rx, ry, rz, l2, f1, f2, f3, f4, f5);
                 bad = bad || (valid[k] && !(fabsf(om) <= 3.402823466e38f));
                 acc[k] += om;
             }
