@@ -805,7 +805,7 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
         // batches of tiles so that the plan scratch (16.7 KB per tile) stays around 1 GB
         // (host outputs: smaller batches, so that less of the device-to-host copy is left exposed after the last one)
         const bool host_out = ob && (ob->h_omega || ob->h_inside);
-        const int64_t max_tiles = std::max(1, env_int("WN_TILE_BATCH", host_out ? 1 << 15 : 1 << 16));
+        const int64_t max_tiles = std::max(1, env_int("WN_TILE_BATCH", host_out ? 1 << 15 : 1 << 17));
         int64_t units, tiles_per_unit; // grid: unit = one z layer of tiles; points: unit = one tile
         if (GRID) {
             units = (grid_layers + 7) / 8;
@@ -844,10 +844,14 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
             }
             WN_CUDA(cudaMemsetAsync(a.plan_cursor, 0, sizeof(unsigned long long), st));
             wn::k_tile_plan<GRID><<<blocks, wn::kPlanThreads, 0, st>>>(a);
+            // a CTA walks a run of consecutive tiles, its warps taking sub-blocks dynamically (see k_tile_query)
+            a.launch_tiles = blocks;
+            a.tiles_per_cta = std::max(1, env_int("WN_TILE_RUN", 1));
+            const int qblocks = (blocks + a.tiles_per_cta - 1) / a.tiles_per_cta;
             if (stats)
-                wn::k_tile_query<GRID, true><<<blocks, wn::kQueryThreads, 0, st>>>(a);
+                wn::k_tile_query<GRID, true><<<qblocks, wn::kQueryThreads, 0, st>>>(a);
             else
-                wn::k_tile_query<GRID, false><<<blocks, wn::kQueryThreads, 0, st>>>(a);
+                wn::k_tile_query<GRID, false><<<qblocks, wn::kQueryThreads, 0, st>>>(a);
             if (overlap) {
                 // results of z layers [8*u0, 8*(u0+nunits)) of the slab are final: ship them while the next batch runs
                 const int64_t per_layer = (int64_t)a.g.nx * a.g.ny;

@@ -35,6 +35,14 @@
 
 namespace wn {
 
+// resident CTAs per SM the query kernels are compiled for (register budget = 65536 / (256 * N)). Measured on cfg2:
+// 4 -> 4.49, 5 -> 4.63 (48 registers, 8 B spilled), 6 -> 4.36 G queries/s.
+#ifndef WN_Q_MIN_CTAS
+#define WN_Q_MIN_CTAS 5
+#endif
+#ifndef WN_TQ_MIN_CTAS
+#define WN_TQ_MIN_CTAS 5
+#endif
 constexpr int kQueryThreads = 256;
 constexpr int kQueryWarps = kQueryThreads / 32;
 constexpr int kTileQPL = 2;                       // queries per lane in k_tile_query: 8 warps * 32 * 2 = 512 = 8^3
@@ -88,6 +96,7 @@ struct QueryArgs
     unsigned long long* plan_cursor; // bump allocator over the arena (reset before every k_tile_plan launch)
     long long plan_arena_bytes;
     float kappa;              // far set needs |c - P| >= kappa * tile radius and |c - P| - R >= kappa/2 * tile radius
+    int tiles_per_cta, launch_tiles; // k_tile_query: consecutive tiles per CTA, tiles in this launch
     int probe_stride;         // > 0: k_tile_plan only classifies every probe_stride-th tile and adds the class sizes to `probe`
     unsigned long long* probe; // [5] far, conditional, direct, exact records, fallback tiles
 };
@@ -183,7 +192,7 @@ __device__ __forceinline__ bool warp_traverse(const WnTreeView& t, const float b
         int e = i, after = 0;
         bool leaf, notest = false;
         if (LISTED) {
-            const int2 it = s_items[i];
+            const int2 it = __ldg(s_items + i);
             e = it.x >> 3;
             leaf = (it.x & 4) != 0;
             notest = (it.x & 3) == kClsCondFar;
@@ -267,15 +276,15 @@ __device__ __forceinline__ bool warp_traverse(const WnTreeView& t, const float b
 // Query point set-up shared by the kernels. Grid: CTA tile = 8 x 8 x (4*QPL) lattice points, warp tile 4 x 4 x (2*QPL).
 // ----------------------------------------------------------------------------------------------------------------
 template <int QPL>
-__device__ __forceinline__ void grid_points(const QueryArgs& a, float (&qx)[QPL], float (&qy)[QPL], float (&qz)[QPL], bool (&valid)[QPL],
-                                            int64_t (&oidx)[QPL])
+__device__ __forceinline__ void grid_points(const QueryArgs& a, const int block, const int wid, float (&qx)[QPL], float (&qy)[QPL],
+                                            float (&qz)[QPL], bool (&valid)[QPL], int64_t (&oidx)[QPL])
 {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int bx = blockIdx.x % a.tiles_x;
-    const int by = (blockIdx.x / a.tiles_x) % a.tiles_y;
+    const int lane = threadIdx.x & 31;
+    const int bx = block % a.tiles_x;
+    const int by = (block / a.tiles_x) % a.tiles_y;
     // CTA layer l of this launch covers the lattice layer tile_z0 + l * layer_step (strided sharding across GPUs: every
     // layer_step-th layer, results stored compactly: local layer out_layer0 + l)
-    const int l = blockIdx.x / (a.tiles_x * a.tiles_y);
+    const int l = block / (a.tiles_x * a.tiles_y);
     const int bz = a.tile_z0 + l * a.layer_step;
     const int x = bx * 8 + (wid & 1) * 4 + (lane & 3);
     const int y = by * 8 + ((wid >> 1) & 1) * 4 + ((lane >> 2) & 3);
@@ -294,15 +303,16 @@ __device__ __forceinline__ void grid_points(const QueryArgs& a, float (&qx)[QPL]
 
 // Points: warp w of block b owns slots [(b*8 + w) * 32*QPL, +32*QPL); `stage` = 24*QPL float4 of shared memory per warp.
 template <int QPL>
-__device__ __forceinline__ void list_points(const QueryArgs& a, int64_t block, float4* stage, float (&qx)[QPL], float (&qy)[QPL],
-                                            float (&qz)[QPL], bool (&valid)[QPL], int64_t (&oidx)[QPL])
+__device__ __forceinline__ void list_points(const QueryArgs& a, int64_t block, const int wid, float4* stage, float (&qx)[QPL],
+                                            float (&qy)[QPL], float (&qz)[QPL], bool (&valid)[QPL], int64_t (&oidx)[QPL])
 {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
     const int64_t wbase = (block * kQueryWarps + wid) * (32 * QPL);
     const bool staged = a.perm == nullptr && a.q_aligned16 && wbase + 32 * QPL <= a.n;
     if (staged) {
         // 32*QPL points = 96*QPL floats = 24*QPL float4, contiguous and 16-byte aligned: vectorised, coalesced
         const float4* src = reinterpret_cast<const float4*>(a.q + 3 * wbase);
+        __syncwarp(); // a previous use of this warp's stage (k_tile_query runs several tasks per warp) has been read
         for (int j = lane; j < 24 * QPL; j += 32) stage[j] = __ldg(src + j);
         __syncwarp();
     }
@@ -360,16 +370,16 @@ __device__ __forceinline__ void flush_counters(const QueryArgs& a, TravCounters&
 
 // ---- generic kernel --------------------------------------------------------------------------------------------
 template <int QPL, bool GRID, bool STATS>
-__global__ void __launch_bounds__(kQueryThreads) k_query(const QueryArgs a)
+__global__ void __launch_bounds__(kQueryThreads, WN_Q_MIN_CTAS) k_query(const QueryArgs a)
 {
     __shared__ float4 stage[GRID ? 1 : kQueryWarps * 24 * QPL];
     float qx[QPL], qy[QPL], qz[QPL], acc[QPL];
     bool valid[QPL];
     int64_t oidx[QPL];
     if (GRID)
-        grid_points<QPL>(a, qx, qy, qz, valid, oidx);
+        grid_points<QPL>(a, (int)blockIdx.x, threadIdx.x >> 5, qx, qy, qz, valid, oidx);
     else
-        list_points<QPL>(a, blockIdx.x, stage + (threadIdx.x >> 5) * 24 * QPL, qx, qy, qz, valid, oidx);
+        list_points<QPL>(a, blockIdx.x, threadIdx.x >> 5, stage + (threadIdx.x >> 5) * 24 * QPL, qx, qy, qz, valid, oidx);
 #pragma unroll
     for (int k = 0; k < QPL; ++k) acc[k] = 0.0f;
     TravCounters cnt;
@@ -756,97 +766,114 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
 }
 
 // ---- tiled path: query -----------------------------------------------------------------------------------------
+// A CTA owns a run of consecutive tiles; its warps pull (tile, 4x4x4 sub-block) tasks from a CTA-local counter, so a warp
+// whose sub-block lies close to the surface (long conditional walk) does not hold seven finished warps at a barrier:
+// nothing here synchronises the CTA after the counter is set up. The plan's packets are read through L1 (warp-uniform).
 template <bool GRID, bool STATS>
-__global__ void __launch_bounds__(kQueryThreads) k_tile_query(const QueryArgs a)
+__global__ void __launch_bounds__(kQueryThreads, WN_TQ_MIN_CTAS) k_tile_query(const QueryArgs a)
 {
-    __shared__ int2 s_items[kTileAllCap];
-    __shared__ __align__(16) float s_samp[kTileSampleStride];
+    __shared__ int s_next;
     __shared__ float4 stage[GRID ? 1 : kQueryWarps * 24 * kTileQPL];
     constexpr int QPL = kTileQPL;
-    float qx[QPL], qy[QPL], qz[QPL], acc[QPL];
-    bool valid[QPL];
-    int64_t oidx[QPL];
-    if (GRID)
-        grid_points<QPL>(a, qx, qy, qz, valid, oidx);
-    else
-        list_points<QPL>(a, (int64_t)blockIdx.x + a.tile_base, stage + (threadIdx.x >> 5) * 24 * QPL, qx, qy, qz, valid, oidx);
-    const TileHeader hdr = a.plan_hdr[blockIdx.x];
-    const bool fallback = (hdr.flags & kTileFallback) != 0;
-    const char* pk = a.plan_arena + hdr.offset;
-    if (!fallback) {
-        const int2* src = reinterpret_cast<const int2*>(pk);
-        for (int j = threadIdx.x; j < hdr.n_cond; j += kQueryThreads) s_items[j] = src[j];
-        if (threadIdx.x < kTileSampleStride) s_samp[threadIdx.x] = a.plan_samples[(int64_t)blockIdx.x * kTileSampleStride + threadIdx.x];
-    }
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) s_next = 0;
     __syncthreads();
+    const int tile0 = (int)blockIdx.x * a.tiles_per_cta;
+    const int n_task = min(a.tiles_per_cta, a.launch_tiles - tile0) * kQueryWarps;
     TravCounters cnt;
-    bool bad = false;
-#pragma unroll
-    for (int k = 0; k < QPL; ++k) acc[k] = 0.0f;
-    if (!fallback) {
-        // ---- direct records: far for every point of the tile; gathered contiguously by the plan ---------------------
-        const float4* __restrict__ dr = reinterpret_cast<const float4*>(pk + (((long long)hdr.n_cond * 8 + 15) & ~15ll));
-        for (int j = 0; j < hdr.n_dir; ++j) {
-            const float4 f0 = __ldg(dr + 0), f1 = __ldg(dr + 1), f2 = __ldg(dr + 2), f3 = __ldg(dr + 3), f4 = __ldg(dr + 4), f5 = __ldg(dr + 5);
-            dr += 6;
-#pragma unroll
-            for (int k = 0; k < QPL; ++k) {
-                const float rx = qx[k] - f0.x, ry = qy[k] - f0.y, rz = qz[k] - f0.z;
-                const float l2 = __fadd_rn(__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)), __fmul_rn(rz, rz)); // as in warp_traverse
-                const float om = eval_record(rx, ry, rz, l2, f1, f2, f3, f4, f5);
-                bad = bad || (valid[k] && !(fabsf(om) <= 3.402823466e38f));
-                acc[k] += om;
-            }
-        }
-        // ---- exact triangles: leaves that are near for every point of the tile ------------------------------------------
-        const float4* __restrict__ tr = dr; // triangles follow the direct records in the packet
-        for (int j = 0; j < hdr.n_tri; ++j) {
-            const float4 ta = __ldg(tr + 0), tb = __ldg(tr + 1), tc = __ldg(tr + 2);
-            tr += 3;
-#pragma unroll
-            for (int k = 0; k < QPL; ++k) acc[k] += wn_tri_solid_angle(qx[k], qy[k], qz[k], ta, tb, tc);
-        }
-        if (STATS) {
-#pragma unroll
-            for (int k = 0; k < QPL; ++k) {
-                if (valid[k]) {
-                    cnt.A += hdr.n_dir;
-                    cnt.E += hdr.n_tri;
-                }
-            }
-        }
-        // ---- conditional records ------------------------------------------------------------------------------------
-        bad = warp_traverse<QPL, STATS, true>(a.tree, a.beta2, qx, qy, qz, valid, acc, s_items, hdr.n_cond, cnt) || bad;
-    }
-    if (__syncthreads_or((int)(bad || fallback))) {
-        // generic traversal of the whole tree for this tile (list overflow, non-finite far field, degenerate tile)
+    while (true) {
+        int task = 0;
+        if (lane == 0) task = atomicAdd(&s_next, 1);
+        task = __shfl_sync(kFull, task, 0);
+        if (task >= n_task) break;
+        const int tile = tile0 + task / kQueryWarps, sub = task % kQueryWarps;
+        float qx[QPL], qy[QPL], qz[QPL], acc[QPL];
+        bool valid[QPL];
+        int64_t oidx[QPL];
+        if (GRID)
+            grid_points<QPL>(a, tile, sub, qx, qy, qz, valid, oidx);
+        else
+            list_points<QPL>(a, (int64_t)tile + a.tile_base, sub, stage + (threadIdx.x >> 5) * 24 * QPL, qx, qy, qz, valid, oidx);
+        const int4 h4 = __ldg(reinterpret_cast<const int4*>(a.plan_hdr + tile));
+        const long long offset = __ldg(&a.plan_hdr[tile].offset);
+        const int n_cond = h4.x, n_dir = h4.y, n_tri = h4.z;
+        const bool fallback = (h4.w & kTileFallback) != 0;
+        const char* pk = a.plan_arena + offset;
+        bool bad = false;
 #pragma unroll
         for (int k = 0; k < QPL; ++k) acc[k] = 0.0f;
-        warp_traverse<QPL, STATS, false>(a.tree, a.beta2, qx, qy, qz, valid, acc, nullptr, 0, cnt);
-    } else {
-        const float cx = s_samp[64], cy = s_samp[65], cz = s_samp[66];
-        const float ihx = s_samp[67], ihy = s_samp[68], ihz = s_samp[69];
+        if (!fallback) {
+            // ---- direct records: far for every point of the tile; gathered contiguously by the plan -----------------
+            const float4* __restrict__ dr = reinterpret_cast<const float4*>(pk + (((long long)n_cond * 8 + 15) & ~15ll));
+            for (int j = 0; j < n_dir; ++j) {
+                const float4 f0 = __ldg(dr + 0), f1 = __ldg(dr + 1), f2 = __ldg(dr + 2), f3 = __ldg(dr + 3), f4 = __ldg(dr + 4), f5 = __ldg(dr + 5);
+                dr += 6;
 #pragma unroll
-        for (int k = 0; k < QPL; ++k) {
-            float wx[4], wy[4], wz[4];
-            cheb_weights((qx[k] - cx) * ihx, wx);
-            cheb_weights((qy[k] - cy) * ihy, wy);
-            cheb_weights((qz[k] - cz) * ihz, wz);
-            float far = 0.0f;
+                for (int k = 0; k < QPL; ++k) {
+                    const float rx = qx[k] - f0.x, ry = qy[k] - f0.y, rz = qz[k] - f0.z;
+                    const float l2 = __fadd_rn(__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)), __fmul_rn(rz, rz)); // as in warp_traverse
+                    const float om = eval_record(rx, ry, rz, l2, f1, f2, f3, f4, f5);
+                    bad = bad || (valid[k] && !(fabsf(om) <= 3.402823466e38f));
+                    acc[k] += om;
+                }
+            }
+            // ---- exact triangles: leaves that are near for every point of the tile --------------------------------------
+            const float4* __restrict__ tr = dr; // triangles follow the direct records in the packet
+            for (int j = 0; j < n_tri; ++j) {
+                const float4 ta = __ldg(tr + 0), tb = __ldg(tr + 1), tc = __ldg(tr + 2);
+                tr += 3;
+#pragma unroll
+                for (int k = 0; k < QPL; ++k) acc[k] += wn_tri_solid_angle(qx[k], qy[k], qz[k], ta, tb, tc);
+            }
+            if (STATS) {
+#pragma unroll
+                for (int k = 0; k < QPL; ++k) {
+                    if (valid[k]) {
+                        cnt.A += n_dir;
+                        cnt.E += n_tri;
+                    }
+                }
+            }
+            // ---- conditional records --------------------------------------------------------------------------------
+            bad = warp_traverse<QPL, STATS, true>(a.tree, a.beta2, qx, qy, qz, valid, acc, reinterpret_cast<const int2*>(pk), n_cond, cnt) || bad;
+        }
+        // The fallback is a per-warp matter: a point's result never depends on its neighbours.
+        if (fallback || __any_sync(kFull, bad)) {
+            // generic traversal of the whole tree for this sub-block (list overflow, non-finite far field, degenerate tile)
+#pragma unroll
+            for (int k = 0; k < QPL; ++k) acc[k] = 0.0f;
+            warp_traverse<QPL, STATS, false>(a.tree, a.beta2, qx, qy, qz, valid, acc, nullptr, 0, cnt);
+        } else {
+            const float4* __restrict__ samp = reinterpret_cast<const float4*>(a.plan_samples + (int64_t)tile * kTileSampleStride);
+            const float4 g0 = __ldg(samp + 16), g1 = __ldg(samp + 17); // centre xyz, 1/half-extent xyz
+            float wx[QPL][4], wy[QPL][4], wz[QPL][4], far[QPL];
+#pragma unroll
+            for (int k = 0; k < QPL; ++k) {
+                cheb_weights((qx[k] - g0.x) * g0.w, wx[k]);
+                cheb_weights((qy[k] - g0.y) * g1.x, wy[k]);
+                cheb_weights((qz[k] - g0.z) * g1.y, wz[k]);
+                far[k] = 0.0f;
+            }
 #pragma unroll
             for (int kz = 0; kz < 4; ++kz) {
-                float sz = 0.0f;
+                float sz[QPL];
+#pragma unroll
+                for (int k = 0; k < QPL; ++k) sz[k] = 0.0f;
 #pragma unroll
                 for (int ky = 0; ky < 4; ++ky) {
-                    const float4 row = *reinterpret_cast<const float4*>(&s_samp[(kz * 4 + ky) * 4]);
-                    sz += wy[ky] * (wx[0] * row.x + wx[1] * row.y + wx[2] * row.z + wx[3] * row.w);
+                    const float4 row = __ldg(samp + kz * 4 + ky);
+#pragma unroll
+                    for (int k = 0; k < QPL; ++k)
+                        sz[k] += wy[k][ky] * (wx[k][0] * row.x + wx[k][1] * row.y + wx[k][2] * row.z + wx[k][3] * row.w);
                 }
-                far += wz[kz] * sz;
+#pragma unroll
+                for (int k = 0; k < QPL; ++k) far[k] += wz[k][kz] * sz[k];
             }
-            acc[k] += far;
+#pragma unroll
+            for (int k = 0; k < QPL; ++k) acc[k] += far[k];
         }
+        write_results<QPL>(a, oidx, acc);
     }
-    write_results<QPL>(a, oidx, acc);
     if (STATS) flush_counters(a, cnt);
 }
 
