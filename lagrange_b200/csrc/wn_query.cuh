@@ -54,6 +54,7 @@ constexpr int kTileFrontCap = 1024;               // breadth-first frontier
 constexpr int kTileFarCap = 512;                  // far set
 constexpr int kTileDirCap = 512;                  // direct records
 constexpr int kTileExactCap = 1024;               // exact leaves (also bounded by the frontier buffer reused for offsets)
+constexpr int kPlanMaxRounds = 96;                // breadth-first rounds = hierarchy depth bound (deeper: generic path)
 constexpr int kTileSamples = 64;                  // 4^3 Chebyshev points
 constexpr int kTileSampleStride = 72;             // 64 samples + centre(3) + 1/half-extent(3) + radius + pad
 constexpr int kTileFallback = 1;                  // header flag: tile must be processed by the generic traversal
@@ -414,27 +415,6 @@ __device__ __forceinline__ void plan_append(int* list, int* count, int cap, int 
         *overflow = 1;
 }
 
-// in-place ascending bitonic sort of s[0..N), N a power of two, by the whole CTA (lists longer than 64)
-__device__ __forceinline__ void plan_bitonic_sort(int* s, int N)
-{
-    for (int k = 2; k <= N; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < N; i += kPlanThreads) {
-                const int p = i ^ j;
-                if (p > i) {
-                    const int va = s[i], vb = s[p];
-                    const bool asc = (i & k) == 0;
-                    if ((va > vb) == asc) {
-                        s[i] = vb;
-                        s[p] = va;
-                    }
-                }
-            }
-            __syncthreads();
-        }
-    }
-}
-
 // ascending sort of s[0..n), n <= 64, by ONE warp: two keys per lane (elements lane and lane + 32), bitonic network with
 // shuffles, no shared-memory traffic and no block barrier
 __device__ __forceinline__ void plan_warp_sort64(int* s, int n)
@@ -464,6 +444,43 @@ __device__ __forceinline__ void plan_warp_sort64(int* s, int n)
     if (lane + 32 < n) s[lane + 32] = b;
 }
 
+// ascending sort of s[0..n), 64 < n <= 2 * kTileFrontCap, distinct keys, by the whole CTA: 64-key chunks by the warps'
+// shuffle network, then log2(n/64) merge rounds in which every key finds its rank in the sibling run by binary search
+// (ping-pong with tmp). ~4x fewer instructions and ~6x fewer barriers than a bitonic network at the usual n ~ 100-300.
+__device__ __forceinline__ void plan_merge_sort(int* s, int* tmp, int n)
+{
+    const int wid = threadIdx.x >> 5;
+    for (int c = wid * 64; c < n; c += kPlanWarps * 64) plan_warp_sort64(s + c, min(64, n - c));
+    __syncthreads();
+    int* src = s;
+    int* dst = tmp;
+    for (int L = 64; L < n; L <<= 1) {
+        for (int i = threadIdx.x; i < n; i += kPlanThreads) {
+            const int start = i & ~(L - 1);
+            const int sib = start ^ L;
+            const int sib_len = max(0, min(L, n - sib));
+            const int key = src[i];
+            int lo = 0, hi = sib_len;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (src[sib + mid] < key)
+                    lo = mid + 1;
+                else
+                    hi = mid;
+            }
+            dst[min(start, sib) + (i - start) + lo] = key;
+        }
+        __syncthreads();
+        int* x = src;
+        src = dst;
+        dst = x;
+    }
+    if (src != s) {
+        for (int i = threadIdx.x; i < n; i += kPlanThreads) s[i] = src[i];
+        __syncthreads();
+    }
+}
+
 template <bool GRID>
 __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
 {
@@ -473,7 +490,8 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
     __shared__ int s_exact[kTileExactCap];
     __shared__ int s_far[kTileFarCap];
     __shared__ float s_samp[kPlanWarps][kTileSamples];
-    __shared__ int s_cnt[8]; // 0,1 frontier sizes; 2 cond; 3 far; 4 overflow / bad; 5 dir; 6 exact; 7 triangles
+    __shared__ int s_fcnt[kPlanMaxRounds + 1]; // frontier size of every round
+    __shared__ int s_cnt[8]; // 0,1 unused; 2 cond; 3 far; 4 overflow / bad; 5 dir; 6 exact; 7 triangles
     __shared__ float s_geo[8];
     __shared__ float s_red[kPlanWarps][6];
     __shared__ long long s_off;
@@ -531,6 +549,7 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
         }
     }
     if (tid < 8) s_cnt[tid] = 0;
+    if (tid <= kPlanMaxRounds) s_fcnt[tid] = 0;
     if (tid == 0) s_off = 0;
     __syncthreads();
     if (tid == 0) {
@@ -562,7 +581,7 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
         if (!finite) s_cnt[4] = 1; // non-finite coordinates (or an empty tile): generic path
         const int n_entries = t.n_entries;
         if (n_entries > 1) {
-            plan_push_kids(__ldg(t.kids), 0, s_front[0], &s_cnt[0], &s_cnt[4]);
+            plan_push_kids(__ldg(t.kids), 0, s_front[0], &s_fcnt[0], &s_cnt[4]);
         } else if (n_entries == 1) {
             s_exact[0] = 0; // the root is a leaf: exact for everybody
             s_cnt[6] = 1;
@@ -574,13 +593,19 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
                 hz = s_geo[5] > 0.0f ? 1.0f / s_geo[5] : 0.0f;
 
     // ---- breadth-first classification ----------------------------------------------------------------------------
-    int cur = 0;
-    while (true) {
-        const int F = min(s_cnt[cur], kTileFrontCap);
-        if (F == 0 || s_cnt[4]) break;
-        int* nxt = s_front[cur ^ 1];
+    // One barrier per round: every round has its own frontier counter (no reset between rounds), and the decision to stop
+    // is taken by the barrier itself (an OR over all threads), so no thread can leave the loop on a flag another thread
+    // is still about to set.
+    int round = 0;
+    bool stop = s_cnt[4] != 0;
+    while (!stop) {
+        const int F = min(s_fcnt[round], kTileFrontCap);
+        if (F == 0) break;
+        const int* cur = s_front[round & 1];
+        int* nxt = s_front[(round + 1) & 1];
+        int* ncnt = &s_fcnt[round + 1];
         for (int idx = tid; idx < F; idx += kPlanThreads) {
-            const int word = s_front[cur][idx];
+            const int word = cur[idx];
             const int e = word & 0x3fffffff, manc = (word >> 30) & 1;
             const float4 f0 = rec_hot(t, e, 0);
             const int4 k4 = __ldg(t.kids + e);
@@ -602,20 +627,19 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
                     plan_append(s_dir, &s_cnt[5], kTileDirCap, e, &s_cnt[4]);
             } else if (allnear) {
                 if (!leaf)
-                    plan_push_kids(k4, manc, nxt, &s_cnt[cur ^ 1], &s_cnt[4]);
+                    plan_push_kids(k4, manc, nxt, ncnt, &s_cnt[4]);
                 else if (manc)
                     plan_append(s_cond, &s_cnt[2], kTileAllCap, tile_key(e, true, kClsCond), &s_cnt[4]);
                 else
                     plan_append(s_exact, &s_cnt[6], kTileExactCap, e, &s_cnt[4]);
             } else {
                 plan_append(s_cond, &s_cnt[2], kTileAllCap, tile_key(e, leaf, kClsCond), &s_cnt[4]);
-                if (!leaf) plan_push_kids(k4, 1, nxt, &s_cnt[cur ^ 1], &s_cnt[4]);
+                if (!leaf) plan_push_kids(k4, 1, nxt, ncnt, &s_cnt[4]);
             }
         }
-        __syncthreads();
-        if (tid == 0) s_cnt[cur] = 0;
-        cur ^= 1;
-        __syncthreads();
+        ++round;
+        if (round >= kPlanMaxRounds) s_cnt[4] = 1; // deeper than any sane hierarchy: generic path
+        stop = __syncthreads_or(s_cnt[4]) != 0;
     }
     __syncthreads();
     bool fallback = s_cnt[4] != 0;
@@ -640,13 +664,7 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
     __syncthreads();
 #pragma unroll
     for (int l = 0; l < 4; ++l) {
-        if (lens[l] > 64) { // uniform over the CTA
-            int N = 128;
-            while (N < lens[l]) N <<= 1;
-            for (int j = lens[l] + tid; j < N; j += kPlanThreads) lists[l][j] = 0x7fffffff;
-            __syncthreads();
-            plan_bitonic_sort(lists[l], N);
-        }
+        if (lens[l] > 64) plan_merge_sort(lists[l], &s_front[0][0], lens[l]); // uniform over the CTA; the frontier is done
     }
 
     // ---- triangles of the exact class: exclusive prefix of the leaf sizes (warp 0) --------------------------------------
