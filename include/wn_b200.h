@@ -188,6 +188,10 @@ WN_API wn_status wn_create_from_packed(const void* src, int64_t nbytes, const wn
 WN_API wn_status wn_debug_node_moments(const wn_engine* e, int64_t first_node, int64_t count, float* out_23);
 /* Hierarchy topology as built on the device: child[num_internal * width] with the wn_create_from_topology encoding. */
 WN_API wn_status wn_debug_topology(const wn_engine* e, int32_t* child, int64_t capacity_nodes, int64_t* num_internal);
+/* Class sizes of the tiles planned by the last tiled batch of this engine (K6'): out[4 * i + {0,1,2,3}] = conditional
+ * records, direct records, gathered exact triangles, flags (1 = tile fell back to the generic traversal). Host output;
+ * *num_tiles = tiles in that batch (call with out = NULL to size the buffer). */
+WN_API wn_status wn_debug_last_plan(const wn_engine* e, int32_t* out, int64_t capacity_tiles, int64_t* num_tiles);
 /* Stand-alone radix sort of (key,value) pairs on the device (K2), exposed for tests. Host pointers. */
 WN_API wn_status wn_debug_sort_pairs_u64(uint64_t* keys, uint32_t* values, int64_t n, int32_t begin_bit, int32_t end_bit);
 WN_API wn_status wn_debug_sort_pairs_u32(uint32_t* keys, uint32_t* values, int64_t n, int32_t begin_bit, int32_t end_bit);

@@ -77,6 +77,7 @@ SIGNATURES = {
     "wn_create_from_packed": (ctypes.c_int, [_vp, _i64, ctypes.POINTER(wn_options), ctypes.POINTER(_vp)]),
     "wn_debug_node_moments": (ctypes.c_int, [_vp, _i64, _i64, _vp]),
     "wn_debug_topology": (ctypes.c_int, [_vp, _vp, _i64, ctypes.POINTER(_i64)]),
+    "wn_debug_last_plan": (ctypes.c_int, [_vp, _vp, _i64, ctypes.POINTER(_i64)]),
     "wn_debug_sort_pairs_u64": (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32]),
     "wn_debug_sort_pairs_u32": (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32]),
     "wn_debug_fma_peak": (ctypes.c_int, [_i32, _i32, ctypes.POINTER(_f), ctypes.POINTER(_f)]),

@@ -192,6 +192,7 @@ struct wn_engine
     mutable DevBuf s_in, s_out_f, s_out_b, s_sort, s_stats, s_partial, s_plan_hdr, s_plan_items, s_plan_samples;
     mutable PinnedBuf p_small;
     mutable cudaStream_t copy_stream = nullptr; // D2H of finished batches while the next batch computes
+    mutable int64_t last_plan_tiles = 0;        // tiles of the last k_tile_plan launch (wn_debug_last_plan)
     mutable float last_probe_share = -1.0f;     // far-set share measured by the last tiling probe (diagnostics)
     mutable float probe_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     mutable int probe_dims[3] = {0, 0, 0};
@@ -846,6 +847,7 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
             wn::k_tile_plan<GRID><<<blocks, wn::kPlanThreads, 0, st>>>(a);
             // a CTA walks a run of consecutive tiles, its warps taking sub-blocks dynamically (see k_tile_query)
             a.launch_tiles = blocks;
+            e->last_plan_tiles = blocks;
             a.tiles_per_cta = std::max(1, env_int("WN_TILE_RUN", 1));
             const int qblocks = (blocks + a.tiles_per_cta - 1) / a.tiles_per_cta;
             if (stats)
@@ -1341,6 +1343,27 @@ wn_status wn_debug_topology(const wn_engine* e, int32_t* child, int64_t capacity
     for (size_t k = 0; k < n; ++k) {
         const int c = h[k];
         child[k] = c < 0 ? WN_CHILD_EMPTY : (c >= e->kept_nI ? wn_enc_tri((int)prim[(size_t)(c - e->kept_nI)]) : c);
+    }
+    return WN_OK;
+}
+
+wn_status wn_debug_last_plan(const wn_engine* e, int32_t* out, int64_t capacity_tiles, int64_t* num_tiles)
+{
+    if (!e || !num_tiles) return fail(WN_ERR_INVALID_ARGUMENT, "null argument");
+    std::lock_guard<std::mutex> lock(e->mu);
+    *num_tiles = e->last_plan_tiles;
+    if (!out) return WN_OK;
+    if (capacity_tiles < e->last_plan_tiles) return fail(WN_ERR_INVALID_ARGUMENT, "output buffer too small");
+    if (e->last_plan_tiles == 0) return WN_OK;
+    DeviceGuard guard(e->device);
+    std::vector<wn::TileHeader> h((size_t)e->last_plan_tiles);
+    WN_CUDA(cudaDeviceSynchronize());
+    WN_CUDA(cudaMemcpy(h.data(), (const char*)e->s_plan_hdr.p + 256, h.size() * sizeof(wn::TileHeader), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < h.size(); ++i) {
+        out[4 * i + 0] = h[i].n_cond;
+        out[4 * i + 1] = h[i].n_dir;
+        out[4 * i + 2] = h[i].n_tri;
+        out[4 * i + 3] = h[i].flags;
     }
     return WN_OK;
 }

@@ -362,6 +362,15 @@ class FastWindingNumber:
         self._check(self._lib.wn_debug_node_moments(self._handle(), first, count, ctypes.c_void_p(out.ctypes.data)))
         return out
 
+    def debug_last_plan(self) -> np.ndarray:
+        """[tiles, 4] int32: conditional records, direct records, exact triangles, flags of the last tiled batch."""
+        n = ctypes.c_int64()
+        self._check(self._lib.wn_debug_last_plan(self._handle(), None, 0, ctypes.byref(n)))
+        out = np.empty((n.value, 4), dtype=np.int32)
+        if n.value:
+            self._check(self._lib.wn_debug_last_plan(self._handle(), ctypes.c_void_p(out.ctypes.data), n.value, ctypes.byref(n)))
+        return out
+
     def debug_topology(self) -> np.ndarray:
         n = ctypes.c_int64()
         self._check(self._lib.wn_debug_topology(self._handle(), None, 0, ctypes.byref(n)))

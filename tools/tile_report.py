@@ -28,3 +28,16 @@ for name, tiling in (("generic", False), ("tiled", True)):
     st = eng.query_stats_grid(o, s, d, tiling=tiling)
     rep[name] = {k: st[k] / n for k in ("node_tests", "far_field_evals", "exact_triangles", "lane_slots")}
 print(json.dumps(rep))
+hdr = eng.debug_last_plan()
+if len(hdr):
+    dist = {}
+    for j, name in enumerate(("n_cond", "n_dir", "n_tri")):
+        v = hdr[:, j]
+        dist[name] = {"mean": float(v.mean()), "p50": int(np.percentile(v, 50)), "p90": int(np.percentile(v, 90)), "p99": int(np.percentile(v, 99)),
+                      "max": int(v.max())}
+    dist["fallback_tiles"] = int((hdr[:, 3] & 1).sum())
+    dist["tiles"] = int(len(hdr))
+    w = hdr[:, 0].astype(np.float64)
+    order = np.sort(w)[::-1]
+    dist["share_of_cond_in_top10pct_tiles"] = float(order[: len(order) // 10].sum() / max(w.sum(), 1))
+    print(json.dumps({"last_batch_tiles": dist}))
