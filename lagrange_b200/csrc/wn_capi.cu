@@ -189,7 +189,7 @@ struct wn_engine
     std::vector<void*> kept_allocs; // device allocations that back the kept arrays
     // per-engine query scratch, guarded by mu
     mutable std::mutex mu;
-    mutable DevBuf s_in, s_out_f, s_out_b, s_sort, s_stats, s_partial, s_plan_hdr, s_plan_items, s_plan_samples;
+    mutable DevBuf s_in, s_out_f, s_out_b, s_sort, s_stats, s_partial, s_plan_hdr, s_plan_items, s_plan_samples, s_plan_order;
     mutable PinnedBuf p_small;
     mutable cudaStream_t copy_stream = nullptr; // D2H of finished batches while the next batch computes
     mutable int64_t last_plan_tiles = 0;        // tiles of the last k_tile_plan launch (wn_debug_last_plan)
@@ -826,11 +826,14 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
         WN_CUDA(e->s_plan_hdr.reserve((size_t)launch_tiles * sizeof(wn::TileHeader) + 256));
         WN_CUDA(e->s_plan_items.reserve((size_t)arena_bytes));
         WN_CUDA(e->s_plan_samples.reserve((size_t)launch_tiles * wn::kTileSampleStride * sizeof(float)));
+        WN_CUDA(e->s_plan_order.reserve((size_t)launch_tiles * sizeof(int)));
         a.plan_hdr = (wn::TileHeader*)((char*)e->s_plan_hdr.p + 256);
         a.plan_cursor = (unsigned long long*)e->s_plan_hdr.p;
         a.plan_arena = (char*)e->s_plan_items.p;
         a.plan_arena_bytes = arena_bytes;
         a.plan_samples = (float*)e->s_plan_samples.p;
+        a.tile_order = (int*)e->s_plan_order.p;
+        a.heavy_cond = env_int("WN_TILE_HEAVY", 192);
         a.kappa = tile_kappa();
         const bool overlap = GRID && ob && (ob->h_omega || ob->h_inside) && units > units_per_launch;
         if (overlap && !e->copy_stream) WN_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
@@ -843,7 +846,8 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
             } else {
                 a.tile_base = u0;
             }
-            WN_CUDA(cudaMemsetAsync(a.plan_cursor, 0, sizeof(unsigned long long), st));
+            a.launch_tiles = blocks;
+            WN_CUDA(cudaMemsetAsync(a.plan_cursor, 0, 2 * sizeof(unsigned long long), st)); // arena cursor + the two order counters
             wn::k_tile_plan<GRID><<<blocks, wn::kPlanThreads, 0, st>>>(a);
             // a CTA walks a run of consecutive tiles, its warps taking sub-blocks dynamically (see k_tile_query)
             a.launch_tiles = blocks;
@@ -1172,6 +1176,7 @@ wn_status wn_destroy(wn_engine* e)
         e->s_plan_hdr.release();
         e->s_plan_items.release();
         e->s_plan_samples.release();
+        e->s_plan_order.release();
         e->p_small.release();
         if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     }

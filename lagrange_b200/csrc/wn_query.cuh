@@ -98,6 +98,8 @@ struct QueryArgs
     long long plan_arena_bytes;
     float kappa;              // far set needs |c - P| >= kappa * tile radius and |c - P| - R >= kappa/2 * tile radius
     int tiles_per_cta, launch_tiles; // k_tile_query: consecutive tiles per CTA, tiles in this launch
+    int* tile_order;          // [launch_tiles] tiles with long conditional lists first (written by k_tile_plan, counters after plan_cursor)
+    int heavy_cond;           // a tile is 'heavy' from this many conditional records on
     int probe_stride;         // > 0: k_tile_plan only classifies every probe_stride-th tile and adds the class sizes to `probe`
     unsigned long long* probe; // [5] far, conditional, direct, exact records, fallback tiles
 };
@@ -776,6 +778,13 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
         h.offset = s_off;
         h.pad = 0;
         a.plan_hdr[blockIdx.x] = h;
+        // Longest-processing-time-first: the query kernel takes heavy tiles (long conditional walk, or generic fallback) before
+        // light ones, so the tail of the launch is made of short CTAs. Heavy tiles fill the order from the front, light ones
+        // from the back; within a class the order stays close to the launch order (neighbouring tiles share records in L1/L2).
+        unsigned int* cnt = reinterpret_cast<unsigned int*>(a.plan_cursor + 1);
+        const bool heavy = fallback || n_cond >= a.heavy_cond;
+        const int pos = heavy ? (int)atomicAdd(cnt, 1u) : a.launch_tiles - 1 - (int)atomicAdd(cnt + 1, 1u);
+        a.tile_order[pos] = (int)blockIdx.x;
         if (a.stats) {
             // executed work of the plan: far-set evaluations at the sample points (counted as far-field evaluations)
             atomicAdd(a.stats + 1, (unsigned long long)(fallback ? 0 : n_far) * kTileSamples);
@@ -804,7 +813,7 @@ __global__ void __launch_bounds__(kQueryThreads, WN_TQ_MIN_CTAS) k_tile_query(co
         if (lane == 0) task = atomicAdd(&s_next, 1);
         task = __shfl_sync(kFull, task, 0);
         if (task >= n_task) break;
-        const int tile = tile0 + task / kQueryWarps, sub = task % kQueryWarps;
+        const int tile = __ldg(a.tile_order + tile0 + task / kQueryWarps), sub = task % kQueryWarps;
         float qx[QPL], qy[QPL], qz[QPL], acc[QPL];
         bool valid[QPL];
         int64_t oidx[QPL];
