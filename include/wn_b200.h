@@ -173,6 +173,17 @@ WN_API wn_status wn_exact(const wn_engine* e, const float* q_xyz, int64_t n, flo
 WN_API wn_status wn_exact_grid(const wn_engine* e, const float origin[3], const float spacing[3], const int64_t dims[3],
                                int64_t z_begin, int64_t z_end, float* out_omega, uint8_t* out_inside, void* stream);
 
+/* ---- narrow-band signed distance on a lattice (replaces the OpenVDB meshToVolume call of -------
+ * volume::mesh_to_volume with Sign::WindingNumber, modules/volume/src/mesh_to_volume.cpp:147-183) ----------------------
+ * out_sdf[(z*ny + y)*nx + x] = s * min(distance from the cell centre origin + spacing*(ijk + 1/2) to the mesh, band), with
+ * s = -1 where the winding-number predicate (wn_is_inside, accuracy `beta`) holds and +1 elsewhere; WN_SDF_UNSIGNED skips
+ * the predicate (s = +1). band is in world units (the reference uses 3 voxels on either side). The distance is exact:
+ * closest triangle, searched on the engine's own hierarchy. out_sdf: host or device. num_active (optional, host): number of
+ * cells with distance < band (the narrow band OpenVDB would keep active). */
+#define WN_SDF_UNSIGNED 4u
+WN_API wn_status wn_sdf_grid(const wn_engine* e, const float origin[3], const float spacing[3], const int64_t dims[3], float band,
+                             float beta, uint32_t flags, float* out_sdf, int64_t* num_active, void* stream);
+
 /* ---- tree replication across GPUs ---------------------------------------------------------------------------
  * The packed tree is position independent: wn_tree_pack writes it into one contiguous buffer (host or device) that
  * can be broadcast (NCCL over NVLink) and adopted on another device with wn_create_from_packed. */

@@ -20,6 +20,7 @@
 
 #include "../../include/wn_b200.h"
 #include "wn_query.cuh"
+#include "wn_sdf.cuh"
 
 namespace {
 
@@ -189,7 +190,7 @@ struct wn_engine
     std::vector<void*> kept_allocs; // device allocations that back the kept arrays
     // per-engine query scratch, guarded by mu
     mutable std::mutex mu;
-    mutable DevBuf s_in, s_out_f, s_out_b, s_sort, s_stats, s_partial, s_plan_hdr, s_plan_items, s_plan_samples, s_plan_order;
+    mutable DevBuf s_in, s_out_f, s_out_b, s_sort, s_stats, s_partial, s_plan_hdr, s_plan_items, s_plan_samples, s_plan_order, s_sdf_inside;
     mutable PinnedBuf p_small;
     mutable cudaStream_t copy_stream = nullptr; // D2H of finished batches while the next batch computes
     mutable int64_t last_plan_tiles = 0;        // tiles of the last k_tile_plan launch (wn_debug_last_plan)
@@ -1177,6 +1178,7 @@ wn_status wn_destroy(wn_engine* e)
         e->s_plan_items.release();
         e->s_plan_samples.release();
         e->s_plan_order.release();
+        e->s_sdf_inside.release();
         e->p_small.release();
         if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     }
@@ -1350,6 +1352,62 @@ wn_status wn_debug_topology(const wn_engine* e, int32_t* child, int64_t capacity
         child[k] = c < 0 ? WN_CHILD_EMPTY : (c >= e->kept_nI ? wn_enc_tri((int)prim[(size_t)(c - e->kept_nI)]) : c);
     }
     return WN_OK;
+}
+
+wn_status wn_sdf_grid(const wn_engine* e, const float* origin, const float* spacing, const int64_t* dims, float band, float beta,
+                      uint32_t flags, float* out_sdf, int64_t* num_active, void* stream)
+{
+    if (!e) return fail(WN_ERR_INVALID_ARGUMENT, "engine is null");
+    if (!out_sdf) return fail(WN_ERR_INVALID_ARGUMENT, "no output requested");
+    if (!(band > 0.0f) || !(band <= 3.0e38f)) return fail(WN_ERR_INVALID_ARGUMENT, "band must be positive and finite");
+    wn::GridDesc g;
+    int64_t n = 0;
+    wn_status s = check_grid(origin, spacing, dims, 0, dims ? dims[2] : 0, g, n);
+    if (s != WN_OK) return s;
+    if (num_active) *num_active = 0;
+    if (n == 0) return WN_OK;
+    const int64_t tiles = (int64_t)((g.nx + 7) / 8) * ((g.ny + 7) / 8) * ((g.nz + 7) / 8);
+    if (tiles > INT_MAX) return fail(WN_ERR_UNSUPPORTED, "lattice too large for one launch; split it");
+    DeviceGuard guard(e->device);
+    if (!guard.ok) return fail(WN_ERR_CUDA, "cannot select CUDA device %d", e->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t* d_inside = nullptr;
+    if (!(flags & WN_SDF_UNSIGNED)) {
+        {
+            std::lock_guard<std::mutex> lock(e->mu);
+            WN_CUDA(e->s_sdf_inside.reserve((size_t)n));
+            d_inside = (uint8_t*)e->s_sdf_inside.p;
+        }
+        // the sign: the reference's interior test, FastWindingNumber::is_inside at every voxel centre
+        s = grid_impl(e, origin, spacing, dims, 0, dims[2], beta, flags & WN_QUERY_NO_TILING, nullptr, d_inside, nullptr, stream);
+        if (s != WN_OK) return s;
+    }
+    std::lock_guard<std::mutex> lock(e->mu);
+    OutBufs ob;
+    s = prepare_outputs(e, n, out_sdf, nullptr, ob);
+    if (s != WN_OK) return s;
+    WN_CUDA(e->s_stats.reserve(16 * sizeof(unsigned long long)));
+    unsigned long long* d_active = (unsigned long long*)e->s_stats.p;
+    WN_CUDA(cudaMemsetAsync(d_active, 0, sizeof(unsigned long long), st));
+    wn::SdfArgs a;
+    memset(&a, 0, sizeof(a));
+    a.tree = e->view;
+    a.g = g;
+    a.tiles_x = (g.nx + 7) / 8;
+    a.tiles_y = (g.ny + 7) / 8;
+    a.band = band;
+    a.inside = d_inside;
+    a.out = ob.d_omega;
+    a.active = d_active;
+    wn::k_sdf_grid<<<(int)tiles, wn::kQueryThreads, 0, st>>>(a);
+    WN_CUDA(cudaGetLastError());
+    if (num_active) {
+        unsigned long long h = 0;
+        WN_CUDA(cudaMemcpyAsync(&h, d_active, sizeof(h), cudaMemcpyDeviceToHost, st));
+        WN_CUDA(cudaStreamSynchronize(st));
+        *num_active = (int64_t)h;
+    }
+    return finish_outputs(n, ob, st);
 }
 
 wn_status wn_debug_last_plan(const wn_engine* e, int32_t* out, int64_t capacity_tiles, int64_t* num_tiles)

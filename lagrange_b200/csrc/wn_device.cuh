@@ -620,6 +620,58 @@ WN_HD float wn_tri_solid_angle(float qx, float qy, float qz, const float4& a, co
     return 2.0f * atan2f(num, den);
 }
 
+// Squared distance from p to triangle (a, b, c): closest-point regions (Ericson, Real-Time Collision Detection, 5.1.5).
+WN_HD float wn_point_tri_dist2(float px, float py, float pz, const float4& a, const float4& b, const float4& c)
+{
+    const float abx = b.x - a.x, aby = b.y - a.y, abz = b.z - a.z;
+    const float acx = c.x - a.x, acy = c.y - a.y, acz = c.z - a.z;
+    const float apx = px - a.x, apy = py - a.y, apz = pz - a.z;
+    const float d1 = abx * apx + aby * apy + abz * apz;
+    const float d2 = acx * apx + acy * apy + acz * apz;
+    float cx, cy, cz; // closest point
+    if (d1 <= 0.0f && d2 <= 0.0f) {
+        cx = a.x, cy = a.y, cz = a.z;
+    } else {
+        const float bpx = px - b.x, bpy = py - b.y, bpz = pz - b.z;
+        const float d3 = abx * bpx + aby * bpy + abz * bpz;
+        const float d4 = acx * bpx + acy * bpy + acz * bpz;
+        if (d3 >= 0.0f && d4 <= d3) {
+            cx = b.x, cy = b.y, cz = b.z;
+        } else {
+            const float vc = d1 * d4 - d3 * d2;
+            if (vc <= 0.0f && d1 >= 0.0f && d3 <= 0.0f) {
+                const float v = d1 / (d1 - d3);
+                cx = a.x + v * abx, cy = a.y + v * aby, cz = a.z + v * abz;
+            } else {
+                const float cpx = px - c.x, cpy = py - c.y, cpz = pz - c.z;
+                const float d5 = abx * cpx + aby * cpy + abz * cpz;
+                const float d6 = acx * cpx + acy * cpy + acz * cpz;
+                if (d6 >= 0.0f && d5 <= d6) {
+                    cx = c.x, cy = c.y, cz = c.z;
+                } else {
+                    const float vb = d5 * d2 - d1 * d6;
+                    if (vb <= 0.0f && d2 >= 0.0f && d6 <= 0.0f) {
+                        const float w = d2 / (d2 - d6);
+                        cx = a.x + w * acx, cy = a.y + w * acy, cz = a.z + w * acz;
+                    } else {
+                        const float va = d3 * d6 - d5 * d4;
+                        if (va <= 0.0f && (d4 - d3) >= 0.0f && (d5 - d6) >= 0.0f) {
+                            const float w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
+                            cx = b.x + w * (c.x - b.x), cy = b.y + w * (c.y - b.y), cz = b.z + w * (c.z - b.z);
+                        } else {
+                            const float denom = 1.0f / (va + vb + vc);
+                            const float v = vb * denom, w = vc * denom;
+                            cx = a.x + abx * v + acx * w, cy = a.y + aby * v + acy * w, cz = a.z + abz * v + acz * w;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    const float dx = px - cx, dy = py - cy, dz = pz - cz;
+    return dx * dx + dy * dy + dz * dz;
+}
+
 // FastWindingNumber.cpp:66 computes  omega / (4.f * pi) > 0.5f  with pi a double (constants.h:16), i.e. in double.
 // Over all floats this is exactly  omega >= 6.2831854820251465f  (the float nearest to, and just above, 2 pi);
 // tests/test_predicate.py checks the equivalence against the oracle's literal restatement.

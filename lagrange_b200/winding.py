@@ -263,6 +263,23 @@ class FastWindingNumber:
             out.extend(range(layer * 8, min(nz, layer * 8 + 8)))
         return out
 
+    def sdf_grid(self, origin, spacing, dims, band, accuracy_scale=None, signed=True, device_output=False, out=None, tiling=True):
+        """Narrow-band distance to the mesh at the lattice's cell centres, negative where ``is_inside`` holds, clamped to
+        +-band (world units). Returns (sdf [nz, ny, nx] float32, number of cells with distance < band). wn_sdf_grid."""
+        o, s, d, _, _, n = self._grid_args(origin, spacing, dims, None)
+        if out is None:
+            if device_output:
+                import torch
+
+                out = torch.empty(n, dtype=torch.float32, device="cuda")
+            else:
+                out = np.empty(n, dtype=np.float32)
+        flags = self._flags(False, tiling) | (0 if signed else 4)
+        active = ctypes.c_int64()
+        self._check(self._lib.wn_sdf_grid(self._handle(), o, s, d, float(band), float(accuracy_scale or 0.0), flags,
+                                          _Buf(out, np.float32, writable=True).ptr, ctypes.byref(active), _current_stream_ptr()))
+        return out.reshape(int(dims[2]), int(dims[1]), int(dims[0])), int(active.value)
+
     def is_inside_grid(self, origin, spacing, dims, **kw):
         return self.query_grid(origin, spacing, dims, want_inside=True, want_omega=False, **kw)[1]
 

@@ -48,6 +48,7 @@ def lib() -> ctypes.CDLL:
         L = ctypes.CDLL(_LIB_PATH)
         L.wno_num_threads.restype = ctypes.c_int
         L.wno_exact64.argtypes = [_f32p, ctypes.c_int64, _i32p, ctypes.c_int64, _f32p, ctypes.c_int64, _f64p, ctypes.c_int]
+        L.wno_distance64.argtypes = [_f32p, ctypes.c_int64, _i32p, ctypes.c_int64, _f32p, ctypes.c_int64, _f64p, ctypes.c_int]
         L.wno_exact32.argtypes = [_f32p, ctypes.c_int64, _i32p, ctypes.c_int64, _f32p, ctypes.c_int64, _f32p, ctypes.c_int]
         L.wno_ref_create.restype = ctypes.c_void_p
         L.wno_ref_create.argtypes = [_f32p, ctypes.c_int64, _i32p, ctypes.c_int64, ctypes.c_int]
@@ -89,6 +90,14 @@ def exact64(vertices, facets, queries, nthreads: int = 0) -> np.ndarray:
     v, f, q = _f32(vertices), _i32(facets), _f32(queries).reshape(-1, 3)
     out = np.empty(len(q), dtype=np.float64)
     lib().wno_exact64(_p(v, _f32p), len(v), _p(f, _i32p), len(f), _p(q, _f32p), len(q), _p(out, _f64p), nthreads)
+    return out
+
+
+def distance64(vertices, facets, queries, nthreads: int = 0) -> np.ndarray:
+    """Ground truth for the narrow-band distance: double-precision brute-force distance to the closest triangle."""
+    v, f, q = _f32(vertices), _i32(facets), _f32(queries).reshape(-1, 3)
+    out = np.empty(len(q), dtype=np.float64)
+    lib().wno_distance64(_p(v, _f32p), len(v), _p(f, _i32p), len(f), _p(q, _f32p), len(q), _p(out, _f64p), nthreads)
     return out
 
 

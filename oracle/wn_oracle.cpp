@@ -790,6 +790,59 @@ int wno_exact64(const float* v, int64_t nV, const int32_t* tri, int64_t nT, cons
     return 0;
 }
 
+// ---- unsigned distance (ground truth for the narrow-band distance kernel K10) -------------
+// Double precision, brute force over all triangles. Deliberately a different formulation from the kernel's region walk:
+// the foot of the perpendicular if it falls inside the triangle, else the nearest of the three edges.
+static double seg_dist2_d(const double* p, const double* a, const double* b)
+{
+    const double ab[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
+    const double ap[3] = {p[0] - a[0], p[1] - a[1], p[2] - a[2]};
+    const double len2 = ab[0] * ab[0] + ab[1] * ab[1] + ab[2] * ab[2];
+    double t = len2 > 0 ? (ap[0] * ab[0] + ap[1] * ab[1] + ap[2] * ab[2]) / len2 : 0.0;
+    t = t < 0 ? 0 : (t > 1 ? 1 : t);
+    const double d[3] = {ap[0] - t * ab[0], ap[1] - t * ab[1], ap[2] - t * ab[2]};
+    return d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+}
+
+static double tri_dist2_d(const double* a, const double* b, const double* c, const double* p)
+{
+    const double e0[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
+    const double e1[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
+    const double n[3] = {e0[1] * e1[2] - e0[2] * e1[1], e0[2] * e1[0] - e0[0] * e1[2], e0[0] * e1[1] - e0[1] * e1[0]};
+    const double n2 = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
+    if (n2 > 0) {
+        const double ap[3] = {p[0] - a[0], p[1] - a[1], p[2] - a[2]};
+        // barycentric coordinates of the projection: u = n . (e0 x ap)... via the two cross products with the normal
+        const double c0[3] = {ap[1] * e1[2] - ap[2] * e1[1], ap[2] * e1[0] - ap[0] * e1[2], ap[0] * e1[1] - ap[1] * e1[0]};
+        const double c1[3] = {e0[1] * ap[2] - e0[2] * ap[1], e0[2] * ap[0] - e0[0] * ap[2], e0[0] * ap[1] - e0[1] * ap[0]};
+        const double v = (c0[0] * n[0] + c0[1] * n[1] + c0[2] * n[2]) / n2; // weight of b
+        const double w = (c1[0] * n[0] + c1[1] * n[1] + c1[2] * n[2]) / n2; // weight of c
+        if (v >= 0 && w >= 0 && v + w <= 1) {
+            const double h = ap[0] * n[0] + ap[1] * n[1] + ap[2] * n[2];
+            return h * h / n2;
+        }
+    }
+    return std::min(seg_dist2_d(p, a, b), std::min(seg_dist2_d(p, b, c), seg_dist2_d(p, c, a)));
+}
+
+int wno_distance64(const float* v, int64_t nV, const int32_t* tri, int64_t nT, const float* q, int64_t nQ, double* out, int nthreads)
+{
+    (void)nV;
+    nthreads = resolve_threads(nthreads);
+    std::vector<double> tv(size_t(nT) * 9);
+    for (int64_t t = 0; t < nT; ++t)
+        for (int k = 0; k < 3; ++k)
+            for (int a = 0; a < 3; ++a) tv[size_t(t) * 9 + k * 3 + a] = double(v[size_t(tri[t * 3 + k]) * 3 + a]);
+#pragma omp parallel for schedule(dynamic, 64) num_threads(nthreads)
+    for (int64_t i = 0; i < nQ; ++i) {
+        const double qq[3] = {double(q[i * 3]), double(q[i * 3 + 1]), double(q[i * 3 + 2])};
+        double best = std::numeric_limits<double>::infinity();
+        for (int64_t t = 0; t < nT; ++t) best = std::min(best, tri_dist2_d(&tv[t * 9], &tv[t * 9 + 3], &tv[t * 9 + 6], qq));
+        out[i] = std::sqrt(best);
+    }
+    return 0;
+}
+
 // ---- reference restatement ------------------------------------------------------------------------------------
 void* wno_ref_create(const float* v, int64_t nV, const int32_t* tri, int64_t nT, int order)
 {

@@ -49,6 +49,7 @@ def lib():
         L.emul_query.argtypes = [ctypes.c_void_p, _f32p, ctypes.c_int64, ctypes.c_float, _f32p, _u64p]
         L.emul_inside_from_omega.restype = ctypes.c_int
         L.emul_inside_from_omega.argtypes = [ctypes.c_float]
+        L.emul_point_tri_dist2.argtypes = [_f32p, _f32p, ctypes.c_int64, _f32p]
         L.emul_lattice_coord.restype = ctypes.c_float
         L.emul_lattice_coord.argtypes = [ctypes.c_float, ctypes.c_float, ctypes.c_int]
         _lib = L
@@ -110,3 +111,12 @@ class EmulEngine:
         lib().emul_query(self._h, q.ctypes.data_as(_f32p), len(q), beta, out.ctypes.data_as(_f32p),
                          cnt.ctypes.data_as(_u64p) if counters else None)
         return (out, cnt) if counters else out
+
+
+def point_tri_dist2(points, tris):
+    """Squared distances point[i] -> triangle tris[i] ([n,3,3]) with the device's float routine (wn_point_tri_dist2)."""
+    p = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 3)
+    t = np.ascontiguousarray(tris, dtype=np.float32).reshape(-1, 9)
+    out = np.empty(len(p), dtype=np.float32)
+    lib().emul_point_tri_dist2(p.ctypes.data_as(_f32p), t.ctypes.data_as(_f32p), len(p), out.ctypes.data_as(_f32p))
+    return out

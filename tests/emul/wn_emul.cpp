@@ -237,6 +237,16 @@ int emul_inside_from_omega(float omega)
     return wn_inside_from_omega(omega) ? 1 : 0;
 }
 
+// distance from each point to each triangle (a, b, c rows of 3 floats), squared, with the device's float routine
+void emul_point_tri_dist2(const float* p, const float* tri9, int64_t n, float* out)
+{
+    for (int64_t i = 0; i < n; ++i) {
+        const float* t = tri9 + 9 * i;
+        out[i] = wn_point_tri_dist2(p[3 * i], p[3 * i + 1], p[3 * i + 2], make_float4(t[0], t[1], t[2], 0.0f), make_float4(t[3], t[4], t[5], 0.0f),
+                                    make_float4(t[6], t[7], t[8], 0.0f));
+    }
+}
+
 float emul_lattice_coord(float origin, float spacing, int i)
 {
     return wn_lattice_coord(origin, spacing, i);
