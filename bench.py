@@ -187,6 +187,28 @@ def run_reference(args):
     }), flush=True)
 
 
+def profile_traffic():
+    """DRAM bytes (read + write) per launch of the dominant kernel, k_tile_query, from the committed `ncu --set full` summary
+    (profiles/r1k_tile_plan_query_ncu_full.txt: one launch = 131072 tiles = 67.1 M queries). The tree (362 MB) is part of it:
+    every launch streams the records it touches from HBM once; the algorithmic output is 1 byte per query."""
+    path = os.path.join(ROOT, "profiles", "r1k_tile_plan_query_ncu_full.txt")
+    try:
+        rd = wr = None
+        in_query = False
+        for ln in open(path):
+            if ln.startswith("## "):
+                in_query = "k_tile_query" in ln
+            elif in_query and ln.startswith("dram__bytes_read.sum "):
+                rd = float(ln.split()[-1]) * 1e6
+            elif in_query and ln.startswith("dram__bytes_write.sum "):
+                wr = float(ln.split()[-1]) * 1e6
+        return None if rd is None or wr is None else {"bytes_per_launch": rd + wr, "queries_per_launch": 131072 * 512,
+                                                      "source": "profiles/r1k_tile_plan_query_ncu_full.txt (k_tile_query)"}
+    except Exception:
+        return None
+
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -342,6 +364,7 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    ncu_traffic = profile_traffic()
     algo_bytes = n_local * 1  # implicit lattice in, 1 byte out per query (12 B in only for explicit points)
     roofline = {
         "bound": "fp32_fma", "achieved": achieved_tflops, "peak": fma_peak, "unit": "TFLOP/s", "frac": achieved_tflops / fma_peak,
@@ -353,7 +376,7 @@ def main():
         "reference_algorithm": {"flops_per_query": per_point["algorithmic_flops"] / nq, "tests_per_query": per_point["node_tests"] / nq,
                                 "evals_per_query": per_point["far_field_evals"] / nq, "exact_tris_per_query": per_point["exact_triangles"] / nq,
                                 "equivalent_tflops": per_point["algorithmic_flops"] / nq * n_local / (ms_local * 1e-3) / 1e12},
-        "traffic": None,
+        "traffic": None if ncu_traffic is None else ncu_traffic["bytes_per_launch"], "traffic_detail": ncu_traffic,
         "hbm": {"achieved_gbs": algo_bytes / (ms_local * 1e-3) / 1e9, "peak_gbs": hbm_peak, "peak_source": hbm_src,
                 "frac": algo_bytes / (ms_local * 1e-3) / 1e9 / hbm_peak},
     }
@@ -371,9 +394,9 @@ def main():
                    "leaf_size": args.leaf_size, "tiled": tiled},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 60, "d2h_bytes_per_step": n_total, "ms_per_step": e2e_ms,
                 "api": "FastWindingNumber.query_grid -> wn_query_grid with a pinned HOST output buffer (lattice is implicit: 60-byte descriptor in)"},
-        # per step and rank: tiled = (k_tile_plan + k_tile_query) per batch of <= 65536 tiles (the probe that picks the path runs
+        # per step and rank: tiled = (k_tile_plan + k_tile_query) per batch of <= 131072 tiles (the probe that picks the path runs
         # once, in the warm-up, and is remembered per lattice); generic = one k_query
-        "gpu_launches": args.steps * (2 * max(1, -(-(-(-n_local // 512)) // 65536)) if tiled else 1),
+        "gpu_launches": args.steps * (2 * max(1, -(-(-(-n_local // 512)) // 131072)) if tiled else 1),
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         "build": {k: build_info.get(k) for k in ("build_ms", "build_ms_morton", "build_ms_sort", "build_ms_hierarchy", "build_ms_moments",
                                                  "build_ms_pack", "build_wall_ms", "num_entries", "tree_bytes", "max_depth")},

@@ -47,7 +47,10 @@ constexpr int kQueryThreads = 256;
 constexpr int kQueryWarps = kQueryThreads / 32;
 constexpr int kTileQPL = 2;                       // queries per lane in k_tile_query: 8 warps * 32 * 2 = 512 = 8^3
 constexpr int kTileQueries = kQueryThreads * kTileQPL;
-constexpr int kPlanThreads = 128;                 // k_tile_plan: latency bound, small CTAs so that many are resident
+#ifndef WN_PLAN_THREADS
+#define WN_PLAN_THREADS 128
+#endif
+constexpr int kPlanThreads = WN_PLAN_THREADS;                 // k_tile_plan: latency bound, small CTAs so that many are resident
 constexpr int kPlanWarps = kPlanThreads / 32;
 constexpr int kTileAllCap = 2048;                 // classified records per tile (conditional + direct + exact)
 constexpr int kTileFrontCap = 1024;               // breadth-first frontier
@@ -551,7 +554,7 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
         }
     }
     if (tid < 8) s_cnt[tid] = 0;
-    if (tid <= kPlanMaxRounds) s_fcnt[tid] = 0;
+    for (int r = tid; r <= kPlanMaxRounds; r += kPlanThreads) s_fcnt[r] = 0;
     if (tid == 0) s_off = 0;
     __syncthreads();
     if (tid == 0) {
@@ -662,7 +665,8 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
     //      parallel, with shuffles; long ones by the whole CTA. -------------------------------------------------------
     int* const lists[4] = {s_cond, s_far, s_dir, s_exact};
     const int lens[4] = {n_cond, n_far, n_dir, n_ex};
-    if (lens[wid] > 1 && lens[wid] <= 64) plan_warp_sort64(lists[wid], lens[wid]);
+    for (int l = wid; l < 4; l += kPlanWarps)
+        if (lens[l] > 1 && lens[l] <= 64) plan_warp_sort64(lists[l], lens[l]);
     __syncthreads();
 #pragma unroll
     for (int l = 0; l < 4; ++l) {
@@ -762,11 +766,11 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
     }
     fallback = __syncthreads_or((int)(bad || fallback)) != 0;
     float* sout = a.plan_samples + (int64_t)blockIdx.x * kTileSampleStride;
-    if (!fallback && tid < kTileSamples) {
+    for (int j = tid; !fallback && j < kTileSamples; j += kPlanThreads) {
         float s = 0.0f;
 #pragma unroll
-        for (int w = 0; w < kPlanWarps; ++w) s += s_samp[w][tid];
-        sout[tid] = s;
+        for (int w = 0; w < kPlanWarps; ++w) s += s_samp[w][j];
+        sout[j] = s;
     }
     if (tid < 8) sout[kTileSamples + tid] = s_geo[tid];
     if (tid == 0) {
