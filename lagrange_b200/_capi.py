@@ -27,7 +27,7 @@ class wn_options(ctypes.Structure):
     _fields_ = [
         ("struct_size", ctypes.c_uint32), ("device", ctypes.c_int32), ("accuracy_scale", ctypes.c_float), ("order", ctypes.c_int32),
         ("leaf_size", ctypes.c_int32), ("morton_bits", ctypes.c_int32), ("radius_mode", ctypes.c_int32),
-        ("approximate_single_triangles", ctypes.c_int32), ("keep_build_data", ctypes.c_int32), ("reserved", ctypes.c_int32 * 7),
+        ("approximate_single_triangles", ctypes.c_int32), ("keep_build_data", ctypes.c_int32), ("hierarchy", ctypes.c_int32), ("reserved", ctypes.c_int32 * 6),
     ]
 
 

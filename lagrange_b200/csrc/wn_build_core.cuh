@@ -48,6 +48,79 @@ static inline unsigned wn_host_atomic_max_u(unsigned* p, unsigned v)
 #define WN_ERR_TOPOLOGY_BAD_CHILD 1
 #define WN_ERR_TOPOLOGY_DEPTH 2
 
+// ---- balanced k-d hierarchy (K3', wn_kd.cuh): the implicit tree over the final triangle order ------------------------
+// Range [lo, lo + n) and path bits of the level-`level` node that contains position p in the implicit balanced tree over N.
+WN_HD void wn_kd_locate(int N, int p, int level, int& lo, int& n, unsigned& path)
+{
+    lo = 0;
+    n = N;
+    path = 0;
+    for (int l = 0; l < level; ++l) {
+        const int nl = n >= 2 ? n / 2 : n; // a single triangle stays where it is (path bit 0)
+        if (p < lo + nl) {
+            n = nl;
+            path = path << 1;
+        } else {
+            lo += nl;
+            n -= nl;
+            path = (path << 1) | 1u;
+        }
+    }
+}
+
+// Internal node of a range [lo, lo + n), n >= 2: the index of the gap it splits (between lo + n/2 - 1 and lo + n/2). Every
+// gap 0..N-2 is split by exactly one range, so gaps number the N-1 internal nodes; the root's gap and gap 0 swap so that
+// the root is node 0 like in the Karras layout.
+WN_HD int wn_kd_node_id(int N, int lo, int n)
+{
+    const int gap = lo + n / 2 - 1;
+    const int root_gap = N / 2 - 1;
+    return gap == root_gap ? 0 : (gap == 0 ? root_gap : gap);
+}
+
+
+WN_HD int wn_kd_axis(const float ext[3])
+{
+    return (ext[0] >= ext[1] && ext[0] >= ext[2]) ? 0 : (ext[1] >= ext[2] ? 1 : 2);
+}
+
+// 16-bit position of coordinate c inside [blo, blo + ext] (unfused, so host emulation and device agree)
+WN_HD unsigned wn_kd_quant(float c, float blo, float ext)
+{
+    if (!(ext > 0.0f) || !(c == c)) return 0u;
+    const float u = WN_MUL(WN_DIV(WN_SUB(c, blo), ext), 65535.0f);
+    return (unsigned)(u < 0.0f ? 0.0f : (u > 65535.0f ? 65535.0f : u));
+}
+
+// Internal node that splits gap g: find its range by descending from the root, emit children / parents / slots in the
+// layout of wn_lbvh_node (internal nodes 0..N-2, leaf of sorted position p = node N-1 + p). parent[] was preset to -1.
+WN_HD void wn_kd_emit_node(int N, int g, int* child, int* parent, unsigned char* slot)
+{
+    int lo = 0, n = N;
+    while (true) {
+        const int nl = n / 2;
+        const int gap = lo + nl - 1;
+        if (g == gap) break;
+        if (g < gap) {
+            n = nl;
+        } else {
+            lo += nl;
+            n -= nl;
+        }
+    }
+    const int id = wn_kd_node_id(N, lo, n);
+    const int nI = N - 1;
+    const int nl = n / 2, nr = n - nl;
+    const int cl = nl >= 2 ? wn_kd_node_id(N, lo, nl) : nI + lo;
+    const int cr = nr >= 2 ? wn_kd_node_id(N, lo + nl, nr) : nI + lo + nl;
+    child[2 * (size_t)id] = cl;
+    child[2 * (size_t)id + 1] = cr;
+    parent[cl] = id;
+    parent[cr] = id;
+    slot[cl] = 0;
+    slot[cr] = 1;
+}
+
 struct WnBuild
 {
     // mesh

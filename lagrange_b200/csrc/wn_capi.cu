@@ -20,6 +20,7 @@
 
 #include "../../include/wn_b200.h"
 #include "wn_query.cuh"
+#include "wn_kd.cuh"
 #include "wn_sdf.cuh"
 
 namespace {
@@ -363,6 +364,7 @@ wn_status validate_options(const wn_options* in, wn_options* out, bool imported)
     if (out->leaf_size < 1 || out->leaf_size > WN_MAX_LEAF_SIZE) return fail(WN_ERR_INVALID_ARGUMENT, "leaf_size must be in [1, %d]", WN_MAX_LEAF_SIZE);
     if (out->morton_bits != 30 && out->morton_bits != 63) return fail(WN_ERR_INVALID_ARGUMENT, "morton_bits must be 30 or 63");
     if (out->radius_mode != WN_RADIUS_BOX_CORNER && out->radius_mode != WN_RADIUS_VERTEX) return fail(WN_ERR_INVALID_ARGUMENT, "bad radius_mode");
+    if (out->hierarchy != WN_HIERARCHY_LBVH && out->hierarchy != WN_HIERARCHY_KD) return fail(WN_ERR_INVALID_ARGUMENT, "bad hierarchy");
     return WN_OK;
 }
 
@@ -467,6 +469,7 @@ wn_status create_impl(const float* v_xyz, int64_t nV, const int32_t* tri, int64_
             add((size_t)nT * 4);
             add((size_t)nT * 4);
             add((size_t)wn::sort_scratch_bytes(nT));
+            if (opt.hierarchy == WN_HIERARCHY_KD) add((size_t)nT * 6 * sizeof(int));
         } else {
             add((size_t)nI_max * W * 4);
             add((size_t)nN_max * 4);
@@ -534,21 +537,48 @@ wn_status create_impl(const float* v_xyz, int64_t nV, const int32_t* tri, int64_
             WN_CUDA_C(cudaStreamSynchronize(st));
             if (h_err) return cleanup(fail(WN_ERR_INVALID_ARGUMENT, "triangle references a vertex index outside [0, num_vertices)"));
         }
-        const int bpa = opt.morton_bits == 63 ? 21 : 10;
-        wn::k_morton<uint64_t><<<wn::grid_for(nT), wn::kBuildThreads, 0, st>>>(d_v, d_tri, (int)nT, d_small, bpa, k0, v0);
-        WN_CUDA_C(cudaGetLastError());
-        tm.mark(); // 1: morton
-        const int which = wn::radix_sort_pairs<uint64_t>(k0, v0, k1, v1, nT, 0, opt.morton_bits, sort_scratch, st);
-        WN_CUDA_C(cudaGetLastError());
-        const uint64_t* keys = which ? k1 : k0;
-        d_prim = which ? v1 : v0;
-        tm.mark(); // 2: sort
+        const bool kd = opt.hierarchy == WN_HIERARCHY_KD && nT >= 2;
+        const uint64_t* keys = nullptr;
+        if (!kd) {
+            const int bpa = opt.morton_bits == 63 ? 21 : 10;
+            wn::k_morton<uint64_t><<<wn::grid_for(nT), wn::kBuildThreads, 0, st>>>(d_v, d_tri, (int)nT, d_small, bpa, k0, v0);
+            WN_CUDA_C(cudaGetLastError());
+            tm.mark(); // 1: morton
+            const int which = wn::radix_sort_pairs<uint64_t>(k0, v0, k1, v1, nT, 0, opt.morton_bits, sort_scratch, st);
+            WN_CUDA_C(cudaGetLastError());
+            keys = which ? k1 : k0;
+            d_prim = which ? v1 : v0;
+            tm.mark(); // 2: sort
+        } else {
+            // K3': balanced k-d order (wn_kd.cuh): per level, node centroid bounds -> keys -> one stable sort
+            int levels = 0;
+            while (((int64_t)1 << levels) < nT) ++levels;
+            int* d_bounds = nullptr;
+            WN_CUDA_C(dalloc((void**)&d_bounds, (size_t)nT * 6 * sizeof(int)));
+            wn::k_iota<<<wn::grid_for(nT), wn::kBuildThreads, 0, st>>>(v0, (int)nT);
+            tm.mark(); // 1
+            unsigned *cur = v0, *other = v1;
+            for (int l = 0; l < levels; ++l) {
+                const int nodes = 1 << l; // < nT
+                wn::k_kd_init_bounds<<<wn::grid_for((int64_t)nodes * 6), wn::kBuildThreads, 0, st>>>(d_bounds, nodes);
+                wn::k_kd_bounds<<<wn::grid_for(nT), wn::kBuildThreads, 0, st>>>(d_v, d_tri, cur, (int)nT, l, d_bounds);
+                wn::k_kd_keys<<<wn::grid_for(nT), wn::kBuildThreads, 0, st>>>(d_v, d_tri, cur, (int)nT, l, d_bounds, k0, nullptr);
+                const int which = wn::radix_sort_pairs<uint64_t>(k0, cur, k1, other, nT, 0, 16 + l, sort_scratch, st);
+                if (which) std::swap(cur, other);
+            }
+            WN_CUDA_C(cudaGetLastError());
+            d_prim = cur;
+            tm.mark(); // 2: order
+        }
         WN_CUDA_C(dalloc((void**)&b.child, (size_t)b.nI * 2 * sizeof(int)));
         WN_CUDA_C(dalloc((void**)&b.parent, (size_t)nN * sizeof(int)));
         WN_CUDA_C(dalloc((void**)&b.slot, (size_t)nN));
         WN_CUDA_C(cudaMemsetAsync(b.parent, 0xff, (size_t)nN * sizeof(int), st));
         WN_CUDA_C(cudaMemsetAsync(b.slot, 0, (size_t)nN, st));
-        if (nT >= 2) {
+        if (kd) {
+            wn::k_kd_tree<<<wn::grid_for(nT - 1), wn::kBuildThreads, 0, st>>>((int)nT, b.child, b.parent, b.slot);
+            WN_CUDA_C(cudaGetLastError());
+        } else if (nT >= 2) {
             wn::k_lbvh<<<wn::grid_for(nT - 1), wn::kBuildThreads, 0, st>>>(keys, (int)nT, b.child, b.parent, b.slot);
             WN_CUDA_C(cudaGetLastError());
         } else {
@@ -1146,6 +1176,7 @@ wn_status wn_options_init(wn_options* opt)
     opt->radius_mode = WN_RADIUS_BOX_CORNER;
     opt->approximate_single_triangles = 0;
     opt->keep_build_data = 0;
+    opt->hierarchy = WN_HIERARCHY_LBVH;
     return WN_OK;
 }
 

@@ -94,10 +94,12 @@ class FastWindingNumber:
       order           Taylor order 0/1/2 (reference default 2)
       topology        (n_nodes, width) int32 child table to import instead of building the LBVH (oracle-tree mode)
       leaf_size, morton_bits, radius_mode ('box_corner' | 'vertex'), approximate_single_triangles, device
+      hierarchy       'lbvh' (Morton + Karras, fastest build) or 'kd' (balanced object-median splits, faster queries)
     """
 
     def __init__(self, mesh=None, facets=None, *, accuracy_scale=2.0, order=2, topology=None, leaf_size=1, morton_bits=63,
-                 radius_mode="box_corner", approximate_single_triangles=None, keep_build_data=False, device=None, _handle=None):
+                 radius_mode="box_corner", approximate_single_triangles=None, keep_build_data=False, device=None, hierarchy="lbvh",
+                 _handle=None):
         self._h = None
         self._lib = _capi.lib()
         if _handle is not None:
@@ -132,6 +134,9 @@ class FastWindingNumber:
         opt.morton_bits = int(morton_bits)
         opt.radius_mode = {"box_corner": _capi.WN_RADIUS_BOX_CORNER, "vertex": _capi.WN_RADIUS_VERTEX}[radius_mode]
         opt.keep_build_data = 1 if keep_build_data else 0
+        if hierarchy not in ("lbvh", "kd"):
+            raise Error("hierarchy must be 'lbvh' or 'kd'")
+        opt.hierarchy = {"lbvh": 0, "kd": 1}[hierarchy]
         opt.device = -1 if device is None else int(device)
         if approximate_single_triangles is None:
             approximate_single_triangles = topology is not None

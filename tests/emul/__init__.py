@@ -35,7 +35,7 @@ def lib():
         L = ctypes.CDLL(_LIB)
         L.emul_build.restype = ctypes.c_void_p
         L.emul_build.argtypes = [_f32p, ctypes.c_int64, _i32p, ctypes.c_int64, _i32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
-                                 ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+                                 ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
         L.emul_destroy.argtypes = [ctypes.c_void_p]
         for name in ("emul_error", "emul_max_depth", "emul_width"):
             getattr(L, name).restype = ctypes.c_int
@@ -57,7 +57,8 @@ def lib():
 
 
 class EmulEngine:
-    def __init__(self, vertices, facets, child=None, leaf_size=1, order=2, radius_mode=0, approx_single=None, morton_bits=63):
+    def __init__(self, vertices, facets, child=None, leaf_size=1, order=2, radius_mode=0, approx_single=None, morton_bits=63,
+                 hierarchy="lbvh"):
         self.v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 3)
         self.f = np.ascontiguousarray(facets, dtype=np.int32).reshape(-1, 3)
         if approx_single is None:
@@ -69,7 +70,7 @@ class EmulEngine:
         else:
             nn, w, cp = 0, 0, None
         self._h = lib().emul_build(self.v.ctypes.data_as(_f32p), len(self.v), self.f.ctypes.data_as(_i32p), len(self.f), cp, nn, w,
-                                   leaf_size, order, radius_mode, approx_single, morton_bits)
+                                   leaf_size, order, radius_mode, approx_single, morton_bits, {"lbvh": 0, "kd": 1}[hierarchy])
 
     def __del__(self):
         if getattr(self, "_h", None):

@@ -33,7 +33,7 @@ extern "C" {
 
 // child_in == nullptr: LBVH build (Morton + stable sort + Karras). Otherwise imported topology (neutral encoding).
 void* emul_build(const float* v, int64_t nV, const int32_t* tri, int64_t nT, const int32_t* child_in, int64_t num_nodes, int width,
-                 int leaf_size, int order, int radius_mode, int approx_single, int morton_bits)
+                 int leaf_size, int order, int radius_mode, int approx_single, int morton_bits, int hierarchy)
 {
     Emul* e = new Emul;
     e->v.assign(v, v + nV * 3);
@@ -67,6 +67,55 @@ void* emul_build(const float* v, int64_t nV, const int32_t* tri, int64_t nT, con
                     hi[a] = std::max(hi[a], c);
                 }
             }
+        const int64_t nN = (int64_t)b.nI + b.nL;
+        e->child.assign((size_t)b.nI * 2, -1);
+        e->parent.assign(nN, -1);
+        e->slot.assign(nN, 0);
+        if (hierarchy == 1 && nT >= 2) {
+            // K3' (wn_kd.cuh): per level, node centroid bounds -> (path, 16-bit coordinate) keys -> stable sort
+            std::vector<unsigned> perm(nT);
+            std::iota(perm.begin(), perm.end(), 0u);
+            int levels = 0;
+            while (((int64_t)1 << levels) < nT) ++levels;
+            for (int l = 0; l < levels; ++l) {
+                const int nodes = 1 << l;
+                std::vector<float> nlo((size_t)nodes * 3, 3.4e38f), nhi((size_t)nodes * 3, -3.4e38f);
+                std::vector<uint64_t> key(nT);
+                for (int pass = 0; pass < 2; ++pass)
+                    for (int p = 0; p < (int)nT; ++p) {
+                        int rlo, rn;
+                        unsigned path;
+                        wn_kd_locate((int)nT, p, l, rlo, rn, path);
+                        const float* c = &cen[3 * (size_t)perm[p]];
+                        if (pass == 0) {
+                            if (rn < 2) continue;
+                            for (int a = 0; a < 3; ++a)
+                                if (c[a] == c[a]) {
+                                    nlo[3 * (size_t)path + a] = std::min(nlo[3 * (size_t)path + a], c[a]);
+                                    nhi[3 * (size_t)path + a] = std::max(nhi[3 * (size_t)path + a], c[a]);
+                                }
+                        } else {
+                            unsigned q = 0;
+                            if (rn >= 2) {
+                                float ext3[3];
+                                for (int a = 0; a < 3; ++a)
+                                    ext3[a] = nhi[3 * (size_t)path + a] >= nlo[3 * (size_t)path + a] ? nhi[3 * (size_t)path + a] - nlo[3 * (size_t)path + a] : 0.0f;
+                                const int axis = wn_kd_axis(ext3);
+                                q = wn_kd_quant(c[axis], nlo[3 * (size_t)path + axis], ext3[axis]);
+                            }
+                            key[p] = ((uint64_t)path << 16) | q;
+                        }
+                    }
+                std::vector<unsigned> idx2(nT);
+                std::iota(idx2.begin(), idx2.end(), 0u);
+                std::stable_sort(idx2.begin(), idx2.end(), [&](unsigned a, unsigned c2) { return key[a] < key[c2]; });
+                std::vector<unsigned> np(nT);
+                for (int64_t i = 0; i < nT; ++i) np[i] = perm[idx2[i]];
+                perm.swap(np);
+            }
+            e->prim = perm;
+            for (int g = 0; g < (int)nT - 1; ++g) wn_kd_emit_node((int)nT, g, e->child.data(), e->parent.data(), e->slot.data());
+        } else {
         const float ext = std::max(hi[0] - lo[0], std::max(hi[1] - lo[1], hi[2] - lo[2]));
         const float inv = ext > 0.0f ? 1.0f / ext : 0.0f;
         std::vector<uint64_t> keys(nT);
@@ -81,15 +130,12 @@ void* emul_build(const float* v, int64_t nV, const int32_t* tri, int64_t nT, con
         std::vector<uint64_t> sorted(nT);
         for (int64_t i = 0; i < nT; ++i) sorted[i] = keys[idx[i]];
         e->prim = idx;
-        const int64_t nN = (int64_t)b.nI + b.nL;
-        e->child.assign((size_t)b.nI * 2, -1);
-        e->parent.assign(nN, -1);
-        e->slot.assign(nN, 0);
         if (nT >= 2) {
             for (int i = 0; i < (int)nT - 1; ++i) wn_lbvh_node(sorted.data(), (int)nT, i, e->child.data(), e->parent.data(), e->slot.data());
         } else {
             e->child[0] = 1;
             e->parent[1] = 0;
+        }
         }
         b.child = e->child.data();
         b.parent = e->parent.data();

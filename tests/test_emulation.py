@@ -167,3 +167,38 @@ def test_inside_threshold_matches_the_reference_expression(oracle_mod, emul_mod)
         x = np.nextafter(x, np.float32(100))
     for v in (-1.0, 0.0, 6.28, 6.2832, 100.0, float("inf"), float("nan")):
         assert bool(L.emul_inside_from_omega(v)) == oracle_mod.inside_predicate(v)
+
+
+def test_kd_hierarchy_is_balanced_and_complete(emul_mod, prim, oracle_mod):
+    """K3' (wn_kd.cuh): the balanced object-median hierarchy, emulated on the host from the device source."""
+    V, F = prim.generate_torus(5, 1, 20, 11)  # 440 triangles: not a power of two
+    em = emul_mod.EmulEngine(V, F, hierarchy="kd")
+    assert em.error == 0
+    topo = em.topology()
+    assert topo.shape == (len(F) - 1, 2)
+    # every triangle exactly once, every internal node exactly once, depth = ceil(log2 n)
+    seen_tri, seen_node = np.zeros(len(F), dtype=int), np.zeros(len(topo), dtype=int)
+    depth = {0: 0}
+    stack = [0]
+    seen_node[0] = 1
+    while stack:
+        u = stack.pop()
+        sizes = []
+        for c in topo[u]:
+            if c >= 0:
+                seen_node[c] += 1
+                depth[c] = depth[u] + 1
+                stack.append(c)
+            elif c <= -2:
+                seen_tri[-(c + 2)] += 1
+                depth[("t", -(c + 2))] = depth[u] + 1
+    assert np.all(seen_tri == 1) and np.all(seen_node == 1)
+    assert max(depth.values()) == int(np.ceil(np.log2(len(F))))
+    check_packed_structure(em, len(F))
+    # same engine semantics on this hierarchy: the error against the exact winding number is the restatement's error class
+    q = prim.uniform_points_in_bbox(*prim.mesh_bbox(V), 4000, seed=2)
+    w = em.solid_angle(q) / (4 * np.pi)
+    w_exact = oracle_mod.exact64(V, F, q) / (4 * np.pi)
+    w_ref = oracle_mod.RefEngine(V, F).solid_angle(q) / (4 * np.pi)
+    assert np.abs(w - w_exact).max() < 2.0 * max(np.abs(w_ref - w_exact).max(), 2e-3)
+    assert np.abs(w - w_exact).mean() < 2.0 * np.abs(w_ref - w_exact).mean()

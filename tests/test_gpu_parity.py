@@ -425,3 +425,58 @@ def test_cfg2_full_size_sphere_properties(lb, prim):
     assert torch.equal(ins.bool()[clear], (rad < 1.0)[clear])
     # symmetry of the lattice and of the icosphere under the central inversion z -> -z of this slab
     assert (ins != ins.flip(0)).float().mean() < 1e-4
+
+
+# ---- K3': balanced k-d hierarchy (wn_options.hierarchy = WN_HIERARCHY_KD) ----------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", [1, 3])
+def test_kd_hierarchy_equals_host_emulation(prim, emul_mod, cfg):
+    import lagrange_b200 as lb
+
+    V, F, q, _ = small_config(prim, cfg)
+    eng = lb.FastWindingNumber(V, F, hierarchy="kd", keep_build_data=True)
+    em = emul_mod.EmulEngine(V, F, hierarchy="kd")
+    assert np.array_equal(eng.debug_topology(), em.topology())
+    # same topology, same moments (unfused build arithmetic), same folded records: the traversal differs only by the device's
+    # rsqrt / FMA contraction in the exact-triangle term
+    got = eng.solid_angle(q[:20000], tiling=False)
+    want = em.solid_angle(q[:20000])
+    assert np.abs(got - want).max() < 2e-5 * FOUR_PI
+
+
+@pytest.mark.gpu
+def test_kd_hierarchy_error_class_and_tiled_path(prim, oracle_mod):
+    import lagrange_b200 as lb
+
+    V, F, q, lattice = small_config(prim, 1)
+    kd = lb.FastWindingNumber(V, F, hierarchy="kd")
+    lbvh = lb.FastWindingNumber(V, F)
+    w_exact = oracle_mod.exact64(V, F, q) / FOUR_PI
+    e_kd = np.abs(kd.solid_angle(q) / FOUR_PI - w_exact)
+    e_lb = np.abs(lbvh.solid_angle(q) / FOUR_PI - w_exact)
+    assert e_kd.max() < 1.5 * e_lb.max() and e_kd.mean() < 1.5 * e_lb.mean()
+    clear = band_mask(w_exact, 2.0 * e_kd.max())
+    assert np.array_equal(kd.is_inside(q)[clear].astype(bool), (w_exact > 0.5)[clear])
+    # tiled vs generic on the k-d tree: same accepted records, far set interpolated
+    o, s, d = lattice
+    om_t = kd.solid_angle_grid(o, s, d, tiling=True)
+    om_g = kd.solid_angle_grid(o, s, d, tiling=False)
+    assert np.abs(om_t - om_g).max() < 3e-5 * FOUR_PI
+    # leaf_size > 1 collapses subtrees of the balanced tree like it does for the LBVH
+    kd8 = lb.FastWindingNumber(V, F, hierarchy="kd", leaf_size=8)
+    e8 = np.abs(kd8.solid_angle(q) / FOUR_PI - w_exact)
+    assert e8.max() < 1.5 * e_lb.max()
+
+
+@pytest.mark.gpu
+def test_kd_hierarchy_degenerate_inputs(prim):
+    import lagrange_b200 as lb
+
+    # all centroids identical (stacked copies of one triangle), two triangles, three triangles
+    V = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], dtype=np.float32)
+    for copies in (2, 3, 37):
+        F = np.tile(np.array([[0, 1, 2]], dtype=np.int32), (copies, 1))
+        eng = lb.FastWindingNumber(V, F, hierarchy="kd")
+        ref = lb.FastWindingNumber(V, F)
+        q = np.array([[0.2, 0.2, 0.5], [0.2, 0.2, -0.5], [3, 3, 3]], dtype=np.float32)
+        assert np.allclose(eng.solid_angle(q), ref.solid_angle(q), atol=1e-5 * copies)
