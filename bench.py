@@ -44,7 +44,9 @@ def parse_args():
     ap.add_argument("--config", type=int, default=2, help="BASELINE config (2 = headline)")
     ap.add_argument("--grid", type=int, default=0, help="override lattice resolution (debug)")
     ap.add_argument("--subdiv", type=int, default=-1, help="override sphere subdivision level (debug)")
-    ap.add_argument("--leaf-size", type=int, default=int(os.environ.get("WN_BENCH_LEAF", "1")))
+    ap.add_argument("--leaf-size", type=int, default=int(os.environ.get("WN_BENCH_LEAF", "4")), help="max triangles per leaf")
+    ap.add_argument("--hierarchy", default=os.environ.get("WN_BENCH_HIERARCHY", "kd"), choices=["lbvh", "kd"],
+                    help="kd: balanced object-median hierarchy (faster queries, 7 ms build); lbvh: Morton/Karras (1.9 ms build)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the CPU baseline sample")
     return ap.parse_args()
@@ -242,10 +244,10 @@ def main():
     if rank == 0:
         V, F, (origin, spacing, dims), name = workload(args)
         # warm-up build on a small mesh: loads the build kernels (CUDA lazy module loading) so that build_ms is kernel time
-        lb.FastWindingNumber(*lb.primitive.generate_subdivided_sphere("icosahedron", 4), leaf_size=args.leaf_size).close()
+        lb.FastWindingNumber(*lb.primitive.generate_subdivided_sphere("icosahedron", 4), leaf_size=args.leaf_size, hierarchy=args.hierarchy).close()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        eng = lb.FastWindingNumber(V, F, leaf_size=args.leaf_size)
+        eng = lb.FastWindingNumber(V, F, leaf_size=args.leaf_size, hierarchy=args.hierarchy)
         torch.cuda.synchronize()
         build_wall_ms = 1e3 * (time.perf_counter() - t0)
         build_info = eng.info
@@ -391,7 +393,7 @@ def main():
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": name, "queries_per_step": n_total, "sharding": f"tile layers (8 z-planes) round-robin over {world} rank(s), tree built on rank 0 and broadcast",
                    "l2": "flushed between timed steps (256 MiB fill); tree %.0f MB" % (build_info.get("tree_bytes", 0) / 1e6),
-                   "leaf_size": args.leaf_size, "tiled": tiled},
+                   "leaf_size": args.leaf_size, "hierarchy": args.hierarchy, "tiled": tiled},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 60, "d2h_bytes_per_step": n_total, "ms_per_step": e2e_ms,
                 "api": "FastWindingNumber.query_grid -> wn_query_grid with a pinned HOST output buffer (lattice is implicit: 60-byte descriptor in)"},
         # per step and rank: tiled = (k_tile_plan + k_tile_query) per batch of <= 131072 tiles (the probe that picks the path runs

@@ -79,6 +79,15 @@ WN_HD int wn_kd_node_id(int N, int lo, int n)
 }
 
 
+// Number of levels whose order has to be computed: ranges of at most leaf_size triangles are collapsed into one leaf later,
+// and the order inside a leaf does not matter.
+WN_HD int wn_kd_levels(int N, int leaf_size)
+{
+    int levels = 0;
+    while ((((long long)N + (1ll << levels) - 1) >> levels) > (leaf_size > 1 ? leaf_size : 1)) ++levels;
+    return levels;
+}
+
 WN_HD int wn_kd_axis(const float ext[3])
 {
     return (ext[0] >= ext[1] && ext[0] >= ext[2]) ? 0 : (ext[1] >= ext[2] ? 1 : 2);

@@ -551,8 +551,7 @@ wn_status create_impl(const float* v_xyz, int64_t nV, const int32_t* tri, int64_
             tm.mark(); // 2: sort
         } else {
             // K3': balanced k-d order (wn_kd.cuh): per level, node centroid bounds -> keys -> one stable sort
-            int levels = 0;
-            while (((int64_t)1 << levels) < nT) ++levels;
+            const int levels = wn_kd_levels((int)nT, opt.leaf_size);
             int* d_bounds = nullptr;
             WN_CUDA_C(dalloc((void**)&d_bounds, (size_t)nT * 6 * sizeof(int)));
             wn::k_iota<<<wn::grid_for(nT), wn::kBuildThreads, 0, st>>>(v0, (int)nT);

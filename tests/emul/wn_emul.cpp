@@ -75,8 +75,7 @@ void* emul_build(const float* v, int64_t nV, const int32_t* tri, int64_t nT, con
             // K3' (wn_kd.cuh): per level, node centroid bounds -> (path, 16-bit coordinate) keys -> stable sort
             std::vector<unsigned> perm(nT);
             std::iota(perm.begin(), perm.end(), 0u);
-            int levels = 0;
-            while (((int64_t)1 << levels) < nT) ++levels;
+            const int levels = wn_kd_levels((int)nT, leaf_size);
             for (int l = 0; l < levels; ++l) {
                 const int nodes = 1 << l;
                 std::vector<float> nlo((size_t)nodes * 3, 3.4e38f), nhi((size_t)nodes * 3, -3.4e38f);

@@ -429,13 +429,13 @@ def test_cfg2_full_size_sphere_properties(lb, prim):
 
 # ---- K3': balanced k-d hierarchy (wn_options.hierarchy = WN_HIERARCHY_KD) ----------------------------------------------
 @pytest.mark.gpu
-@pytest.mark.parametrize("cfg", [1, 3])
-def test_kd_hierarchy_equals_host_emulation(prim, emul_mod, cfg):
+@pytest.mark.parametrize("cfg,leaf", [(1, 1), (3, 1), (1, 4)])
+def test_kd_hierarchy_equals_host_emulation(prim, emul_mod, cfg, leaf):
     import lagrange_b200 as lb
 
     V, F, q, _ = small_config(prim, cfg)
-    eng = lb.FastWindingNumber(V, F, hierarchy="kd", keep_build_data=True)
-    em = emul_mod.EmulEngine(V, F, hierarchy="kd")
+    eng = lb.FastWindingNumber(V, F, hierarchy="kd", keep_build_data=True, leaf_size=leaf)
+    em = emul_mod.EmulEngine(V, F, hierarchy="kd", leaf_size=leaf)
     assert np.array_equal(eng.debug_topology(), em.topology())
     # same topology, same moments (unfused build arithmetic), same folded records: the traversal differs only by the device's
     # rsqrt / FMA contraction in the exact-triangle term

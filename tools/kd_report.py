@@ -27,6 +27,9 @@ def timed(fn, reps=3):
     return best
 
 
+LEAVES = tuple(int(x) for x in os.environ.get("KD_LEAVES", "1,4").split(","))
+
+
 def main():
     cfgs = [int(c) for c in (sys.argv[1] if len(sys.argv) > 1 else "1,2,3,4,5").split(",")]
     rep = {}
@@ -37,7 +40,7 @@ def main():
         dV, dF = torch.from_numpy(V).cuda(), torch.from_numpy(F).cuda()
         row = {"triangles": int(len(F))}
         for h in ("lbvh", "kd"):
-            for leaf in (1, 4):
+            for leaf in LEAVES:
                 lb.FastWindingNumber(dV, dF, hierarchy=h, leaf_size=leaf).close()  # warm
                 eng = lb.FastWindingNumber(dV, dF, hierarchy=h, leaf_size=leaf)
                 info = eng.info
