@@ -103,9 +103,9 @@ WN_HD unsigned wn_kd_quant(float c, float blo, float ext)
 
 // Internal node that splits gap g: find its range by descending from the root, emit children / parents / slots in the
 // layout of wn_lbvh_node (internal nodes 0..N-2, leaf of sorted position p = node N-1 + p). parent[] was preset to -1.
-WN_HD void wn_kd_emit_node(int N, int g, int* child, int* parent, unsigned char* slot)
+WN_HD void wn_kd_emit_node(int N, int g, int* child, int* parent, unsigned char* slot, unsigned char* skip, int leaf_size)
 {
-    int lo = 0, n = N;
+    int lo = 0, n = N, depth = 0;
     while (true) {
         const int nl = n / 2;
         const int gap = lo + nl - 1;
@@ -116,8 +116,11 @@ WN_HD void wn_kd_emit_node(int N, int g, int* child, int* parent, unsigned char*
             lo += nl;
             n -= nl;
         }
+        ++depth;
     }
     const int id = wn_kd_node_id(N, lo, n);
+    // 4-ary tree: internal nodes at odd depth get no record (unless they end up as a collapsed leaf, n <= leaf_size)
+    if (skip) skip[id] = ((depth & 1) && n > (leaf_size > 1 ? leaf_size : 1)) ? 1 : 0;
     const int nI = N - 1;
     const int nl = n / 2, nr = n - nl;
     const int cl = nl >= 2 ? wn_kd_node_id(N, lo, nl) : nI + lo;
@@ -148,6 +151,7 @@ struct WnBuild
     int* ntri;           // [nI+nL]
     int* size;           // [nI+nL] entries in the packed subtree (1 for leaves / collapsed nodes)
     unsigned char* collapsed; // [nI]
+    const unsigned char* skip; // [nI] or null: internal nodes that get no record: their children hang off their parent (4-ary tree)
     unsigned* r2v;       // [nI+nL] vertex-radius^2 as ordered uint (float bits), zero-initialised (WN_RADIUS_VERTEX)
     int* err;            // [1] error flag
     int* max_depth;      // [1]
@@ -246,7 +250,7 @@ WN_HD void wn_climb_leaf(const WnBuild& b, int l)
         // last arriver merges (children in slot order => deterministic)
         WN_THREADFENCE();
         WnLocal ch[WN_MAX_WIDTH];
-        int n = 0, nt = 0, sz = 1;
+        int n = 0, nt = 0, sz = (b.skip && b.skip[p]) ? 0 : 1;
         for (int s = 0; s < b.W; ++s) {
             const int c = b.child[(int64_t)p * b.W + s];
             if (c < 0) continue;
@@ -314,7 +318,7 @@ WN_HD void wn_pack_node(const WnBuild& b, int node)
         const int p = b.parent[cur];
         if (p < 0) break;
         if (b.collapsed[p]) hidden = true;
-        idx += 1;
+        idx += (b.skip && b.skip[p]) ? 0 : 1;
         const int sl = b.slot[cur];
         for (int s = 0; s < sl; ++s) {
             const int c = b.child[(int64_t)p * b.W + s];
@@ -346,6 +350,7 @@ WN_HD void wn_pack_node(const WnBuild& b, int node)
         b.tri_order[tf] = (unsigned)t;
     }
     if (hidden) return;
+    if (!is_tri_leaf && b.skip && b.skip[node]) return; // no record: its children are its parent's children
     const bool leaf_entry = is_tri_leaf || b.collapsed[node];
     WnLocal d;
     wn_load_local(b.local + (int64_t)node * 9, d, false);
@@ -374,9 +379,22 @@ WN_HD void wn_pack_node(const WnBuild& b, int node)
         for (int s = 0; s < b.W; ++s) {
             const int c = b.child[(int64_t)node * b.W + s];
             if (c < 0) continue;
-            kid[n++] = cidx;
-            cidx += b.size[c];
+            if (c < b.nI && b.skip && b.skip[c] && !b.collapsed[c]) {
+                // skipped child: its children (never skipped themselves) take its place
+                for (int s2 = 0; s2 < b.W; ++s2) {
+                    const int g = b.child[(int64_t)c * b.W + s2];
+                    if (g < 0) continue;
+                    if (n < WN_MAX_WIDTH) kid[n] = cidx;
+                    ++n;
+                    cidx += b.size[g];
+                }
+            } else {
+                if (n < WN_MAX_WIDTH) kid[n] = cidx;
+                ++n;
+                cidx += b.size[c];
+            }
         }
+        if (n > WN_MAX_WIDTH) *b.err = WN_ERR_TOPOLOGY_BAD_CHILD;
     }
     b.kids[idx] = make_int4(kid[0], kid[1], kid[2], kid[3]);
 }

@@ -368,6 +368,8 @@ wn_status validate_options(const wn_options* in, wn_options* out, bool imported)
     return WN_OK;
 }
 
+int env_int(const char* name, int dflt); // defined with the query dispatch below
+
 wn_status create_impl(const float* v_xyz, int64_t nV, const int32_t* tri, int64_t nT, const int32_t* child_in, int64_t num_nodes,
                       int32_t width, const wn_options* opt_in, wn_engine** out)
 {
@@ -469,7 +471,7 @@ wn_status create_impl(const float* v_xyz, int64_t nV, const int32_t* tri, int64_
             add((size_t)nT * 4);
             add((size_t)nT * 4);
             add((size_t)wn::sort_scratch_bytes(nT));
-            if (opt.hierarchy == WN_HIERARCHY_KD) add((size_t)nT * 6 * sizeof(int));
+            if (opt.hierarchy == WN_HIERARCHY_KD) add((size_t)nT * 6 * sizeof(int)), add((size_t)nT);
         } else {
             add((size_t)nI_max * W * 4);
             add((size_t)nN_max * 4);
@@ -575,7 +577,12 @@ wn_status create_impl(const float* v_xyz, int64_t nV, const int32_t* tri, int64_
         WN_CUDA_C(cudaMemsetAsync(b.parent, 0xff, (size_t)nN * sizeof(int), st));
         WN_CUDA_C(cudaMemsetAsync(b.slot, 0, (size_t)nN, st));
         if (kd) {
-            wn::k_kd_tree<<<wn::grid_for(nT - 1), wn::kBuildThreads, 0, st>>>((int)nT, b.child, b.parent, b.slot);
+            unsigned char* d_skip = nullptr;
+            if (env_int("WN_KD_WIDE", 1)) {
+                WN_CUDA_C(dalloc((void**)&d_skip, (size_t)b.nI));
+            }
+            wn::k_kd_tree<<<wn::grid_for(nT - 1), wn::kBuildThreads, 0, st>>>((int)nT, b.child, b.parent, b.slot, d_skip, opt.leaf_size);
+            b.skip = d_skip;
             WN_CUDA_C(cudaGetLastError());
         } else if (nT >= 2) {
             wn::k_lbvh<<<wn::grid_for(nT - 1), wn::kBuildThreads, 0, st>>>(keys, (int)nT, b.child, b.parent, b.slot);

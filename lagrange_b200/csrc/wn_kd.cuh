@@ -112,11 +112,11 @@ __global__ void __launch_bounds__(kBuildThreads) k_kd_keys(const float* __restri
 // One thread per internal node (gap): find its range by descending from the root, emit children / parents / slots in the
 // layout of k_lbvh (internal nodes 0..N-2, leaf of sorted position p = node N-1 + p).
 __global__ void __launch_bounds__(kBuildThreads) k_kd_tree(int N, int* __restrict__ child, int* __restrict__ parent,
-                                                           unsigned char* __restrict__ slot)
+                                                           unsigned char* __restrict__ slot, unsigned char* __restrict__ skip, int leaf_size)
 {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= N - 1) return;
-    wn_kd_emit_node(N, g, child, parent, slot);
+    wn_kd_emit_node(N, g, child, parent, slot, skip, leaf_size);
 }
 
 } // namespace wn

@@ -18,7 +18,7 @@ struct Emul
     std::vector<float> v;
     std::vector<int> tri;
     std::vector<int> child, parent, arrive, ntri, size;
-    std::vector<unsigned char> slot, collapsed;
+    std::vector<unsigned char> slot, collapsed, skip;
     std::vector<unsigned> prim, r2v, tri_order;
     std::vector<float4> local, hot, cold, tris;
     std::vector<int4> kids;
@@ -35,6 +35,7 @@ extern "C" {
 void* emul_build(const float* v, int64_t nV, const int32_t* tri, int64_t nT, const int32_t* child_in, int64_t num_nodes, int width,
                  int leaf_size, int order, int radius_mode, int approx_single, int morton_bits, int hierarchy)
 {
+    const bool wide = hierarchy == 1; // the k-d hierarchy is packed 4-ary (odd-depth internal nodes get no record)
     Emul* e = new Emul;
     e->v.assign(v, v + nV * 3);
     e->tri.assign(tri, tri + nT * 3);
@@ -113,7 +114,10 @@ void* emul_build(const float* v, int64_t nV, const int32_t* tri, int64_t nT, con
                 perm.swap(np);
             }
             e->prim = perm;
-            for (int g = 0; g < (int)nT - 1; ++g) wn_kd_emit_node((int)nT, g, e->child.data(), e->parent.data(), e->slot.data());
+            e->skip.assign(b.nI, 0);
+            for (int g = 0; g < (int)nT - 1; ++g)
+                wn_kd_emit_node((int)nT, g, e->child.data(), e->parent.data(), e->slot.data(), wide ? e->skip.data() : nullptr, leaf_size);
+            if (wide) b.skip = e->skip.data();
         } else {
         const float ext = std::max(hi[0] - lo[0], std::max(hi[1] - lo[1], hi[2] - lo[2]));
         const float inv = ext > 0.0f ? 1.0f / ext : 0.0f;
