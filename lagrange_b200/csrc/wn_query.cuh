@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(kQueryThreads, WN_Q_MIN_CTAS) k_query(const Qu
 
 // ---- tiled path: plan ------------------------------------------------------------------------------------------
 // frontier words: entry | (has_mixed_ancestor << 30)
-__device__ __forceinline__ void plan_push_kids(const int4 k4, int flag, int* front, int* count, int* overflow)
+__device__ __forceinline__ void plan_push_kids(const int4 k4, int flag, int* front, int* count, int* overflow, bool& ovf)
 {
     const int kid[4] = {k4.x, k4.y, k4.z, k4.w};
 #pragma unroll
@@ -406,18 +406,18 @@ __device__ __forceinline__ void plan_push_kids(const int4 k4, int flag, int* fro
             if (pos < kTileFrontCap)
                 front[pos] = kid[s] | (flag << 30);
             else
-                *overflow = 1;
+                *overflow = 1, ovf = true;
         }
     }
 }
 
-__device__ __forceinline__ void plan_append(int* list, int* count, int cap, int value, int* overflow)
+__device__ __forceinline__ void plan_append(int* list, int* count, int cap, int value, int* overflow, bool& ovf)
 {
     const int pos = atomicAdd(count, 1);
     if (pos < cap)
         list[pos] = value;
     else
-        *overflow = 1;
+        *overflow = 1, ovf = true;
 }
 
 // ascending sort of s[0..n), n <= 64, by ONE warp: two keys per lane (elements lane and lane + 32), bitonic network with
@@ -553,6 +553,7 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
             }
         }
     }
+    bool my_ovf = false; // this thread overflowed a list: decided at the barrier's OR, never by reading the shared flag mid-round
     if (tid < 8) s_cnt[tid] = 0;
     for (int r = tid; r <= kPlanMaxRounds; r += kPlanThreads) s_fcnt[r] = 0;
     if (tid == 0) s_off = 0;
@@ -586,7 +587,7 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
         if (!finite) s_cnt[4] = 1; // non-finite coordinates (or an empty tile): generic path
         const int n_entries = t.n_entries;
         if (n_entries > 1) {
-            plan_push_kids(__ldg(t.kids), 0, s_front[0], &s_fcnt[0], &s_cnt[4]);
+            plan_push_kids(__ldg(t.kids), 0, s_front[0], &s_fcnt[0], &s_cnt[4], my_ovf);
         } else if (n_entries == 1) {
             s_exact[0] = 0; // the root is a leaf: exact for everybody
             s_cnt[6] = 1;
@@ -625,26 +626,29 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
                 // far set: the record's field must be smooth across the tile, i.e. the tile is small against its distance
                 // both to the expansion centre and to the nearest possible source point (bounding sphere of radius R)
                 if (manc)
-                    plan_append(s_cond, &s_cnt[2], kTileAllCap, tile_key(e, leaf, kClsCondFar), &s_cnt[4]);
+                    plan_append(s_cond, &s_cnt[2], kTileAllCap, tile_key(e, leaf, kClsCondFar), &s_cnt[4], my_ovf);
                 else if (D >= a.kappa * ra && D - sqrtf(fabsf(f0.w)) >= 0.5f * a.kappa * ra)
-                    plan_append(s_far, &s_cnt[3], kTileFarCap, e, &s_cnt[4]);
+                    plan_append(s_far, &s_cnt[3], kTileFarCap, e, &s_cnt[4], my_ovf);
                 else
-                    plan_append(s_dir, &s_cnt[5], kTileDirCap, e, &s_cnt[4]);
+                    plan_append(s_dir, &s_cnt[5], kTileDirCap, e, &s_cnt[4], my_ovf);
             } else if (allnear) {
                 if (!leaf)
-                    plan_push_kids(k4, manc, nxt, ncnt, &s_cnt[4]);
+                    plan_push_kids(k4, manc, nxt, ncnt, &s_cnt[4], my_ovf);
                 else if (manc)
-                    plan_append(s_cond, &s_cnt[2], kTileAllCap, tile_key(e, true, kClsCond), &s_cnt[4]);
+                    plan_append(s_cond, &s_cnt[2], kTileAllCap, tile_key(e, true, kClsCond), &s_cnt[4], my_ovf);
                 else
-                    plan_append(s_exact, &s_cnt[6], kTileExactCap, e, &s_cnt[4]);
+                    plan_append(s_exact, &s_cnt[6], kTileExactCap, e, &s_cnt[4], my_ovf);
             } else {
-                plan_append(s_cond, &s_cnt[2], kTileAllCap, tile_key(e, leaf, kClsCond), &s_cnt[4]);
-                if (!leaf) plan_push_kids(k4, 1, nxt, ncnt, &s_cnt[4]);
+                plan_append(s_cond, &s_cnt[2], kTileAllCap, tile_key(e, leaf, kClsCond), &s_cnt[4], my_ovf);
+                if (!leaf) plan_push_kids(k4, 1, nxt, ncnt, &s_cnt[4], my_ovf);
             }
         }
         ++round;
-        if (round >= kPlanMaxRounds) s_cnt[4] = 1; // deeper than any sane hierarchy: generic path
-        stop = __syncthreads_or(s_cnt[4]) != 0;
+        if (round >= kPlanMaxRounds) { // deeper than any sane hierarchy: generic path
+            my_ovf = true;
+            if (tid == 0) s_cnt[4] = 1;
+        }
+        stop = __syncthreads_or((int)my_ovf) != 0;
     }
     __syncthreads();
     bool fallback = s_cnt[4] != 0;
