@@ -122,3 +122,36 @@ def test_cfg5_full_size_exact_vs_tree_sweep(lb, oracle_mod, prim):
     w = exact / FOUR_PI
     m = (w - 0.5).abs() > 1e-3 + errs[2.0]
     assert torch.equal(ins[m], ins_exact[m])
+
+
+def test_cfg2_full_size_bench_configuration(lb, oracle_mod, prim):
+    """What bench.py measures, at full size: balanced k-d hierarchy, 4-triangle leaves, tiled path, 512^3 lattice.
+    Against the restatement on every lattice point (different trees: agreement outside the band widened by both trees'
+    error), against the exact winding number on a sample, and against the analytic volume of the unit sphere."""
+    V, F = prim.config_mesh(2)
+    _, (o, s, d) = prim.config_queries(2, V, F)
+    eng = lb.FastWindingNumber(V, F, hierarchy="kd", leaf_size=4)
+    om, ins = eng.query_grid(o, s, d, want_omega=True, want_inside=True)
+    # same engine, per-point traversal instead of tiles: the far-set interpolation is the only difference
+    om_g = eng.query_grid(o, s, d, want_omega=True, want_inside=False, tiling=False)[0]
+    assert np.abs(om - om_g).max() < 3e-5 * FOUR_PI
+    # strided sharding (what a rank of an 8-GPU run evaluates) returns exactly the corresponding planes
+    planes = eng.strided_layer_planes(int(d[2]), 3, 8)
+    part = eng.query_grid(o, s, d, layers=(3, 8))[1].reshape(len(planes), int(d[1]), int(d[0]))
+    assert np.array_equal(part, ins.reshape(int(d[2]), int(d[1]), int(d[0]))[planes])
+    # exact winding number on a sample of the lattice (brute force on the GPU, itself checked against exact64 elsewhere)
+    sub = slice(None, None, 65537)
+    P = prim.lattice_points(o, s, d)[sub]
+    w_ex = eng.exact_solid_angle(P) / FOUR_PI
+    err = np.abs(om[sub] / FOUR_PI - w_ex)
+    assert err.max() < 6e-3 and err.mean() < 1e-3, (err.max(), err.mean())
+    clear = band_mask(w_ex, band=1e-3 + 2.0 * err.max())
+    assert np.array_equal(ins[sub][clear].astype(bool), (w_ex > 0.5)[clear])
+    # the restatement on every lattice point
+    ref = oracle_mod.RefEngine(V, F)
+    ins_ref, om_ref = ref.grid(o, s, d, want_omega=True)
+    err_ref = np.abs(om_ref[sub] / FOUR_PI - w_ex).max()
+    wide = band_mask(om_ref / FOUR_PI, band=1e-3 + 2.0 * (err.max() + err_ref))
+    assert np.array_equal(ins[wide], ins_ref[wide])
+    assert np.mean(ins != ins_ref) < 1e-4
+    assert abs(float(ins.sum()) * float(np.prod(s)) - 4.0 / 3.0 * np.pi) < 2e-3
