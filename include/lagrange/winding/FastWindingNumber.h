@@ -35,6 +35,7 @@ struct FastWindingNumberOptions
     int leaf_size = 1; ///< max triangles per LBVH leaf (1..16)
     int morton_bits = 63; ///< 30 or 63
     bool vertex_radius = false; ///< exact cluster radius instead of the reference's box-corner bound
+    bool balanced_hierarchy = false; ///< balanced k-d tree (faster queries, slower build) instead of the Morton LBVH
     int device = -1; ///< CUDA device, -1 = current
 };
 
@@ -74,6 +75,10 @@ public:
     /// Whole lattice or the z-slab [z_begin, z_end); outputs hold dims[0]*dims[1]*(z_end - z_begin) values.
     void is_inside(const Lattice& lattice, uint8_t* out, int64_t z_begin = 0, int64_t z_end = -1) const;
     void solid_angle(const Lattice& lattice, float* out, int64_t z_begin = 0, int64_t z_end = -1) const;
+    /// Narrow-band signed distance at the lattice's cell centres: min(distance to the mesh, band), negative where is_inside
+    /// holds; what volume::mesh_to_volume asks of OpenVDB with Sign::WindingNumber (mesh_to_volume.cpp:160-183, band = 3 voxels).
+    /// Returns the number of cells with distance < band. signed_distance = false skips the predicate.
+    int64_t signed_distance(const Lattice& lattice, float band, float* out, bool signed_distance = true) const;
     /// Exact mode: brute-force sum over all triangles (no hierarchy, no approximation).
     void exact_solid_angle(const float* xyz, size_t n, float* out) const;
 

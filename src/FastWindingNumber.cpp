@@ -37,6 +37,7 @@ void FastWindingNumber::initialize(const float* vertices, int64_t num_vertices, 
     opt.order = options.order;
     opt.leaf_size = options.leaf_size;
     opt.morton_bits = options.morton_bits;
+    opt.hierarchy = options.balanced_hierarchy ? WN_HIERARCHY_KD : WN_HIERARCHY_LBVH;
     opt.radius_mode = options.vertex_radius ? WN_RADIUS_VERTEX : WN_RADIUS_BOX_CORNER;
     opt.device = options.device;
     m_impl = std::make_unique<Impl>();
@@ -119,6 +120,15 @@ void FastWindingNumber::solid_angle(const Lattice& l, float* out, int64_t z_begi
     const wn_engine* e = engine();
     check(wn_query_grid(e, l.origin.data(), l.spacing.data(), l.dims.data(), z_begin, z_end < 0 ? l.dims[2] : z_end, m_impl->beta, WN_QUERY_DEFAULT, out,
                         nullptr, nullptr));
+}
+
+int64_t FastWindingNumber::signed_distance(const Lattice& l, float band, float* out, bool signed_distance) const
+{
+    const wn_engine* e = engine();
+    int64_t active = 0;
+    check(wn_sdf_grid(e, l.origin.data(), l.spacing.data(), l.dims.data(), band, m_impl->beta, signed_distance ? 0u : WN_SDF_UNSIGNED, out, &active,
+                      nullptr));
+    return active;
 }
 
 void FastWindingNumber::exact_solid_angle(const float* xyz, size_t n, float* out) const

@@ -174,6 +174,42 @@ int main()
                     mismatch += engine.is_inside(p) != (g[(size_t(k) * 16 + j) * 40 + i] != 0);
                 }
         CHECK(mismatch == 0);
+
+        // narrow-band signed distance on the same lattice: sign = is_inside, |d| <= band, torus of tube radius 1 around the
+        // circle of radius 5 in the XZ plane => d ~ hypot(hypot(x, z) - 5, y) - 1 (the mesh is an inscribed polyhedron)
+        const float band = 3.f * lat.spacing[0];
+        std::vector<float> sdf(g.size());
+        const int64_t active = engine.signed_distance(lat, band, sdf.data());
+        size_t sign_mismatch = 0, in_band = 0;
+        double worst = 0;
+        for (int k = 0; k < 40; ++k)
+            for (int j = 0; j < 16; ++j)
+                for (int i = 0; i < 40; ++i) {
+                    const size_t idx = (size_t(k) * 16 + j) * 40 + i;
+                    sign_mismatch += (sdf[idx] < 0.f) != (g[idx] != 0);
+                    CHECK(std::fabs(sdf[idx]) <= band);
+                    if (std::fabs(sdf[idx]) < band) {
+                        ++in_band;
+                        const double x = lat.origin[0] + lat.spacing[0] * (i + 0.5), y = lat.origin[1] + lat.spacing[1] * (j + 0.5),
+                                     z = lat.origin[2] + lat.spacing[2] * (k + 0.5);
+                        worst = std::max(worst, std::fabs(double(sdf[idx]) - (std::hypot(std::hypot(x, z) - 5.0, y) - 1.0)));
+                    }
+                }
+        std::printf("signed distance: %lld cells in the band, max deviation from the analytic torus %.3e\n", (long long)active, worst);
+        CHECK(sign_mismatch == 0);
+        CHECK(size_t(active) == in_band);
+        CHECK(worst < 3e-2);
+
+        // the balanced k-d hierarchy classifies the lattice like the LBVH does (different trees: allow the surface shell)
+        lagrange::winding::FastWindingNumberOptions kd_opt;
+        kd_opt.balanced_hierarchy = true;
+        kd_opt.leaf_size = 4;
+        lagrange::winding::FastWindingNumber kd(mesh, kd_opt);
+        std::vector<uint8_t> g2(g.size());
+        kd.is_inside(lat, g2.data());
+        size_t differ = 0;
+        for (size_t i = 0; i < g.size(); ++i) differ += g[i] != g2[i];
+        CHECK(differ <= g.size() / 500);
     }
 
     // --- concurrent const queries from several host threads ---------------------------------------------------------
