@@ -947,6 +947,33 @@ wn_status points_impl(const wn_engine* e, const float* q_xyz, int64_t n, float b
     std::lock_guard<std::mutex> lock(e->mu);
     cudaStream_t st = (cudaStream_t)stream;
     const float b = beta > 0.0f ? beta : e->opt.accuracy_scale;
+    // Small host batches (the reference's own calling pattern is one point per call, FastWindingNumber.cpp:60-76): the kernel
+    // reads the queries from, and writes the results to, pinned host memory directly (unified addressing), so a call is one
+    // launch and one synchronisation instead of two staged copies around it. Same kernel, same arithmetic.
+    if (n <= 256 && !stats && e->view.n_entries > 0 && !is_device_pointer(q_xyz) && (!out_omega || !is_device_pointer(out_omega)) &&
+        (!out_inside || !is_device_pointer(out_inside))) {
+        const size_t nq = (size_t)n;
+        WN_CUDA(e->p_small.reserve(256 * (3 * sizeof(float) + sizeof(float) + 1)));
+        float* pin_q = (float*)e->p_small.p;
+        float* pin_om = pin_q + 3 * 256;
+        uint8_t* pin_in = (uint8_t*)(pin_om + 256);
+        memcpy(pin_q, q_xyz, nq * 3 * sizeof(float));
+        wn::QueryArgs a;
+        memset(&a, 0, sizeof(a));
+        a.tree = e->view;
+        a.beta2 = b * b;
+        a.q = pin_q;
+        a.n = n;
+        a.q_aligned16 = 1;
+        a.out_omega = out_omega ? pin_om : nullptr;
+        a.out_inside = out_inside ? pin_in : nullptr;
+        launch_query<false, false>(1, (int)((n + wn::kQueryWarps * 32 - 1) / (wn::kQueryWarps * 32)), a, st);
+        WN_CUDA(cudaGetLastError());
+        WN_CUDA(cudaStreamSynchronize(st));
+        if (out_omega) memcpy(out_omega, pin_om, nq * sizeof(float));
+        if (out_inside) memcpy(out_inside, pin_in, nq);
+        return WN_OK;
+    }
     const float* d_q = nullptr;
     wn_status s = stage_points(e, q_xyz, n, &d_q, st);
     if (s != WN_OK) return s;
