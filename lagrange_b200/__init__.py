@@ -5,9 +5,9 @@
 The compute path is libwn_b200.so (hand-written CUDA, C-ABI in include/wn_b200.h). Importing this package does not
 need a GPU; constructing an engine does, and fails loudly without one (no CPU fallback).
 """
-from . import callers, primitive, volume
+from . import callers, io, primitive, volume
 from .mesh import SurfaceMesh
 from .winding import Error, FastWindingNumber
 
-__all__ = ["FastWindingNumber", "SurfaceMesh", "Error", "primitive", "callers", "volume"]
+__all__ = ["FastWindingNumber", "SurfaceMesh", "Error", "primitive", "callers", "volume", "io"]
 __version__ = "0.1.0"
