@@ -48,6 +48,83 @@ static inline unsigned wn_host_atomic_max_u(unsigned* p, unsigned v)
 #define WN_ERR_TOPOLOGY_BAD_CHILD 1
 #define WN_ERR_TOPOLOGY_DEPTH 2
 
+// ---- k-d hierarchy with SAH-guided split positions (K3'', wn_kd.cuh): explicit node ranges, level by level ---------------
+// A node is a range [start, start + n) of the current triangle order. Internal nodes are numbered by the gap they split
+// (start + nl - 1), with the root's gap and gap 0 swapped so that the root is node 0.
+#define WN_KDX_MIN_SAH 16 /* ranges shorter than this are split at the median */
+
+WN_HD int wn_kdx_gap_id(int gap, int root_gap)
+{
+    return gap == root_gap ? 0 : (gap == 0 ? root_gap : gap);
+}
+
+WN_HD float wn_kdx_half_area(const float* lo, const float* hi)
+{
+    if (!(hi[0] >= lo[0]) || !(hi[1] >= lo[1]) || !(hi[2] >= lo[2])) return 0.0f; // empty (or NaN) box
+    const float dx = WN_SUB(hi[0], lo[0]), dy = WN_SUB(hi[1], lo[1]), dz = WN_SUB(hi[2], lo[2]);
+    return WN_ADD(WN_ADD(WN_MUL(dx, dy), WN_MUL(dy, dz)), WN_MUL(dz, dx));
+}
+
+// Left count of a range of n >= WN_KDX_MIN_SAH triangles sorted along its axis, from the boxes of its 8 equal segments
+// (seg[k*6 + 0..2] = min, + 3..5 = max; element i of the range belongs to segment (8 i) / n): the candidate "first k
+// segments | rest" with the least  area(left) * n_left + area(right) * n_right;  ties keep the candidate nearest the median.
+WN_HD int wn_kdx_choose(int n, const float* seg)
+{
+    float plo[8][3], phi[8][3], slo[8][3], shi[8][3]; // prefix boxes of segments 0..k, suffix boxes of segments k..7
+    for (int k = 0; k < 8; ++k)
+        for (int a = 0; a < 3; ++a) {
+            const float l = seg[k * 6 + a], h = seg[k * 6 + 3 + a];
+            plo[k][a] = k == 0 ? l : wn_min(plo[k - 1][a], l);
+            phi[k][a] = k == 0 ? h : wn_max(phi[k - 1][a], h);
+        }
+    for (int k = 7; k >= 0; --k)
+        for (int a = 0; a < 3; ++a) {
+            const float l = seg[k * 6 + a], h = seg[k * 6 + 3 + a];
+            slo[k][a] = k == 7 ? l : wn_min(slo[k + 1][a], l);
+            shi[k][a] = k == 7 ? h : wn_max(shi[k + 1][a], h);
+        }
+    const int order[7] = {4, 3, 5, 2, 6, 1, 7};
+    int best_nl = n / 2;
+    float best = 3.4e38f;
+    for (int c = 0; c < 7; ++c) {
+        const int k = order[c];
+        const int nl = (int)(((long long)k * n + 7) / 8); // elements of segments 0..k-1
+        if (nl < 1 || nl > n - 1) continue;
+        const float cost = WN_ADD(WN_MUL(wn_kdx_half_area(plo[k - 1], phi[k - 1]), (float)nl), WN_MUL(wn_kdx_half_area(slo[k], shi[k]), (float)(n - nl)));
+        if (cost < best) {
+            best = cost;
+            best_nl = nl;
+        }
+    }
+    return best_nl;
+}
+
+// A finished range (n <= leaf_size, or a single triangle) hangs off (pid, side): its inner structure is the implicit halving
+// tree (it is collapsed into one leaf record later; only the arrays have to be complete).
+WN_HD void wn_kdx_emit_halving(int N, int s, int m, int pid, int side, int root_gap, int* child, int* parent, unsigned char* slot,
+                               unsigned char* skip)
+{
+    const int nI = N - 1;
+    int st_s[40], st_m[40], st_p[40], st_side[40], top = 0;
+    st_s[0] = s, st_m[0] = m, st_p[0] = pid, st_side[0] = side, top = 1;
+    while (top > 0) {
+        --top;
+        const int cs = st_s[top], cm = st_m[top], cp = st_p[top], cside = st_side[top];
+        const int id = cm == 1 ? nI + cs : wn_kdx_gap_id(cs + cm / 2 - 1, root_gap);
+        if (cp >= 0) {
+            child[2 * (size_t)cp + cside] = id;
+            parent[id] = cp;
+            slot[id] = (unsigned char)cside;
+        }
+        if (cm >= 2) {
+            if (skip) skip[id] = 0;
+            if (top + 2 > 40) return; // cannot happen for m <= 2^19
+            st_s[top] = cs, st_m[top] = cm / 2, st_p[top] = id, st_side[top] = 0, ++top;
+            st_s[top] = cs + cm / 2, st_m[top] = cm - cm / 2, st_p[top] = id, st_side[top] = 1, ++top;
+        }
+    }
+}
+
 // ---- balanced k-d hierarchy (K3', wn_kd.cuh): the implicit tree over the final triangle order ------------------------
 // Range [lo, lo + n) and path bits of the level-`level` node that contains position p in the implicit balanced tree over N.
 WN_HD void wn_kd_locate(int N, int p, int level, int& lo, int& n, unsigned& path)

@@ -364,7 +364,7 @@ wn_status validate_options(const wn_options* in, wn_options* out, bool imported)
     if (out->leaf_size < 1 || out->leaf_size > WN_MAX_LEAF_SIZE) return fail(WN_ERR_INVALID_ARGUMENT, "leaf_size must be in [1, %d]", WN_MAX_LEAF_SIZE);
     if (out->morton_bits != 30 && out->morton_bits != 63) return fail(WN_ERR_INVALID_ARGUMENT, "morton_bits must be 30 or 63");
     if (out->radius_mode != WN_RADIUS_BOX_CORNER && out->radius_mode != WN_RADIUS_VERTEX) return fail(WN_ERR_INVALID_ARGUMENT, "bad radius_mode");
-    if (out->hierarchy != WN_HIERARCHY_LBVH && out->hierarchy != WN_HIERARCHY_KD) return fail(WN_ERR_INVALID_ARGUMENT, "bad hierarchy");
+    if (out->hierarchy < WN_HIERARCHY_LBVH || out->hierarchy > WN_HIERARCHY_KD_SAH) return fail(WN_ERR_INVALID_ARGUMENT, "bad hierarchy");
     return WN_OK;
 }
 
@@ -471,7 +471,14 @@ wn_status create_impl(const float* v_xyz, int64_t nV, const int32_t* tri, int64_
             add((size_t)nT * 4);
             add((size_t)nT * 4);
             add((size_t)wn::sort_scratch_bytes(nT));
-            if (opt.hierarchy == WN_HIERARCHY_KD) add((size_t)nT * 6 * sizeof(int)), add((size_t)nT);
+            if (opt.hierarchy != WN_HIERARCHY_LBVH) add((size_t)nT * 6 * sizeof(int)), add((size_t)nT);
+            if (opt.hierarchy == WN_HIERARCHY_KD_SAH) {
+                for (int r = 0; r < 2; ++r) add((size_t)(nT + 1) * 4), add((size_t)nT * 4), add((size_t)nT);
+                add((size_t)nT * 4), add((size_t)nT * 4), add((size_t)nT * 4);
+                add((size_t)wn::scan_scratch_elems(nT) * 4 + 256);
+                add(((size_t)nT / WN_KDX_MIN_SAH + 1) * 48 * 4);
+                add(64);
+            }
         } else {
             add((size_t)nI_max * W * 4);
             add((size_t)nN_max * 4);
@@ -540,8 +547,79 @@ wn_status create_impl(const float* v_xyz, int64_t nV, const int32_t* tri, int64_
             if (h_err) return cleanup(fail(WN_ERR_INVALID_ARGUMENT, "triangle references a vertex index outside [0, num_vertices)"));
         }
         const bool kd = opt.hierarchy == WN_HIERARCHY_KD && nT >= 2;
+        const bool kdx = opt.hierarchy == WN_HIERARCHY_KD_SAH && nT >= 2;
         const uint64_t* keys = nullptr;
-        if (!kd) {
+        WN_CUDA_C(dalloc((void**)&b.child, (size_t)b.nI * 2 * sizeof(int)));
+        WN_CUDA_C(dalloc((void**)&b.parent, (size_t)nN * sizeof(int)));
+        WN_CUDA_C(dalloc((void**)&b.slot, (size_t)nN));
+        WN_CUDA_C(cudaMemsetAsync(b.parent, 0xff, (size_t)nN * sizeof(int), st));
+        WN_CUDA_C(cudaMemsetAsync(b.slot, 0, (size_t)nN, st));
+        if (kdx) {
+            // K3'': level-synchronous k-d build with SAH-guided split positions (wn_kd.cuh)
+            const int N = (int)nT, leaf = std::max(1, opt.leaf_size);
+            int* d_bounds = nullptr;
+            unsigned *node_of = nullptr, *lstart[2] = {nullptr, nullptr};
+            int *lpid[2] = {nullptr, nullptr}, *d_nl = nullptr, *d_segbox = nullptr, *d_res = nullptr;
+            unsigned char *lmeta[2] = {nullptr, nullptr}, *d_skip = nullptr;
+            uint32_t *d_cnt = nullptr, *d_scan = nullptr;
+            WN_CUDA_C(dalloc((void**)&d_bounds, (size_t)nT * 6 * sizeof(int)));
+            WN_CUDA_C(dalloc((void**)&d_skip, (size_t)nT));
+            for (int r = 0; r < 2; ++r) {
+                WN_CUDA_C(dalloc((void**)&lstart[r], (size_t)(nT + 1) * 4));
+                WN_CUDA_C(dalloc((void**)&lpid[r], (size_t)nT * 4));
+                WN_CUDA_C(dalloc((void**)&lmeta[r], (size_t)nT));
+            }
+            WN_CUDA_C(dalloc((void**)&node_of, (size_t)nT * 4));
+            WN_CUDA_C(dalloc((void**)&d_nl, (size_t)nT * 4));
+            WN_CUDA_C(dalloc((void**)&d_cnt, (size_t)nT * 4));
+            WN_CUDA_C(dalloc((void**)&d_scan, (size_t)wn::scan_scratch_elems(nT) * 4 + 256));
+            const int64_t seg_rows = nT / WN_KDX_MIN_SAH + 1;
+            WN_CUDA_C(dalloc((void**)&d_segbox, (size_t)seg_rows * 48 * 4));
+            WN_CUDA_C(dalloc((void**)&d_res, 64));
+            wn::k_iota<<<wn::grid_for(nT), wn::kBuildThreads, 0, st>>>(v0, N);
+            WN_CUDA_C(cudaMemsetAsync(node_of, 0, (size_t)nT * 4, st));
+            WN_CUDA_C(cudaMemsetAsync(d_skip, 0, (size_t)nT, st));
+            {
+                const unsigned h_start[2] = {0u, (unsigned)N};
+                const int h_pid = -1;
+                WN_CUDA_C(cudaMemcpyAsync(lstart[0], h_start, sizeof(h_start), cudaMemcpyHostToDevice, st));
+                WN_CUDA_C(cudaMemcpyAsync(lpid[0], &h_pid, sizeof(h_pid), cudaMemcpyHostToDevice, st));
+                WN_CUDA_C(cudaMemsetAsync(lmeta[0], 0, 1, st));
+                WN_CUDA_C(cudaMemsetAsync(d_res, 0, 64, st));
+            }
+            tm.mark(); // 1
+            unsigned *cur = v0, *other = v1;
+            int count = 1;
+            for (int level = 0;; ++level) {
+                if (level > 160) return cleanup(fail(WN_ERR_CUDA, "k-d build did not terminate"));
+                const int r = level & 1;
+                wn::KdxLevel L{lstart[r], lpid[r], lmeta[r], count};
+                wn::k_kd_init_bounds<<<wn::grid_for((int64_t)count * 6), wn::kBuildThreads, 0, st>>>(d_bounds, count);
+                wn::k_kdx_bounds<<<wn::grid_for(nT), wn::kBuildThreads, 0, st>>>(d_v, d_tri, cur, node_of, N, lstart[r], leaf, d_bounds);
+                wn::k_kdx_keys<<<wn::grid_for(nT), wn::kBuildThreads, 0, st>>>(d_v, d_tri, cur, node_of, N, lstart[r], leaf, d_bounds, k0);
+                int nbits = 0;
+                while (((int64_t)1 << nbits) < count) ++nbits;
+                const int which = wn::radix_sort_pairs<uint64_t>(k0, cur, k1, other, nT, 0, 16 + nbits, sort_scratch, st);
+                if (which) std::swap(cur, other);
+                wn::k_kdx_init_segbox<<<wn::grid_for(seg_rows * 48), wn::kBuildThreads, 0, st>>>(d_segbox, seg_rows);
+                wn::k_kdx_segboxes<<<wn::grid_for(nT), wn::kBuildThreads, 0, st>>>(d_v, d_tri, cur, node_of, N, lstart[r], leaf, d_segbox);
+                WN_CUDA_C(cudaMemsetAsync(d_res, 0, 2 * sizeof(int), st));
+                wn::k_kdx_split<<<wn::grid_for(count), wn::kBuildThreads, 0, st>>>(L, N, leaf, level, d_segbox, d_nl, d_cnt, d_res);
+                wn::exclusive_scan_u32(d_cnt, count, d_scan, st);
+                wn::k_kdx_scatter<<<wn::grid_for(count), wn::kBuildThreads, 0, st>>>(L, N, level, d_nl, d_cnt, d_res, lstart[r ^ 1], lpid[r ^ 1],
+                                                                                       lmeta[r ^ 1], b.child, b.parent, b.slot, d_skip, d_res + 1);
+                wn::k_kdx_assign<<<wn::grid_for(nT), wn::kBuildThreads, 0, st>>>(node_of, N, lstart[r], d_nl, d_cnt);
+                int h_res[3] = {0, 0, 0};
+                WN_CUDA_C(cudaMemcpyAsync(h_res, d_res, sizeof(h_res), cudaMemcpyDeviceToHost, st));
+                WN_CUDA_C(cudaStreamSynchronize(st));
+                WN_CUDA_C(cudaGetLastError());
+                if (h_res[0] == 0) break; // nothing was split: every range is a finished leaf range, all linked by this pass
+                count = h_res[1];
+            }
+            d_prim = cur;
+            b.skip = env_int("WN_KD_WIDE", 1) ? d_skip : nullptr;
+            tm.mark(); // 2: order + hierarchy
+        } else if (!kd) {
             const int bpa = opt.morton_bits == 63 ? 21 : 10;
             wn::k_morton<uint64_t><<<wn::grid_for(nT), wn::kBuildThreads, 0, st>>>(d_v, d_tri, (int)nT, d_small, bpa, k0, v0);
             WN_CUDA_C(cudaGetLastError());
@@ -571,12 +649,9 @@ wn_status create_impl(const float* v_xyz, int64_t nV, const int32_t* tri, int64_
             d_prim = cur;
             tm.mark(); // 2: order
         }
-        WN_CUDA_C(dalloc((void**)&b.child, (size_t)b.nI * 2 * sizeof(int)));
-        WN_CUDA_C(dalloc((void**)&b.parent, (size_t)nN * sizeof(int)));
-        WN_CUDA_C(dalloc((void**)&b.slot, (size_t)nN));
-        WN_CUDA_C(cudaMemsetAsync(b.parent, 0xff, (size_t)nN * sizeof(int), st));
-        WN_CUDA_C(cudaMemsetAsync(b.slot, 0, (size_t)nN, st));
-        if (kd) {
+        if (kdx) {
+            // tree arrays were written level by level above
+        } else if (kd) {
             unsigned char* d_skip = nullptr;
             if (env_int("WN_KD_WIDE", 1)) {
                 WN_CUDA_C(dalloc((void**)&d_skip, (size_t)b.nI));

@@ -119,4 +119,204 @@ __global__ void __launch_bounds__(kBuildThreads) k_kd_tree(int N, int* __restric
     wn_kd_emit_node(N, g, child, parent, slot, skip, leaf_size);
 }
 
+// ---- K3'': SAH-guided split positions (WN_HIERARCHY_KD_SAH). Same idea as K3', but a range sorted along its axis is cut
+//      where  area(left) n_left + area(right) n_right  is least among the seven "first k eighths | rest" candidates (exact
+//      triangle boxes of the eight segments), so node ranges are explicit: per level, arrays over the nodes in position order.
+struct KdxLevel
+{
+    const unsigned* start; // [count + 1], start[count] = N
+    const int* pid;        // [count] id of the parent internal node (-1: root)
+    const unsigned char* meta; // [count] bit 0: slot in the parent, bit 1: already linked into the tree arrays
+    int count;
+};
+
+__global__ void __launch_bounds__(kBuildThreads) k_kdx_bounds(const float* __restrict__ v, const int* __restrict__ tri,
+                                                              const unsigned* __restrict__ perm, const unsigned* __restrict__ node_of, int N,
+                                                              const unsigned* __restrict__ start, int leaf, int* __restrict__ bounds)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned node = 0xffffffffu;
+    int enc[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
+    bool active = false;
+    if (p < N) {
+        const unsigned i = node_of[p];
+        active = (int)(start[i + 1] - start[i]) > leaf;
+        if (active) {
+            node = i;
+            float c[3];
+            kd_centroid(v, tri, perm[p], c);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                if (c[a] == c[a]) {
+                    enc[a] = float_to_ordered(c[a]);
+                    enc[3 + a] = enc[a];
+                }
+            }
+        }
+    }
+    const unsigned same = __match_any_sync(0xffffffffu, node);
+    if (same == 0xffffffffu) {
+        if (!active) return;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            enc[a] = __reduce_min_sync(0xffffffffu, enc[a]);
+            enc[3 + a] = __reduce_max_sync(0xffffffffu, enc[3 + a]);
+        }
+        if ((threadIdx.x & 31) != 0) return;
+    } else if (!active) {
+        return;
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        atomicMin(&bounds[6 * (size_t)node + a], enc[a]);
+        atomicMax(&bounds[6 * (size_t)node + 3 + a], enc[3 + a]);
+    }
+}
+
+__global__ void __launch_bounds__(kBuildThreads) k_kdx_keys(const float* __restrict__ v, const int* __restrict__ tri,
+                                                            const unsigned* __restrict__ perm, const unsigned* __restrict__ node_of, int N,
+                                                            const unsigned* __restrict__ start, int leaf, const int* __restrict__ bounds,
+                                                            uint64_t* __restrict__ keys)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= N) return;
+    const unsigned i = node_of[p];
+    unsigned q = 0;
+    if ((int)(start[i + 1] - start[i]) > leaf) {
+        const int* b = bounds + 6 * (size_t)i;
+        float blo[3], ext[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            blo[a] = ordered_to_float(b[a]);
+            ext[a] = b[3 + a] >= b[a] ? WN_SUB(ordered_to_float(b[3 + a]), blo[a]) : 0.0f;
+        }
+        const int axis = wn_kd_axis(ext);
+        float c[3];
+        kd_centroid(v, tri, perm[p], c);
+        q = wn_kd_quant(c[axis], blo[axis], ext[axis]);
+    }
+    keys[p] = ((uint64_t)i << 16) | q;
+}
+
+// boxes of the eight segments of every range with at least WN_KDX_MIN_SAH triangles; segbox row = start / WN_KDX_MIN_SAH
+__global__ void __launch_bounds__(kBuildThreads) k_kdx_segboxes(const float* __restrict__ v, const int* __restrict__ tri,
+                                                                const unsigned* __restrict__ perm, const unsigned* __restrict__ node_of, int N,
+                                                                const unsigned* __restrict__ start, int leaf, int* __restrict__ segbox)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= N) return;
+    const unsigned i = node_of[p];
+    const int s = (int)start[i], n = (int)(start[i + 1] - start[i]);
+    if (n <= leaf || n < WN_KDX_MIN_SAH) return;
+    const int seg = (int)(((long long)(p - s) * 8) / n);
+    const unsigned t = perm[p];
+    const int i0 = tri[3 * t], i1 = tri[3 * t + 1], i2 = tri[3 * t + 2];
+    int* row = segbox + ((size_t)(s / WN_KDX_MIN_SAH) * 8 + seg) * 6;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float x0 = v[3 * i0 + a], x1 = v[3 * i1 + a], x2 = v[3 * i2 + a];
+        const float lo = fminf(x0, fminf(x1, x2)), hi = fmaxf(x0, fmaxf(x1, x2)); // NaN coordinates are ignored by fminf/fmaxf
+        if (lo == lo) atomicMin(&row[a], float_to_ordered(lo));
+        if (hi == hi) atomicMax(&row[3 + a], float_to_ordered(hi));
+    }
+}
+
+// one thread per node: left count (0 = not split at this level), children count for the scan, bookkeeping in res[]:
+// res[0] += nodes split, res[2] = root gap (level 0)
+__global__ void __launch_bounds__(kBuildThreads) k_kdx_split(KdxLevel L, int N, int leaf, int level, const int* __restrict__ segbox,
+                                                             int* __restrict__ nl, uint32_t* __restrict__ cnt, int* __restrict__ res)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L.count) return;
+    const int s = (int)L.start[i], n = (int)(L.start[i + 1] - L.start[i]);
+    int left = 0;
+    if (n > leaf) {
+        left = n / 2;
+        if (n >= WN_KDX_MIN_SAH) {
+            float seg[48];
+            const int* row = segbox + (size_t)(s / WN_KDX_MIN_SAH) * 48;
+#pragma unroll
+            for (int k = 0; k < 48; ++k) // untouched sentinels decode to an empty box, like the host emulation's
+                seg[k] = row[k] == INT_MAX ? 3.4e38f : (row[k] == INT_MIN ? -3.4e38f : ordered_to_float(row[k]));
+            left = wn_kdx_choose(n, seg);
+        }
+        atomicAdd(&res[0], 1);
+    }
+    nl[i] = left;
+    cnt[i] = left > 0 ? 2u : 1u;
+    if (level == 0) res[2] = left > 0 ? s + left - 1 : N / 2 - 1;
+}
+
+// one thread per node: link it into the tree arrays, write its children (or itself, carried) into the next level
+__global__ void __launch_bounds__(kBuildThreads) k_kdx_scatter(KdxLevel L, int N, int level, const int* __restrict__ nl, const uint32_t* __restrict__ off,
+                                                               const int* __restrict__ res, unsigned* __restrict__ nstart, int* __restrict__ npid,
+                                                               unsigned char* __restrict__ nmeta, int* __restrict__ child, int* __restrict__ parent,
+                                                               unsigned char* __restrict__ slot, unsigned char* __restrict__ skip, int* __restrict__ total)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L.count) return;
+    const int s = (int)L.start[i], n = (int)(L.start[i + 1] - L.start[i]);
+    const int pid = L.pid[i], side = L.meta[i] & 1;
+    const bool linked = (L.meta[i] & 2) != 0;
+    const int root_gap = res[2], nI = N - 1;
+    const int left = nl[i];
+    const unsigned j = off[i];
+    if (left > 0) {
+        const int id = wn_kdx_gap_id(s + left - 1, root_gap);
+        if (pid >= 0) {
+            child[2 * (size_t)pid + side] = id;
+            parent[id] = pid;
+            slot[id] = (unsigned char)side;
+        }
+        if (skip) skip[id] = (level & 1) ? 1 : 0;
+        const int cs[2] = {s, s + left}, cm[2] = {left, n - left};
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            nstart[j + c] = (unsigned)cs[c];
+            npid[j + c] = id;
+            if (cm[c] == 1) { // a single triangle: leaf node nI + position, linked right away
+                child[2 * (size_t)id + c] = nI + cs[c];
+                parent[nI + cs[c]] = id;
+                slot[nI + cs[c]] = (unsigned char)c;
+                nmeta[j + c] = (unsigned char)(c | 2);
+            } else {
+                nmeta[j + c] = (unsigned char)c;
+            }
+        }
+    } else {
+        if (!linked) wn_kdx_emit_halving(N, s, n, pid, side, root_gap, child, parent, slot, skip);
+        nstart[j] = (unsigned)s;
+        npid[j] = pid;
+        nmeta[j] = (unsigned char)(side | 2);
+    }
+    if (i == L.count - 1) {
+        const int tot = (int)j + (left > 0 ? 2 : 1);
+        nstart[tot] = (unsigned)N;
+        *total = tot;
+    }
+}
+
+// elements follow their node into the next level
+__global__ void __launch_bounds__(kBuildThreads) k_kdx_assign(unsigned* __restrict__ node_of, int N, const unsigned* __restrict__ start,
+                                                              const int* __restrict__ nl, const uint32_t* __restrict__ off)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= N) return;
+    const unsigned i = node_of[p];
+    const int left = nl[i];
+    node_of[p] = off[i] + ((left > 0 && p >= (int)start[i] + left) ? 1u : 0u);
+}
+
+__global__ void __launch_bounds__(kBuildThreads) k_fill_int(int* __restrict__ p, int64_t n, int value)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = value;
+}
+
+__global__ void __launch_bounds__(kBuildThreads) k_kdx_init_segbox(int* __restrict__ segbox, int64_t rows)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < rows * 48) segbox[i] = (i % 6) < 3 ? INT_MAX : INT_MIN;
+}
+
 } // namespace wn

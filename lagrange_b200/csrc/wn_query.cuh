@@ -23,7 +23,7 @@
 //                    conditional: everything under a node that only some points accept -> short list with skip links in
 //                                list coordinates, walked by warp_traverse with the full per-point logic
 //                  k_tile_query streams the gathered records/triangles through tight loops (no tests, no votes, no
-//                  divergence), runs warp_traverse over the conditional list (staged in shared memory) and adds the
+//                  divergence), runs warp_traverse over the conditional list (read through L1, warp-uniform) and adds the
 //                  tensor-product Chebyshev interpolant of the far set. Which records a point accepts is unchanged; only
 //                  where their sum is evaluated differs (interpolation error ~1e-5 * 4 pi, bounded in tests).
 // All FP32 CUDA-core work (FMA pipe + MUFU rsqrt/atan): no tensor cores by design (BASELINE.json north_star).
@@ -174,7 +174,7 @@ __device__ __forceinline__ float eval_record(float rx, float ry, float rz, float
 
 // ----------------------------------------------------------------------------------------------------------------
 // The per-point traversal. LISTED = false: records are the packed tree itself. LISTED = true: records are the tile's
-// conditional list in shared memory (key, skip position). Accumulates into acc. Returns true if a far-field value the
+// conditional list in the plan's packet (key, skip position). Accumulates into acc. Returns true if a far-field value the
 // list cannot recover from was not finite (the caller then redoes the tile generically; the reference descends in
 // that case).
 // ----------------------------------------------------------------------------------------------------------------

@@ -134,9 +134,9 @@ class FastWindingNumber:
         opt.morton_bits = int(morton_bits)
         opt.radius_mode = {"box_corner": _capi.WN_RADIUS_BOX_CORNER, "vertex": _capi.WN_RADIUS_VERTEX}[radius_mode]
         opt.keep_build_data = 1 if keep_build_data else 0
-        if hierarchy not in ("lbvh", "kd"):
-            raise Error("hierarchy must be 'lbvh' or 'kd'")
-        opt.hierarchy = {"lbvh": 0, "kd": 1}[hierarchy]
+        if hierarchy not in ("lbvh", "kd", "kd_sah"):
+            raise Error("hierarchy must be 'lbvh', 'kd' or 'kd_sah'")
+        opt.hierarchy = {"lbvh": 0, "kd": 1, "kd_sah": 2}[hierarchy]
         opt.device = -1 if device is None else int(device)
         if approximate_single_triangles is None:
             approximate_single_triangles = topology is not None

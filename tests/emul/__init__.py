@@ -70,7 +70,7 @@ class EmulEngine:
         else:
             nn, w, cp = 0, 0, None
         self._h = lib().emul_build(self.v.ctypes.data_as(_f32p), len(self.v), self.f.ctypes.data_as(_i32p), len(self.f), cp, nn, w,
-                                   leaf_size, order, radius_mode, approx_single, morton_bits, {"lbvh": 0, "kd": 1}[hierarchy])
+                                   leaf_size, order, radius_mode, approx_single, morton_bits, {"lbvh": 0, "kd": 1, "kd_sah": 2}[hierarchy])
 
     def __del__(self):
         if getattr(self, "_h", None):

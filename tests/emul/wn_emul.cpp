@@ -35,7 +35,7 @@ extern "C" {
 void* emul_build(const float* v, int64_t nV, const int32_t* tri, int64_t nT, const int32_t* child_in, int64_t num_nodes, int width,
                  int leaf_size, int order, int radius_mode, int approx_single, int morton_bits, int hierarchy)
 {
-    const bool wide = hierarchy == 1; // the k-d hierarchy is packed 4-ary (odd-depth internal nodes get no record)
+    const bool wide = hierarchy >= 1; // the k-d hierarchies are packed 4-ary (odd-depth internal nodes get no record)
     Emul* e = new Emul;
     e->v.assign(v, v + nV * 3);
     e->tri.assign(tri, tri + nT * 3);
@@ -72,7 +72,135 @@ void* emul_build(const float* v, int64_t nV, const int32_t* tri, int64_t nT, con
         e->child.assign((size_t)b.nI * 2, -1);
         e->parent.assign(nN, -1);
         e->slot.assign(nN, 0);
-        if (hierarchy == 1 && nT >= 2) {
+        if (hierarchy == 2 && nT >= 2) {
+            // K3'' (wn_kd.cuh): level-synchronous k-d build with SAH-guided split positions, explicit node ranges
+            const int N = (int)nT, leaf = std::max(1, leaf_size), nI = N - 1;
+            std::vector<unsigned> perm(nT), node_of(nT, 0u);
+            std::iota(perm.begin(), perm.end(), 0u);
+            std::vector<unsigned> start{0u, (unsigned)N};
+            std::vector<int> pid{-1};
+            std::vector<unsigned char> meta{0};
+            e->skip.assign(b.nI, 0);
+            int root_gap = 0;
+            for (int level = 0;; ++level) {
+                const int count = (int)pid.size();
+                std::vector<float> nlo((size_t)count * 3, 3.4e38f), nhi((size_t)count * 3, -3.4e38f);
+                for (int p = 0; p < N; ++p) {
+                    const unsigned i = node_of[p];
+                    if ((int)(start[i + 1] - start[i]) <= leaf) continue;
+                    const float* c = &cen[3 * (size_t)perm[p]];
+                    for (int a = 0; a < 3; ++a)
+                        if (c[a] == c[a]) {
+                            nlo[3 * (size_t)i + a] = std::min(nlo[3 * (size_t)i + a], c[a]);
+                            nhi[3 * (size_t)i + a] = std::max(nhi[3 * (size_t)i + a], c[a]);
+                        }
+                }
+                std::vector<uint64_t> key(nT);
+                for (int p = 0; p < N; ++p) {
+                    const unsigned i = node_of[p];
+                    unsigned q = 0;
+                    if ((int)(start[i + 1] - start[i]) > leaf) {
+                        float ext3[3];
+                        for (int a = 0; a < 3; ++a) ext3[a] = nhi[3 * (size_t)i + a] >= nlo[3 * (size_t)i + a] ? nhi[3 * (size_t)i + a] - nlo[3 * (size_t)i + a] : 0.0f;
+                        const int axis = wn_kd_axis(ext3);
+                        q = wn_kd_quant(cen[3 * (size_t)perm[p] + axis], nlo[3 * (size_t)i + axis], ext3[axis]);
+                    }
+                    key[p] = ((uint64_t)i << 16) | q;
+                }
+                {
+                    std::vector<unsigned> idx2(nT);
+                    std::iota(idx2.begin(), idx2.end(), 0u);
+                    std::stable_sort(idx2.begin(), idx2.end(), [&](unsigned a, unsigned c2) { return key[a] < key[c2]; });
+                    std::vector<unsigned> np(nT);
+                    for (int64_t i = 0; i < nT; ++i) np[i] = perm[idx2[i]];
+                    perm.swap(np); // node_of is unchanged: the sort only permutes inside ranges
+                }
+                // split decisions
+                std::vector<int> nl(count, 0);
+                std::vector<unsigned> off(count + 1, 0u);
+                int n_split = 0;
+                for (int i = 0; i < count; ++i) {
+                    const int s0 = (int)start[i], n = (int)(start[i + 1] - start[i]);
+                    int left = 0;
+                    if (n > leaf) {
+                        left = n / 2;
+                        if (n >= WN_KDX_MIN_SAH) {
+                            float seg[48];
+                            for (int k = 0; k < 8; ++k)
+                                for (int a = 0; a < 3; ++a) seg[k * 6 + a] = 3.4e38f, seg[k * 6 + 3 + a] = -3.4e38f;
+                            bool any_lo[48] = {false};
+                            for (int j = 0; j < n; ++j) {
+                                const int sgm = (int)(((long long)j * 8) / n);
+                                const unsigned t = perm[s0 + j];
+                                for (int a = 0; a < 3; ++a) {
+                                    const float x0 = v[3 * tri[3 * t] + a], x1 = v[3 * tri[3 * t + 1] + a], x2 = v[3 * tri[3 * t + 2] + a];
+                                    const float lo2 = fminf(x0, fminf(x1, x2)), hi2 = fmaxf(x0, fmaxf(x1, x2));
+                                    if (lo2 == lo2) seg[sgm * 6 + a] = std::min(seg[sgm * 6 + a], lo2), any_lo[sgm * 6 + a] = true;
+                                    if (hi2 == hi2) seg[sgm * 6 + 3 + a] = std::max(seg[sgm * 6 + 3 + a], hi2), any_lo[sgm * 6 + 3 + a] = true;
+                                }
+                            }
+                            // the device decodes untouched ordered-int sentinels (INT_MAX / INT_MIN) to NaN-like floats; an empty side is
+                            // an empty box either way (wn_kdx_half_area returns 0 when hi >= lo fails)
+                            left = wn_kdx_choose(n, seg);
+                        }
+                        ++n_split;
+                    }
+                    nl[i] = left;
+                    off[i + 1] = off[i] + (left > 0 ? 2u : 1u);
+                    if (level == 0) root_gap = left > 0 ? s0 + left - 1 : N / 2 - 1;
+                }
+                // scatter
+                const int total = (int)off[count];
+                std::vector<unsigned> nstart(total + 1);
+                std::vector<int> npid(total);
+                std::vector<unsigned char> nmeta(total);
+                for (int i = 0; i < count; ++i) {
+                    const int s0 = (int)start[i], n = (int)(start[i + 1] - start[i]);
+                    const int side = meta[i] & 1;
+                    const bool linked = (meta[i] & 2) != 0;
+                    const unsigned j = off[i];
+                    const int left = nl[i];
+                    if (left > 0) {
+                        const int id = wn_kdx_gap_id(s0 + left - 1, root_gap);
+                        if (pid[i] >= 0) {
+                            e->child[2 * (size_t)pid[i] + side] = id;
+                            e->parent[id] = pid[i];
+                            e->slot[id] = (unsigned char)side;
+                        }
+                        e->skip[id] = (level & 1) ? 1 : 0;
+                        const int cs[2] = {s0, s0 + left}, cm[2] = {left, n - left};
+                        for (int c = 0; c < 2; ++c) {
+                            nstart[j + c] = (unsigned)cs[c];
+                            npid[j + c] = id;
+                            if (cm[c] == 1) {
+                                e->child[2 * (size_t)id + c] = nI + cs[c];
+                                e->parent[nI + cs[c]] = id;
+                                e->slot[nI + cs[c]] = (unsigned char)c;
+                                nmeta[j + c] = (unsigned char)(c | 2);
+                            } else {
+                                nmeta[j + c] = (unsigned char)c;
+                            }
+                        }
+                    } else {
+                        if (!linked) wn_kdx_emit_halving(N, s0, n, pid[i], side, root_gap, e->child.data(), e->parent.data(), e->slot.data(), e->skip.data());
+                        nstart[j] = (unsigned)s0;
+                        npid[j] = pid[i];
+                        nmeta[j] = (unsigned char)(side | 2);
+                    }
+                }
+                nstart[total] = (unsigned)N;
+                for (int p = 0; p < N; ++p) {
+                    const unsigned i = node_of[p];
+                    node_of[p] = off[i] + ((nl[i] > 0 && p >= (int)start[i] + nl[i]) ? 1u : 0u);
+                }
+                if (n_split == 0) break;
+                start.swap(nstart);
+                pid.swap(npid);
+                meta.swap(nmeta);
+            }
+            e->prim = perm;
+            if (wide) b.skip = e->skip.data();
+        } else if (hierarchy == 1 && nT >= 2) {
             // K3' (wn_kd.cuh): per level, node centroid bounds -> (path, 16-bit coordinate) keys -> stable sort
             std::vector<unsigned> perm(nT);
             std::iota(perm.begin(), perm.end(), 0u);

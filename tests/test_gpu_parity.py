@@ -429,13 +429,14 @@ def test_cfg2_full_size_sphere_properties(lb, prim):
 
 # ---- K3': balanced k-d hierarchy (wn_options.hierarchy = WN_HIERARCHY_KD) ----------------------------------------------
 @pytest.mark.gpu
+@pytest.mark.parametrize("hierarchy", ["kd", "kd_sah"])
 @pytest.mark.parametrize("cfg,leaf", [(1, 1), (3, 1), (1, 4)])
-def test_kd_hierarchy_equals_host_emulation(prim, emul_mod, cfg, leaf):
+def test_kd_hierarchy_equals_host_emulation(prim, emul_mod, cfg, leaf, hierarchy):
     import lagrange_b200 as lb
 
     V, F, q, _ = small_config(prim, cfg)
-    eng = lb.FastWindingNumber(V, F, hierarchy="kd", keep_build_data=True, leaf_size=leaf)
-    em = emul_mod.EmulEngine(V, F, hierarchy="kd", leaf_size=leaf)
+    eng = lb.FastWindingNumber(V, F, hierarchy=hierarchy, keep_build_data=True, leaf_size=leaf)
+    em = emul_mod.EmulEngine(V, F, hierarchy=hierarchy, leaf_size=leaf)
     assert np.array_equal(eng.debug_topology(), em.topology())
     # same topology, same moments (unfused build arithmetic), same folded records: the traversal differs only by the device's
     # rsqrt / FMA contraction in the exact-triangle term
@@ -476,7 +477,8 @@ def test_kd_hierarchy_degenerate_inputs(prim):
     V = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], dtype=np.float32)
     for copies in (2, 3, 37):
         F = np.tile(np.array([[0, 1, 2]], dtype=np.int32), (copies, 1))
-        eng = lb.FastWindingNumber(V, F, hierarchy="kd")
         ref = lb.FastWindingNumber(V, F)
         q = np.array([[0.2, 0.2, 0.5], [0.2, 0.2, -0.5], [3, 3, 3]], dtype=np.float32)
-        assert np.allclose(eng.solid_angle(q), ref.solid_angle(q), atol=1e-5 * copies)
+        for hierarchy in ("kd", "kd_sah"):
+            eng = lb.FastWindingNumber(V, F, hierarchy=hierarchy)
+            assert np.allclose(eng.solid_angle(q), ref.solid_angle(q), atol=1e-5 * copies)
