@@ -169,10 +169,11 @@ def test_inside_threshold_matches_the_reference_expression(oracle_mod, emul_mod)
         assert bool(L.emul_inside_from_omega(v)) == oracle_mod.inside_predicate(v)
 
 
-def test_kd_hierarchy_is_balanced_and_complete(emul_mod, prim, oracle_mod):
-    """K3' (wn_kd.cuh): the balanced object-median hierarchy, emulated on the host from the device source."""
+@pytest.mark.parametrize("hierarchy", ["kd", "kd_sah"])
+def test_kd_hierarchy_is_balanced_and_complete(emul_mod, prim, oracle_mod, hierarchy):
+    """K3' / K3'' (wn_kd.cuh): the k-d hierarchies, emulated on the host from the device source."""
     V, F = prim.generate_torus(5, 1, 20, 11)  # 440 triangles: not a power of two
-    em = emul_mod.EmulEngine(V, F, hierarchy="kd")
+    em = emul_mod.EmulEngine(V, F, hierarchy=hierarchy)
     assert em.error == 0
     topo = em.topology()
     assert topo.shape == (len(F) - 1, 2)
@@ -193,7 +194,10 @@ def test_kd_hierarchy_is_balanced_and_complete(emul_mod, prim, oracle_mod):
                 seen_tri[-(c + 2)] += 1
                 depth[("t", -(c + 2))] = depth[u] + 1
     assert np.all(seen_tri == 1) and np.all(seen_node == 1)
-    assert max(depth.values()) == int(np.ceil(np.log2(len(F))))
+    if hierarchy == "kd":
+        assert max(depth.values()) == int(np.ceil(np.log2(len(F))))
+    else:  # SAH cuts lie between 1/8 and 7/8 of a range
+        assert max(depth.values()) <= int(np.ceil(np.log(len(F)) / np.log(8.0 / 7.0)))
     check_packed_structure(em, len(F))
     # same engine semantics on this hierarchy: the error against the exact winding number is the restatement's error class
     q = prim.uniform_points_in_bbox(*prim.mesh_bbox(V), 4000, seed=2)
