@@ -2,7 +2,7 @@
 """Throughput and full-size parity sample of the narrow-band signed distance (K10, wn_sdf_grid) on BASELINE cfg2's mesh:
 1 310 720-triangle icosphere, 512^3 voxels over [-1.1, 1.1]^3, band = 3 voxels (what volume::mesh_to_volume asks of OpenVDB).
 
-    python tools/sdf_report.py > gpurun_out/sdf_report.json
+    python tests/tools/sdf_report.py > gpurun_out/sdf_report.json
 """
 import json
 import os
@@ -12,7 +12,7 @@ import time
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import lagrange_b200 as lb  # noqa: E402
 import oracle  # noqa: E402  (checker only)
 

@@ -2,7 +2,7 @@
 """Query throughput of cfg2 on the GPU-built LBVH vs the restatement's 4-ary SAH topology (imported with
 wn_create_from_topology): how much a higher-quality hierarchy would buy the same kernels.
 
-    python tools/tree_quality.py [subdiv] > gpurun_out/tree_quality.json
+    python tests/tools/tree_quality.py [subdiv] > gpurun_out/tree_quality.json
 """
 import json
 import os
@@ -11,7 +11,7 @@ import sys
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import lagrange_b200 as lb  # noqa: E402
 import oracle  # noqa: E402
 
