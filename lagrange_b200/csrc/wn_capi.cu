@@ -191,6 +191,7 @@ struct wn_engine
     std::vector<void*> kept_allocs; // device allocations that back the kept arrays
     // per-engine query scratch, guarded by mu
     mutable std::mutex mu;
+    mutable std::mutex sdf_mu; // wn_sdf_grid runs two passes (sign, distance) over shared scratch: one caller at a time
     mutable DevBuf s_in, s_out_f, s_out_b, s_sort, s_stats, s_partial, s_plan_hdr, s_plan_items, s_plan_samples, s_plan_order, s_sdf_inside;
     mutable PinnedBuf p_small;
     mutable cudaStream_t copy_stream = nullptr; // D2H of finished batches while the next batch computes
@@ -1513,6 +1514,7 @@ wn_status wn_sdf_grid(const wn_engine* e, const float* origin, const float* spac
     DeviceGuard guard(e->device);
     if (!guard.ok) return fail(WN_ERR_CUDA, "cannot select CUDA device %d", e->device);
     cudaStream_t st = (cudaStream_t)stream;
+    std::lock_guard<std::mutex> sdf_lock(e->sdf_mu);
     uint8_t* d_inside = nullptr;
     if (!(flags & WN_SDF_UNSIGNED)) {
         {
