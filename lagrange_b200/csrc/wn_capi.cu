@@ -191,6 +191,10 @@ struct wn_engine
     std::vector<void*> kept_allocs; // device allocations that back the kept arrays
     // per-engine query scratch, guarded by mu
     mutable std::mutex mu;
+    // the per-engine scratch is reused by every call: work submitted on a different stream than the previous call's waits for it
+    mutable cudaStream_t last_stream = nullptr;
+    mutable cudaEvent_t ev_last = nullptr;
+    mutable bool ev_last_valid = false;
     mutable std::mutex sdf_mu; // wn_sdf_grid runs two passes (sign, distance) over shared scratch: one caller at a time
     mutable DevBuf s_in, s_out_f, s_out_b, s_sort, s_stats, s_partial, s_plan_hdr, s_plan_items, s_plan_samples, s_plan_order, s_sdf_inside;
     mutable PinnedBuf p_small;
@@ -1010,6 +1014,32 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
     return WN_OK;
 }
 
+// Orders the work of consecutive calls that arrive on different streams (they share the engine's scratch buffers). Declared
+// after the engine lock is taken, so it records its event before the lock is released.
+struct StreamOrder
+{
+    const wn_engine* e;
+    cudaStream_t st;
+    StreamOrder(const wn_engine* e_, cudaStream_t st_) : e(e_), st(st_)
+    {
+        if (e->ev_last_valid && e->last_stream != st) cudaStreamWaitEvent(st, e->ev_last, 0);
+    }
+    ~StreamOrder()
+    {
+        if (!e->ev_last && cudaEventCreateWithFlags(&e->ev_last, cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            e->ev_last = nullptr;
+            return;
+        }
+        if (cudaEventRecord(e->ev_last, st) == cudaSuccess) {
+            e->last_stream = st;
+            e->ev_last_valid = true;
+        } else {
+            cudaGetLastError();
+        }
+    }
+};
+
 wn_status points_impl(const wn_engine* e, const float* q_xyz, int64_t n, float beta, uint32_t flags, float* out_omega,
                       uint8_t* out_inside, wn_query_stats* stats, void* stream)
 {
@@ -1022,6 +1052,7 @@ wn_status points_impl(const wn_engine* e, const float* q_xyz, int64_t n, float b
     if (!guard.ok) return fail(WN_ERR_CUDA, "cannot select CUDA device %d", e->device);
     std::lock_guard<std::mutex> lock(e->mu);
     cudaStream_t st = (cudaStream_t)stream;
+    StreamOrder order(e, st);
     const float b = beta > 0.0f ? beta : e->opt.accuracy_scale;
     // Small host batches (the reference's own calling pattern is one point per call, FastWindingNumber.cpp:60-76): the kernel
     // reads the queries from, and writes the results to, pinned host memory directly (unified addressing), so a call is one
@@ -1146,6 +1177,7 @@ wn_status grid_impl(const wn_engine* e, const float* origin, const float* spacin
     if (!guard.ok) return fail(WN_ERR_CUDA, "cannot select CUDA device %d", e->device);
     std::lock_guard<std::mutex> lock(e->mu);
     cudaStream_t st = (cudaStream_t)stream;
+    StreamOrder order(e, st);
     const float b = beta > 0.0f ? beta : e->opt.accuracy_scale;
     OutBufs ob;
     s = prepare_outputs(e, n, out_omega, out_inside, ob);
@@ -1175,6 +1207,7 @@ wn_status exact_impl(const wn_engine* e, bool grid, const float* q_xyz, int64_t 
     if (!guard.ok) return fail(WN_ERR_CUDA, "cannot select CUDA device %d", e->device);
     std::lock_guard<std::mutex> lock(e->mu);
     cudaStream_t st = (cudaStream_t)stream;
+    StreamOrder order(e, st);
     const float* d_q = nullptr;
     wn_status s = WN_OK;
     if (!grid) {
@@ -1324,6 +1357,7 @@ wn_status wn_destroy(wn_engine* e)
         e->s_sdf_inside.release();
         e->p_small.release();
         if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+        if (e->ev_last) cudaEventDestroy(e->ev_last);
     }
     delete e;
     return WN_OK;
@@ -1527,6 +1561,7 @@ wn_status wn_sdf_grid(const wn_engine* e, const float* origin, const float* spac
         if (s != WN_OK) return s;
     }
     std::lock_guard<std::mutex> lock(e->mu);
+    StreamOrder order(e, st);
     OutBufs ob;
     s = prepare_outputs(e, n, out_sdf, nullptr, ob);
     if (s != WN_OK) return s;

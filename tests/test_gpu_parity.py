@@ -482,3 +482,28 @@ def test_kd_hierarchy_degenerate_inputs(prim):
         for hierarchy in ("kd", "kd_sah"):
             eng = lb.FastWindingNumber(V, F, hierarchy=hierarchy)
             assert np.allclose(eng.solid_angle(q), ref.solid_angle(q), atol=1e-5 * copies)
+
+
+@pytest.mark.gpu
+def test_calls_on_different_streams_share_the_engine_safely(prim):
+    """Per-engine scratch (tile plans, staging) is reused by every call; consecutive calls on different CUDA streams are
+    ordered by the library (an event between them), so device-resident results do not depend on the stream pattern."""
+    import torch
+
+    import lagrange_b200 as lb
+
+    V, F = prim.generate_torus(5, 1, 120, 60)
+    eng = lb.FastWindingNumber(V, F, hierarchy="kd", leaf_size=4)
+    lattices = [prim.lattice_for_bbox(*prim.mesh_bbox(V), (96 + 8 * k, 40, 96), inflate=0.05 + 0.01 * k) for k in range(4)]
+    want = [eng.query_grid(o, s, d, want_omega=True, device_output=True) for o, s, d in lattices]
+    want = [(om.clone(), ins.clone()) for om, ins in want]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    got = []
+    for rep in range(3):
+        got.clear()
+        for k, (o, s, d) in enumerate(lattices):
+            with torch.cuda.stream(streams[k & 1]):
+                got.append(eng.query_grid(o, s, d, want_omega=True, device_output=True))
+        torch.cuda.synchronize()
+        for (om, ins), (wom, wins) in zip(got, want):
+            assert torch.equal(om, wom) and torch.equal(ins, wins)
