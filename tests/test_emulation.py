@@ -206,3 +206,49 @@ def test_kd_hierarchy_is_balanced_and_complete(emul_mod, prim, oracle_mod, hiera
     w_ref = oracle_mod.RefEngine(V, F).solid_angle(q) / (4 * np.pi)
     assert np.abs(w - w_exact).max() < 2.0 * max(np.abs(w_ref - w_exact).max(), 2e-3)
     assert np.abs(w - w_exact).mean() < 2.0 * np.abs(w_ref - w_exact).mean()
+
+
+def _check_binary_topology(topo, nT):
+    seen_tri, seen_node = np.zeros(nT, dtype=int), np.zeros(len(topo), dtype=int)
+    stack = [0]
+    seen_node[0] = 1
+    while stack:
+        u = stack.pop()
+        for c in topo[u]:
+            if c >= 0:
+                seen_node[c] += 1
+                stack.append(c)
+            elif c <= -2:
+                seen_tri[-(c + 2)] += 1
+    assert np.all(seen_tri == 1) and np.all(seen_node == 1)
+
+
+@pytest.mark.parametrize("hierarchy", ["kd", "kd_sah"])
+def test_kd_builders_on_random_and_degenerate_soups(emul_mod, oracle_mod, hierarchy):
+    """Random triangle soups of awkward sizes, with duplicated triangles, zero-area triangles and coincident centroids: the
+    k-d builders must always produce a complete tree and the same winding numbers as the exact sum far from the soup."""
+    rng = np.random.RandomState(7)
+    for n in (2, 3, 5, 15, 16, 17, 31, 64, 127, 200):
+        V = rng.randn(3 * n, 3).astype(np.float32)
+        F = np.arange(3 * n, dtype=np.int32).reshape(n, 3)
+        if n >= 5:
+            F[1] = F[0]                      # duplicate
+            F[2] = [F[2, 0], F[2, 0], F[2, 1]]  # zero area
+            V[F[3]] = V[F[4]]                # coincident copy (same centroid, same box)
+        for leaf in (1, 4):
+            em = emul_mod.EmulEngine(V, F, hierarchy=hierarchy, leaf_size=leaf)
+            assert em.error == 0
+            topo = em.topology()
+            assert topo.shape == (n - 1, 2)
+            _check_binary_topology(topo, n)
+            check_packed_structure(em, n)
+            q = (rng.randn(64, 3) * 30).astype(np.float32)  # far away: everything is expanded, errors are tiny
+            w = em.solid_angle(q) / (4 * np.pi)
+            w_exact = oracle_mod.exact64(V, F, q) / (4 * np.pi)
+            assert np.abs(w - w_exact).max() < 2e-4
+    # all triangles identical
+    V = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], dtype=np.float32)
+    F = np.tile(np.array([[0, 1, 2]], dtype=np.int32), (40, 1))
+    em = emul_mod.EmulEngine(V, F, hierarchy=hierarchy)
+    assert em.error == 0
+    _check_binary_topology(em.topology(), 40)
