@@ -594,7 +594,7 @@ wn_status create_impl(const float* v_xyz, int64_t nV, const int32_t* tri, int64_
             }
             tm.mark(); // 1
             unsigned *cur = v0, *other = v1;
-            int count = 1;
+            int count = 1, max_range = N;
             for (int level = 0;; ++level) {
                 if (level > 160) return cleanup(fail(WN_ERR_CUDA, "k-d build did not terminate"));
                 const int r = level & 1;
@@ -606,20 +606,24 @@ wn_status create_impl(const float* v_xyz, int64_t nV, const int32_t* tri, int64_
                 while (((int64_t)1 << nbits) < count) ++nbits;
                 const int which = wn::radix_sort_pairs<uint64_t>(k0, cur, k1, other, nT, 0, 16 + nbits, sort_scratch, st);
                 if (which) std::swap(cur, other);
-                wn::k_kdx_init_segbox<<<wn::grid_for(seg_rows * 48), wn::kBuildThreads, 0, st>>>(d_segbox, seg_rows);
-                wn::k_kdx_segboxes<<<wn::grid_for(nT), wn::kBuildThreads, 0, st>>>(d_v, d_tri, cur, node_of, N, lstart[r], leaf, d_segbox);
+                if (max_range >= WN_KDX_MIN_SAH && max_range > leaf) { // otherwise every split of this level is a median split
+                    wn::k_kdx_init_segbox_nodes<<<wn::grid_for((int64_t)count * 48), wn::kBuildThreads, 0, st>>>(lstart[r], count, leaf, d_segbox);
+                    wn::k_kdx_segboxes<<<wn::grid_for(nT), wn::kBuildThreads, 0, st>>>(d_v, d_tri, cur, node_of, N, lstart[r], leaf, d_segbox);
+                }
                 WN_CUDA_C(cudaMemsetAsync(d_res, 0, 2 * sizeof(int), st));
+                WN_CUDA_C(cudaMemsetAsync(d_res + 3, 0, sizeof(int), st));
                 wn::k_kdx_split<<<wn::grid_for(count), wn::kBuildThreads, 0, st>>>(L, N, leaf, level, d_segbox, d_nl, d_cnt, d_res);
                 wn::exclusive_scan_u32(d_cnt, count, d_scan, st);
                 wn::k_kdx_scatter<<<wn::grid_for(count), wn::kBuildThreads, 0, st>>>(L, N, level, d_nl, d_cnt, d_res, lstart[r ^ 1], lpid[r ^ 1],
                                                                                        lmeta[r ^ 1], b.child, b.parent, b.slot, d_skip, d_res + 1);
                 wn::k_kdx_assign<<<wn::grid_for(nT), wn::kBuildThreads, 0, st>>>(node_of, N, lstart[r], d_nl, d_cnt);
-                int h_res[3] = {0, 0, 0};
+                int h_res[4] = {0, 0, 0, 0};
                 WN_CUDA_C(cudaMemcpyAsync(h_res, d_res, sizeof(h_res), cudaMemcpyDeviceToHost, st));
                 WN_CUDA_C(cudaStreamSynchronize(st));
                 WN_CUDA_C(cudaGetLastError());
                 if (h_res[0] == 0) break; // nothing was split: every range is a finished leaf range, all linked by this pass
                 count = h_res[1];
+                max_range = h_res[3];
             }
             d_prim = cur;
             b.skip = env_int("WN_KD_WIDE", 1) ? d_skip : nullptr;

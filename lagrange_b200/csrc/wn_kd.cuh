@@ -198,27 +198,63 @@ __global__ void __launch_bounds__(kBuildThreads) k_kdx_keys(const float* __restr
     keys[p] = ((uint64_t)i << 16) | q;
 }
 
-// boxes of the eight segments of every range with at least WN_KDX_MIN_SAH triangles; segbox row = start / WN_KDX_MIN_SAH
+// boxes of the eight segments of every range with at least WN_KDX_MIN_SAH triangles; segbox row = start / WN_KDX_MIN_SAH.
+// Consecutive positions mostly share (range, segment): a warp whose lanes all hit the same row reduces first and issues one
+// set of atomics (near the root every warp does; without this the root's 48 addresses take 1.3 M atomics each level).
 __global__ void __launch_bounds__(kBuildThreads) k_kdx_segboxes(const float* __restrict__ v, const int* __restrict__ tri,
                                                                 const unsigned* __restrict__ perm, const unsigned* __restrict__ node_of, int N,
                                                                 const unsigned* __restrict__ start, int leaf, int* __restrict__ segbox)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= N) return;
-    const unsigned i = node_of[p];
-    const int s = (int)start[i], n = (int)(start[i + 1] - start[i]);
-    if (n <= leaf || n < WN_KDX_MIN_SAH) return;
-    const int seg = (int)(((long long)(p - s) * 8) / n);
-    const unsigned t = perm[p];
-    const int i0 = tri[3 * t], i1 = tri[3 * t + 1], i2 = tri[3 * t + 2];
-    int* row = segbox + ((size_t)(s / WN_KDX_MIN_SAH) * 8 + seg) * 6;
+    long long rowid = -1;
+    int enc[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
+    if (p < N) {
+        const unsigned i = node_of[p];
+        const int s = (int)start[i], n = (int)(start[i + 1] - start[i]);
+        if (n > leaf && n >= WN_KDX_MIN_SAH) {
+            const int seg = (int)(((long long)(p - s) * 8) / n);
+            rowid = (long long)(s / WN_KDX_MIN_SAH) * 8 + seg;
+            const unsigned t = perm[p];
+            const int i0 = tri[3 * t], i1 = tri[3 * t + 1], i2 = tri[3 * t + 2];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const float x0 = v[3 * i0 + a], x1 = v[3 * i1 + a], x2 = v[3 * i2 + a];
+                const float lo = fminf(x0, fminf(x1, x2)), hi = fmaxf(x0, fmaxf(x1, x2)); // NaN coordinates are ignored by fminf/fmaxf
+                if (lo == lo) enc[a] = float_to_ordered(lo);
+                if (hi == hi) enc[3 + a] = float_to_ordered(hi);
+            }
+        }
+    }
+    const unsigned same = __match_any_sync(0xffffffffu, rowid);
+    if (same == 0xffffffffu) {
+        if (rowid < 0) return;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            enc[a] = __reduce_min_sync(0xffffffffu, enc[a]);
+            enc[3 + a] = __reduce_max_sync(0xffffffffu, enc[3 + a]);
+        }
+        if ((threadIdx.x & 31) != 0) return;
+    } else if (rowid < 0) {
+        return;
+    }
+    int* row = segbox + (size_t)rowid * 6;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        const float x0 = v[3 * i0 + a], x1 = v[3 * i1 + a], x2 = v[3 * i2 + a];
-        const float lo = fminf(x0, fminf(x1, x2)), hi = fmaxf(x0, fmaxf(x1, x2)); // NaN coordinates are ignored by fminf/fmaxf
-        if (lo == lo) atomicMin(&row[a], float_to_ordered(lo));
-        if (hi == hi) atomicMax(&row[3 + a], float_to_ordered(hi));
+        if (enc[a] != INT_MAX) atomicMin(&row[a], enc[a]);
+        if (enc[3 + a] != INT_MIN) atomicMax(&row[3 + a], enc[3 + a]);
     }
+}
+
+// sentinels for the segment boxes of the ranges that will be measured at this level (one thread per node and value)
+__global__ void __launch_bounds__(kBuildThreads) k_kdx_init_segbox_nodes(const unsigned* __restrict__ start, int count, int leaf,
+                                                                         int* __restrict__ segbox)
+{
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = (int)(g / 48), k = (int)(g % 48);
+    if (i >= count) return;
+    const int s = (int)start[i], n = (int)(start[i + 1] - start[i]);
+    if (n <= leaf || n < WN_KDX_MIN_SAH) return;
+    segbox[(size_t)(s / WN_KDX_MIN_SAH) * 48 + k] = (k % 6) < 3 ? INT_MAX : INT_MIN;
 }
 
 // one thread per node: left count (0 = not split at this level), children count for the scan, bookkeeping in res[]:
@@ -241,6 +277,7 @@ __global__ void __launch_bounds__(kBuildThreads) k_kdx_split(KdxLevel L, int N, 
             left = wn_kdx_choose(n, seg);
         }
         atomicAdd(&res[0], 1);
+        atomicMax(&res[3], max(left, n - left)); // largest range of the next level: the host skips the SAH passes below the threshold
     }
     nl[i] = left;
     cnt[i] = left > 0 ? 2u : 1u;
@@ -311,12 +348,6 @@ __global__ void __launch_bounds__(kBuildThreads) k_fill_int(int* __restrict__ p,
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = value;
-}
-
-__global__ void __launch_bounds__(kBuildThreads) k_kdx_init_segbox(int* __restrict__ segbox, int64_t rows)
-{
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < rows * 48) segbox[i] = (i % 6) < 3 ? INT_MAX : INT_MIN;
 }
 
 } // namespace wn

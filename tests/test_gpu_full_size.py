@@ -125,12 +125,12 @@ def test_cfg5_full_size_exact_vs_tree_sweep(lb, oracle_mod, prim):
 
 
 def test_cfg2_full_size_bench_configuration(lb, oracle_mod, prim):
-    """What bench.py measures, at full size: balanced k-d hierarchy, 4-triangle leaves, tiled path, 512^3 lattice.
+    """What bench.py measures, at full size: k-d hierarchy with SAH-guided cuts, 4-triangle leaves, tiled path, 512^3 lattice.
     Against the restatement on every lattice point (different trees: agreement outside the band widened by both trees'
     error), against the exact winding number on a sample, and against the analytic volume of the unit sphere."""
     V, F = prim.config_mesh(2)
     _, (o, s, d) = prim.config_queries(2, V, F)
-    eng = lb.FastWindingNumber(V, F, hierarchy="kd", leaf_size=4)
+    eng = lb.FastWindingNumber(V, F, hierarchy="kd_sah", leaf_size=4)
     om, ins = eng.query_grid(o, s, d, want_omega=True, want_inside=True)
     # same engine, per-point traversal instead of tiles: the far-set interpolation is the only difference
     om_g = eng.query_grid(o, s, d, want_omega=True, want_inside=False, tiling=False)[0]

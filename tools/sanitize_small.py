@@ -10,7 +10,7 @@ import lagrange_b200 as lb  # noqa: E402
 prim = lb.primitive
 V, F = prim.generate_torus(5, 1, 40, 20)
 os.environ["WN_TILE"] = "1"
-for kw in ({}, {"leaf_size": 4}, {"hierarchy": "kd"}, {"hierarchy": "kd", "leaf_size": 4}):
+for kw in ({}, {"leaf_size": 4}, {"hierarchy": "kd"}, {"hierarchy": "kd", "leaf_size": 4}, {"hierarchy": "kd_sah", "leaf_size": 4}):
     eng = lb.FastWindingNumber(V, F, **kw)
     o, s, d = prim.lattice_for_bbox(*prim.mesh_bbox(V), (50, 17, 45))
     a = eng.query_grid(o, s, d, want_omega=True)[0]
