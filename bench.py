@@ -191,9 +191,9 @@ def run_reference(args):
 
 def profile_traffic():
     """DRAM bytes (read + write) per launch of the dominant kernel, k_tile_query, from the committed `ncu --set full` summary
-    (profiles/r1n_tile_plan_query_ncu_full.txt: one launch = 131072 tiles = 67.1 M queries). The tree (158 MB with 4-triangle leaves) is part of it:
+    (profiles/r1q_tile_plan_query_ncu_full.txt: one launch = 131072 tiles = 67.1 M queries). The tree (158 MB with 4-triangle leaves) is part of it:
     every launch streams the records it touches from HBM once; the algorithmic output is 1 byte per query."""
-    path = os.path.join(ROOT, "profiles", "r1n_tile_plan_query_ncu_full.txt")
+    path = os.path.join(ROOT, "profiles", "r1q_tile_plan_query_ncu_full.txt")
     try:
         rd = wr = None
         in_query = False
@@ -205,7 +205,7 @@ def profile_traffic():
             elif in_query and ln.startswith("dram__bytes_write.sum "):
                 wr = float(ln.split()[-1]) * 1e6
         return None if rd is None or wr is None else {"bytes_per_launch": rd + wr, "queries_per_launch": 131072 * 512,
-                                                      "source": "profiles/r1n_tile_plan_query_ncu_full.txt (k_tile_query)"}
+                                                      "source": "profiles/r1q_tile_plan_query_ncu_full.txt (k_tile_query)"}
     except Exception:
         return None
 
