@@ -51,7 +51,9 @@ static inline unsigned wn_host_atomic_max_u(unsigned* p, unsigned v)
 // ---- k-d hierarchy with SAH-guided split positions (K3'', wn_kd.cuh): explicit node ranges, level by level ---------------
 // A node is a range [start, start + n) of the current triangle order. Internal nodes are numbered by the gap they split
 // (start + nl - 1), with the root's gap and gap 0 swapped so that the root is node 0.
-#define WN_KDX_MIN_SAH 16 /* ranges shorter than this are split at the median */
+#ifndef WN_KDX_MIN_SAH
+#define WN_KDX_MIN_SAH 8 /* ranges shorter than this are split at the median (measured on cfg2: 8 -> 6.25, 16 -> 6.20, 64 -> 6.17 G q/s) */
+#endif
 
 WN_HD int wn_kdx_gap_id(int gap, int root_gap)
 {
