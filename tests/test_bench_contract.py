@@ -1,0 +1,32 @@
+"""bench.py's contract, as far as it can be checked without a GPU: the reference arm (the oracle restatement on the host cores)
+prints one JSON line with the agreed keys, and the roofline traffic is read from the committed ncu summary."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_the_agreed_json_line():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--grid", "32", "--subdiv", "2", "--steps", "1",
+                        "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "winding queries/sec" and line["unit"] == "Gqueries/s"
+    assert line["higher_is_better"] is True and line["n_gpus"] == 1 and line["steps"] == 1 and line["warmup"] == 1
+    assert line["value"] > 0 and line["ms_per_step"] > 0 and line["vs_baseline"] is None
+    assert "workload" in line["config"] and "model" not in line["config"]
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_roofline_traffic_comes_from_the_committed_profile():
+    sys.path.insert(0, ROOT)
+    import bench
+
+    t = bench.profile_traffic()
+    assert t is not None and os.path.exists(os.path.join(ROOT, t["source"].split(" ")[0]))
+    assert t["queries_per_launch"] == 131072 * 512
+    assert 1e8 < t["bytes_per_launch"] < 1e9  # a few bytes per query: the tree once per launch plus the output
