@@ -58,8 +58,8 @@ typedef enum wn_hierarchy {
     WN_HIERARCHY_LBVH = 0, /* Morton codes + one radix sort + Karras 2012: fastest build (1.9 ms for 1.3 M triangles) */
     WN_HIERARCHY_KD = 1,   /* balanced k-d: object-median splits along the longest centroid axis, one radix sort per
                               level: compact equal-count patches, ~13 % faster queries, ~4 ms more build time */
-    WN_HIERARCHY_KD_SAH = 2 /* k-d with the split position chosen by the surface-area heuristic among the seven
-                              "first k eighths | rest" cuts of the sorted range (explicit node ranges, a few ms more) */
+    WN_HIERARCHY_KD_SAH = 2 /* k-d with the split position chosen by the surface-area heuristic among the boundaries of 16
+                              equal-width bins along the axis (the reference builder's rule): fastest queries, ~11 ms build */
 } wn_hierarchy;
 
 typedef struct wn_options {

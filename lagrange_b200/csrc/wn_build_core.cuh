@@ -52,7 +52,7 @@ static inline unsigned wn_host_atomic_max_u(unsigned* p, unsigned v)
 // A node is a range [start, start + n) of the current triangle order. Internal nodes are numbered by the gap they split
 // (start + nl - 1), with the root's gap and gap 0 swapped so that the root is node 0.
 #ifndef WN_KDX_MIN_SAH
-#define WN_KDX_MIN_SAH 8 /* ranges shorter than this are split at the median (measured on cfg2: 8 -> 6.25, 16 -> 6.20, 64 -> 6.17 G q/s) */
+#define WN_KDX_MIN_SAH 8 /* ranges shorter than this are split at the median (measured on cfg2 with the count-eighths rule: 8 -> 6.25, 16 -> 6.20, 64 -> 6.17 G q/s) */
 #endif
 
 WN_HD int wn_kdx_gap_id(int gap, int root_gap)
@@ -67,35 +67,71 @@ WN_HD float wn_kdx_half_area(const float* lo, const float* hi)
     return WN_ADD(WN_ADD(WN_MUL(dx, dy), WN_MUL(dy, dz)), WN_MUL(dz, dx));
 }
 
-// Left count of a range of n >= WN_KDX_MIN_SAH triangles sorted along its axis, from the boxes of its 8 equal segments
-// (seg[k*6 + 0..2] = min, + 3..5 = max; element i of the range belongs to segment (8 i) / n): the candidate "first k
-// segments | rest" with the least  area(left) * n_left + area(right) * n_right;  ties keep the candidate nearest the median.
-WN_HD int wn_kdx_choose(int n, const float* seg)
+// How likely a node with this box is opened by a query. WN_KDX_COST = 0: half the surface area (the ray-tracing SAH);
+// 1: diagonal cubed, 2: diagonal squared (the acceptance sphere of a record has radius beta * R with R ~ half the diagonal, and
+// point queries that fill a volume open the node in proportion to that sphere's volume).
+#ifndef WN_KDX_COST
+#define WN_KDX_COST 0
+#endif
+WN_HD float wn_kdx_measure(const float* lo, const float* hi)
 {
-    float plo[8][3], phi[8][3], slo[8][3], shi[8][3]; // prefix boxes of segments 0..k, suffix boxes of segments k..7
-    for (int k = 0; k < 8; ++k)
+#if WN_KDX_COST == 0
+    return wn_kdx_half_area(lo, hi);
+#else
+    if (!(hi[0] >= lo[0]) || !(hi[1] >= lo[1]) || !(hi[2] >= lo[2])) return 0.0f;
+    const float dx = WN_SUB(hi[0], lo[0]), dy = WN_SUB(hi[1], lo[1]), dz = WN_SUB(hi[2], lo[2]);
+    const float d2 = WN_ADD(WN_ADD(WN_MUL(dx, dx), WN_MUL(dy, dy)), WN_MUL(dz, dz));
+#if WN_KDX_COST == 1
+    return WN_MUL(d2, WN_SQRT(d2));
+#elif WN_KDX_COST == 3
+    return WN_MUL(d2, d2);
+#elif WN_KDX_COST == 4
+    { const float ar = WN_ADD(WN_ADD(WN_MUL(dx, dy), WN_MUL(dy, dz)), WN_MUL(dz, dx)); return WN_MUL(ar, WN_SQRT(ar)); }
+#else
+    return d2;
+#endif
+#endif
+}
+
+// Bins of equal WIDTH along the split axis of a range (the reference builder's rule, SURVEY.md A.6: "16 bins along the longest
+// axis of the centre bounds"); q16 is the 16-bit position of a centroid inside the range's centroid bounds (wn_kd_quant).
+#define WN_KDX_BINS 16
+#define WN_KDX_ROW (WN_KDX_BINS * 7) /* ints per range in the bin table: BINS boxes (min xyz, max xyz) + BINS counts */
+WN_HD int wn_kdx_bin(unsigned q16)
+{
+    const int b = (int)((q16 * (unsigned)WN_KDX_BINS) >> 16);
+    return b < WN_KDX_BINS ? b : WN_KDX_BINS - 1;
+}
+
+// Left count of a range of n >= WN_KDX_MIN_SAH triangles sorted along its axis, from the triangle boxes (box[k*6 + 0..2] = min,
+// + 3..5 = max) and centroid counts of its bins: the cut at a bin boundary with the least
+//   measure(left) * n_left + measure(right) * n_right,
+// both sides holding at least n/8 triangles (bounds the depth like the eighths did); the first such cut on ties, the median
+// if no boundary qualifies (all centroids in one bin).
+WN_HD int wn_kdx_choose(int n, const float* box, const int* cnt)
+{
+    float slo[WN_KDX_BINS][3], shi[WN_KDX_BINS][3]; // boxes of bins k..BINS-1
+    for (int k = WN_KDX_BINS - 1; k >= 0; --k)
         for (int a = 0; a < 3; ++a) {
-            const float l = seg[k * 6 + a], h = seg[k * 6 + 3 + a];
-            plo[k][a] = k == 0 ? l : wn_min(plo[k - 1][a], l);
-            phi[k][a] = k == 0 ? h : wn_max(phi[k - 1][a], h);
+            const float l = box[k * 6 + a], h = box[k * 6 + 3 + a];
+            slo[k][a] = k == WN_KDX_BINS - 1 ? l : wn_min(slo[k + 1][a], l);
+            shi[k][a] = k == WN_KDX_BINS - 1 ? h : wn_max(shi[k + 1][a], h);
         }
-    for (int k = 7; k >= 0; --k)
-        for (int a = 0; a < 3; ++a) {
-            const float l = seg[k * 6 + a], h = seg[k * 6 + 3 + a];
-            slo[k][a] = k == 7 ? l : wn_min(slo[k + 1][a], l);
-            shi[k][a] = k == 7 ? h : wn_max(shi[k + 1][a], h);
-        }
-    const int order[7] = {4, 3, 5, 2, 6, 1, 7};
-    int best_nl = n / 2;
+    float pl[3] = {3.4e38f, 3.4e38f, 3.4e38f}, ph[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+    const int gmin = n / 8 > 1 ? n / 8 : 1;
+    int best_nl = n / 2, pre = 0;
     float best = 3.4e38f;
-    for (int c = 0; c < 7; ++c) {
-        const int k = order[c];
-        const int nl = (int)(((long long)k * n + 7) / 8); // elements of segments 0..k-1
-        if (nl < 1 || nl > n - 1) continue;
-        const float cost = WN_ADD(WN_MUL(wn_kdx_half_area(plo[k - 1], phi[k - 1]), (float)nl), WN_MUL(wn_kdx_half_area(slo[k], shi[k]), (float)(n - nl)));
+    for (int k = 1; k < WN_KDX_BINS; ++k) {
+        for (int a = 0; a < 3; ++a) {
+            pl[a] = wn_min(pl[a], box[(k - 1) * 6 + a]);
+            ph[a] = wn_max(ph[a], box[(k - 1) * 6 + 3 + a]);
+        }
+        pre += cnt[k - 1];
+        if (pre < gmin || n - pre < gmin) continue;
+        const float cost = WN_ADD(WN_MUL(wn_kdx_measure(pl, ph), (float)pre), WN_MUL(wn_kdx_measure(slo[k], shi[k]), (float)(n - pre)));
         if (cost < best) {
             best = cost;
-            best_nl = nl;
+            best_nl = pre;
         }
     }
     return best_nl;

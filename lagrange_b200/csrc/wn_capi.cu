@@ -481,7 +481,7 @@ wn_status create_impl(const float* v_xyz, int64_t nV, const int32_t* tri, int64_
                 for (int r = 0; r < 2; ++r) add((size_t)(nT + 1) * 4), add((size_t)nT * 4), add((size_t)nT);
                 add((size_t)nT * 4), add((size_t)nT * 4), add((size_t)nT * 4);
                 add((size_t)wn::scan_scratch_elems(nT) * 4 + 256);
-                add(((size_t)nT / WN_KDX_MIN_SAH + 1) * 48 * 4);
+                add(((size_t)nT / WN_KDX_MIN_SAH + 1) * WN_KDX_ROW * 4);
                 add(64);
             }
         } else {
@@ -579,7 +579,7 @@ wn_status create_impl(const float* v_xyz, int64_t nV, const int32_t* tri, int64_
             WN_CUDA_C(dalloc((void**)&d_cnt, (size_t)nT * 4));
             WN_CUDA_C(dalloc((void**)&d_scan, (size_t)wn::scan_scratch_elems(nT) * 4 + 256));
             const int64_t seg_rows = nT / WN_KDX_MIN_SAH + 1;
-            WN_CUDA_C(dalloc((void**)&d_segbox, (size_t)seg_rows * 48 * 4));
+            WN_CUDA_C(dalloc((void**)&d_segbox, (size_t)seg_rows * WN_KDX_ROW * 4));
             WN_CUDA_C(dalloc((void**)&d_res, 64));
             wn::k_iota<<<wn::grid_for(nT), wn::kBuildThreads, 0, st>>>(v0, N);
             WN_CUDA_C(cudaMemsetAsync(node_of, 0, (size_t)nT * 4, st));
@@ -607,8 +607,8 @@ wn_status create_impl(const float* v_xyz, int64_t nV, const int32_t* tri, int64_
                 const int which = wn::radix_sort_pairs<uint64_t>(k0, cur, k1, other, nT, 0, 16 + nbits, sort_scratch, st);
                 if (which) std::swap(cur, other);
                 if (max_range >= WN_KDX_MIN_SAH && max_range > leaf) { // otherwise every split of this level is a median split
-                    wn::k_kdx_init_segbox_nodes<<<wn::grid_for((int64_t)count * 48), wn::kBuildThreads, 0, st>>>(lstart[r], count, leaf, d_segbox);
-                    wn::k_kdx_segboxes<<<wn::grid_for(nT), wn::kBuildThreads, 0, st>>>(d_v, d_tri, cur, node_of, N, lstart[r], leaf, d_segbox);
+                    wn::k_kdx_init_segbox_nodes<<<wn::grid_for((int64_t)count * WN_KDX_ROW), wn::kBuildThreads, 0, st>>>(lstart[r], count, leaf, d_segbox);
+                    wn::k_kdx_segboxes<<<wn::grid_for(nT), wn::kBuildThreads, 0, st>>>(d_v, d_tri, cur, node_of, N, lstart[r], leaf, d_bounds, d_segbox);
                 }
                 WN_CUDA_C(cudaMemsetAsync(d_res, 0, 2 * sizeof(int), st));
                 WN_CUDA_C(cudaMemsetAsync(d_res + 3, 0, sizeof(int), st));

@@ -120,8 +120,8 @@ __global__ void __launch_bounds__(kBuildThreads) k_kd_tree(int N, int* __restric
 }
 
 // ---- K3'': SAH-guided split positions (WN_HIERARCHY_KD_SAH). Same idea as K3', but a range sorted along its axis is cut
-//      where  area(left) n_left + area(right) n_right  is least among the seven "first k eighths | rest" candidates (exact
-//      triangle boxes of the eight segments), so node ranges are explicit: per level, arrays over the nodes in position order.
+//      where  area(left) n_left + area(right) n_right  is least among the boundaries of 16 bins of equal width along its axis
+//      (exact triangle boxes and centroid counts per bin, the reference builder's rule), so node ranges are explicit: per level, arrays over the nodes in position order.
 struct KdxLevel
 {
     const unsigned* start; // [count + 1], start[count] = N
@@ -198,23 +198,35 @@ __global__ void __launch_bounds__(kBuildThreads) k_kdx_keys(const float* __restr
     keys[p] = ((uint64_t)i << 16) | q;
 }
 
-// boxes of the eight segments of every range with at least WN_KDX_MIN_SAH triangles; segbox row = start / WN_KDX_MIN_SAH.
-// Consecutive positions mostly share (range, segment): a warp whose lanes all hit the same row reduces first and issues one
-// set of atomics (near the root every warp does; without this the root's 48 addresses take 1.3 M atomics each level).
+// Bin table of every range with at least WN_KDX_MIN_SAH triangles: triangle boxes and centroid counts of WN_KDX_BINS bins of
+// equal width along the range's split axis; row = start / WN_KDX_MIN_SAH, WN_KDX_ROW ints per row. Consecutive positions are
+// sorted along that axis, so a warp mostly hits one (row, bin): it reduces first and issues one set of atomics (near the root
+// every warp does; without this the root's few addresses would take 1.3 M atomics each).
 __global__ void __launch_bounds__(kBuildThreads) k_kdx_segboxes(const float* __restrict__ v, const int* __restrict__ tri,
                                                                 const unsigned* __restrict__ perm, const unsigned* __restrict__ node_of, int N,
-                                                                const unsigned* __restrict__ start, int leaf, int* __restrict__ segbox)
+                                                                const unsigned* __restrict__ start, int leaf, const int* __restrict__ bounds,
+                                                                int* __restrict__ segbox)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    long long rowid = -1;
+    long long slot = -1; // row * BINS + bin
     int enc[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
     if (p < N) {
         const unsigned i = node_of[p];
         const int s = (int)start[i], n = (int)(start[i + 1] - start[i]);
         if (n > leaf && n >= WN_KDX_MIN_SAH) {
-            const int seg = (int)(((long long)(p - s) * 8) / n);
-            rowid = (long long)(s / WN_KDX_MIN_SAH) * 8 + seg;
+            const int* b = bounds + 6 * (size_t)i;
+            float blo[3], ext[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                blo[a] = ordered_to_float(b[a]);
+                ext[a] = b[3 + a] >= b[a] ? WN_SUB(ordered_to_float(b[3 + a]), blo[a]) : 0.0f;
+            }
+            const int axis = wn_kd_axis(ext);
             const unsigned t = perm[p];
+            float c[3];
+            kd_centroid(v, tri, t, c);
+            const int bin = wn_kdx_bin(wn_kd_quant(c[axis], blo[axis], ext[axis]));
+            slot = (long long)(s / WN_KDX_MIN_SAH) * WN_KDX_BINS + bin;
             const int i0 = tri[3 * t], i1 = tri[3 * t + 1], i2 = tri[3 * t + 2];
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
@@ -225,36 +237,41 @@ __global__ void __launch_bounds__(kBuildThreads) k_kdx_segboxes(const float* __r
             }
         }
     }
-    const unsigned same = __match_any_sync(0xffffffffu, rowid);
+    int add = 1;
+    const unsigned same = __match_any_sync(0xffffffffu, slot);
     if (same == 0xffffffffu) {
-        if (rowid < 0) return;
+        if (slot < 0) return;
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
             enc[a] = __reduce_min_sync(0xffffffffu, enc[a]);
             enc[3 + a] = __reduce_max_sync(0xffffffffu, enc[3 + a]);
         }
         if ((threadIdx.x & 31) != 0) return;
-    } else if (rowid < 0) {
+        add = 32;
+    } else if (slot < 0) {
         return;
     }
-    int* row = segbox + (size_t)rowid * 6;
+    const long long row = slot / WN_KDX_BINS;
+    const int bin = (int)(slot % WN_KDX_BINS);
+    int* r = segbox + (size_t)row * WN_KDX_ROW;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        if (enc[a] != INT_MAX) atomicMin(&row[a], enc[a]);
-        if (enc[3 + a] != INT_MIN) atomicMax(&row[3 + a], enc[3 + a]);
+        if (enc[a] != INT_MAX) atomicMin(&r[bin * 6 + a], enc[a]);
+        if (enc[3 + a] != INT_MIN) atomicMax(&r[bin * 6 + 3 + a], enc[3 + a]);
     }
+    atomicAdd(&r[WN_KDX_BINS * 6 + bin], add);
 }
 
-// sentinels for the segment boxes of the ranges that will be measured at this level (one thread per node and value)
+// empty bin table for the ranges that will be measured at this level (one thread per range and value)
 __global__ void __launch_bounds__(kBuildThreads) k_kdx_init_segbox_nodes(const unsigned* __restrict__ start, int count, int leaf,
                                                                          int* __restrict__ segbox)
 {
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = (int)(g / 48), k = (int)(g % 48);
+    const int i = (int)(g / WN_KDX_ROW), k = (int)(g % WN_KDX_ROW);
     if (i >= count) return;
     const int s = (int)start[i], n = (int)(start[i + 1] - start[i]);
     if (n <= leaf || n < WN_KDX_MIN_SAH) return;
-    segbox[(size_t)(s / WN_KDX_MIN_SAH) * 48 + k] = (k % 6) < 3 ? INT_MAX : INT_MIN;
+    segbox[(size_t)(s / WN_KDX_MIN_SAH) * WN_KDX_ROW + k] = k >= WN_KDX_BINS * 6 ? 0 : ((k % 6) < 3 ? INT_MAX : INT_MIN);
 }
 
 // one thread per node: left count (0 = not split at this level), children count for the scan, bookkeeping in res[]:
@@ -269,12 +286,13 @@ __global__ void __launch_bounds__(kBuildThreads) k_kdx_split(KdxLevel L, int N, 
     if (n > leaf) {
         left = n / 2;
         if (n >= WN_KDX_MIN_SAH) {
-            float seg[48];
-            const int* row = segbox + (size_t)(s / WN_KDX_MIN_SAH) * 48;
-#pragma unroll
-            for (int k = 0; k < 48; ++k) // untouched sentinels decode to an empty box, like the host emulation's
-                seg[k] = row[k] == INT_MAX ? 3.4e38f : (row[k] == INT_MIN ? -3.4e38f : ordered_to_float(row[k]));
-            left = wn_kdx_choose(n, seg);
+            float box[WN_KDX_BINS * 6];
+            int bcnt[WN_KDX_BINS];
+            const int* row = segbox + (size_t)(s / WN_KDX_MIN_SAH) * WN_KDX_ROW;
+            for (int k = 0; k < WN_KDX_BINS * 6; ++k) // untouched sentinels decode to an empty box, like the host emulation's
+                box[k] = row[k] == INT_MAX ? 3.4e38f : (row[k] == INT_MIN ? -3.4e38f : ordered_to_float(row[k]));
+            for (int k = 0; k < WN_KDX_BINS; ++k) bcnt[k] = row[WN_KDX_BINS * 6 + k];
+            left = wn_kdx_choose(n, box, bcnt);
         }
         atomicAdd(&res[0], 1);
         atomicMax(&res[3], max(left, n - left)); // largest range of the next level: the host skips the SAH passes below the threshold

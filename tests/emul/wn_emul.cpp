@@ -4,6 +4,7 @@
 // the folded far-field records against the oracle without a GPU. Never linked into the product.
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <numeric>
@@ -125,23 +126,27 @@ void* emul_build(const float* v, int64_t nV, const int32_t* tri, int64_t nT, con
                     if (n > leaf) {
                         left = n / 2;
                         if (n >= WN_KDX_MIN_SAH) {
-                            float seg[48];
-                            for (int k = 0; k < 8; ++k)
-                                for (int a = 0; a < 3; ++a) seg[k * 6 + a] = 3.4e38f, seg[k * 6 + 3 + a] = -3.4e38f;
-                            bool any_lo[48] = {false};
+                            float ext3[3];
+                            for (int a = 0; a < 3; ++a) ext3[a] = nhi[3 * (size_t)i + a] >= nlo[3 * (size_t)i + a] ? nhi[3 * (size_t)i + a] - nlo[3 * (size_t)i + a] : 0.0f;
+                            const int axis = wn_kd_axis(ext3);
+                            float box[WN_KDX_BINS * 6];
+                            int bcnt[WN_KDX_BINS];
+                            for (int k = 0; k < WN_KDX_BINS; ++k) {
+                                bcnt[k] = 0;
+                                for (int a = 0; a < 3; ++a) box[k * 6 + a] = 3.4e38f, box[k * 6 + 3 + a] = -3.4e38f;
+                            }
                             for (int j = 0; j < n; ++j) {
-                                const int sgm = (int)(((long long)j * 8) / n);
                                 const unsigned t = perm[s0 + j];
+                                const int bin = wn_kdx_bin(wn_kd_quant(cen[3 * (size_t)t + axis], nlo[3 * (size_t)i + axis], ext3[axis]));
+                                ++bcnt[bin];
                                 for (int a = 0; a < 3; ++a) {
                                     const float x0 = v[3 * tri[3 * t] + a], x1 = v[3 * tri[3 * t + 1] + a], x2 = v[3 * tri[3 * t + 2] + a];
                                     const float lo2 = fminf(x0, fminf(x1, x2)), hi2 = fmaxf(x0, fmaxf(x1, x2));
-                                    if (lo2 == lo2) seg[sgm * 6 + a] = std::min(seg[sgm * 6 + a], lo2), any_lo[sgm * 6 + a] = true;
-                                    if (hi2 == hi2) seg[sgm * 6 + 3 + a] = std::max(seg[sgm * 6 + 3 + a], hi2), any_lo[sgm * 6 + 3 + a] = true;
+                                    if (lo2 == lo2) box[bin * 6 + a] = std::min(box[bin * 6 + a], lo2);
+                                    if (hi2 == hi2) box[bin * 6 + 3 + a] = std::max(box[bin * 6 + 3 + a], hi2);
                                 }
                             }
-                            // the device decodes untouched ordered-int sentinels (INT_MAX / INT_MIN) to NaN-like floats; an empty side is
-                            // an empty box either way (wn_kdx_half_area returns 0 when hi >= lo fails)
-                            left = wn_kdx_choose(n, seg);
+                            left = wn_kdx_choose(n, box, bcnt);
                         }
                         ++n_split;
                     }
@@ -407,6 +412,125 @@ void emul_query(void* h, const float* q, int64_t n, float beta, float* out, uint
         counters[1] = cnt[1];
         counters[2] = cnt[2];
     }
+}
+
+// Cost model of the tiled query path (k_tile_plan + k_tile_query) on this packed tree, evaluated on the host for every
+// `tile_stride`-th 8x8x8 tile of a lattice: the same classification rules as the plan kernel (tile bounding sphere, far set /
+// direct / dropped / conditional) and the same warp-level walk as warp_traverse<2, ., true> (a 4x4x4 sub-block per warp, two
+// groups of 32 points, per-point resume index, the warp visits an item when any point needs it). Counts what determines the
+// kernels' instruction counts; it lets hierarchy variants be compared without a GPU (tests/tools/hierarchy_cost.py).
+// out[0] tiles, [1] conditional walk steps (per warp, summed), [2] evaluations executed (per 32-point group), [3] far-set
+// records, [4] direct records, [5] conditional items (plan list length), [6] exact triangle evaluations (per group), [7] warps
+void emul_tile_cost(void* h, const float* origin, const float* spacing, const int64_t* dims, int tile_stride, float beta, float kappa,
+                    double* out)
+{
+    Emul* e = static_cast<Emul*>(h);
+    const WnTreeView& t = e->view;
+    const int n = t.n_entries;
+    const float beta2 = beta * beta;
+    for (int k = 0; k < 8; ++k) out[k] = 0.0;
+    if (n == 0) return;
+    const int tx = (int)((dims[0] + 7) / 8), ty = (int)((dims[1] + 7) / 8), tz = (int)((dims[2] + 7) / 8);
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma omp parallel for collapse(2) schedule(dynamic, 4) reduction(+ : acc[:8])
+    for (int bz = 0; bz < tz; bz += tile_stride)
+        for (int by = 0; by < ty; by += tile_stride)
+            for (int bx = 0; bx < tx; bx += tile_stride) {
+                // tile sphere, as in k_tile_plan
+                float lo[3], hi[3];
+                const int b3[3] = {bx, by, bz};
+                for (int a = 0; a < 3; ++a) {
+                    const float l = wn_lattice_coord(origin[a], spacing[a], b3[a] * 8), u = wn_lattice_coord(origin[a], spacing[a], b3[a] * 8 + 7);
+                    lo[a] = std::min(l, u);
+                    hi[a] = std::max(l, u);
+                }
+                float c[3], r2 = 0.0f;
+                for (int a = 0; a < 3; ++a) {
+                    c[a] = 0.5f * (lo[a] + hi[a]);
+                    const float hh = 0.5f * (hi[a] - lo[a]);
+                    r2 += hh * hh;
+                }
+                const float ra = sqrtf(r2) * 1.0001f + 1e-30f;
+                acc[0] += 1;
+                for (int sub = 0; sub < 8; ++sub) {
+                    float qx[64], qy[64], qz[64];
+                    int skip[64];
+                    for (int p = 0; p < 64; ++p) {
+                        const int lx = p & 3, ly = (p >> 2) & 3, lz = p >> 4; // lz 0..3: groups k = lz >> 1
+                        qx[p] = wn_lattice_coord(origin[0], spacing[0], bx * 8 + (sub & 1) * 4 + lx);
+                        qy[p] = wn_lattice_coord(origin[1], spacing[1], by * 8 + ((sub >> 1) & 1) * 4 + ly);
+                        qz[p] = wn_lattice_coord(origin[2], spacing[2], bz * 8 + (sub >> 2) * 4 + lz);
+                        skip[p] = 0;
+                    }
+                    acc[7] += 1;
+                    int i = n > 1 ? 1 : 0, mixed_until = 0;
+                    while (i < n) {
+                        const float4 f0 = t.hot[2 * (int64_t)i], f1 = t.hot[2 * (int64_t)i + 1];
+                        const bool leaf = wn_float_as_int(f0.w) < 0;
+                        const int lk = wn_float_as_int(f1.w);
+                        const int after = leaf ? i + 1 : lk;
+                        const float thr = fabsf(f0.w) * beta2;
+                        const float dx = c[0] - f0.x, dy = c[1] - f0.y, dz = c[2] - f0.z;
+                        const float D = sqrtf(dx * dx + dy * dy + dz * dz);
+                        const float dm = D - ra, dp = D + ra;
+                        const bool allfar = dm > 0.0f && dm * dm > thr * 1.0001f;
+                        const bool allnear = dp * dp <= thr * 0.9999f;
+                        const bool in_mixed = i < mixed_until;
+                        if (!in_mixed && allfar) {
+                            if (sub == 0) {
+                                if (D >= kappa * ra && D - sqrtf(fabsf(f0.w)) >= 0.5f * kappa * ra)
+                                    acc[3] += 1;
+                                else
+                                    acc[4] += 1;
+                            }
+                            i = after;
+                            continue;
+                        }
+                        if (allnear && !leaf) { // dropped: children expanded
+                            i = i + 1;
+                            continue;
+                        }
+                        if (!in_mixed && allnear && leaf) { // exact for everybody, no test
+                            const int count = (lk & (WN_MAX_LEAF_SIZE - 1)) + 1;
+                            acc[6] += 2.0 * count;
+                            i = i + 1;
+                            continue;
+                        }
+                        if (!in_mixed && !leaf) mixed_until = lk;
+                        if (sub == 0) acc[5] += 1; // (an under-count for items only other sub-blocks reach; fine for a model)
+                        bool any_active = false, anyfar[2] = {false, false}, anynear_k[2] = {false, false};
+                        for (int p = 0; p < 64; ++p) {
+                            if (i < skip[p]) continue;
+                            any_active = true;
+                            const float rx = qx[p] - f0.x, ry = qy[p] - f0.y, rz = qz[p] - f0.z;
+                            const float l2 = rx * rx + ry * ry + rz * rz;
+                            const bool nr = allfar ? false : (l2 <= thr);
+                            const int k = p >> 5;
+                            if (nr) {
+                                anynear_k[k] = true;
+                            } else {
+                                anyfar[k] = true;
+                                skip[p] = after;
+                            }
+                        }
+                        // the real warp only visits the item if some lane is active: when none is, it jumped past it earlier
+                        if (!any_active) {
+                            i = after;
+                            continue;
+                        }
+                        acc[1] += 1;
+                        acc[2] += (anyfar[0] ? 1 : 0) + (anyfar[1] ? 1 : 0);
+                        const bool anynear = anynear_k[0] || anynear_k[1];
+                        if (leaf) {
+                            if (anynear) acc[6] += ((anynear_k[0] ? 1 : 0) + (anynear_k[1] ? 1 : 0)) * ((lk & (WN_MAX_LEAF_SIZE - 1)) + 1);
+                            i = i + 1;
+                        } else {
+                            i = anynear ? i + 1 : after;
+                        }
+                    }
+                }
+            }
+    for (int k = 0; k < 8; ++k) out[k] = acc[k];
 }
 
 int emul_inside_from_omega(float omega)
