@@ -96,6 +96,51 @@ void* emul_build(const float* v, int64_t nV, const int32_t* tri, int64_t nT, con
                             nhi[3 * (size_t)i + a] = std::max(nhi[3 * (size_t)i + a], c[a]);
                         }
                 }
+                // RESEARCH VARIANT (host only, WN_EMUL_AXES=3): bins on all three axes, the axis with the cheapest cut wins
+                static const bool kAllAxes = getenv("WN_EMUL_AXES") && atoi(getenv("WN_EMUL_AXES")) == 3;
+                std::vector<int> forced_axis(count, -1), forced_left(count, 0);
+                if (kAllAxes) {
+                    for (int i = 0; i < count; ++i) {
+                        const int s0 = (int)start[i], n = (int)(start[i + 1] - start[i]);
+                        if (n <= leaf || n < WN_KDX_MIN_SAH) continue;
+                        float ext3[3];
+                        for (int a = 0; a < 3; ++a) ext3[a] = nhi[3 * (size_t)i + a] >= nlo[3 * (size_t)i + a] ? nhi[3 * (size_t)i + a] - nlo[3 * (size_t)i + a] : 0.0f;
+                        float best_cost = 3.4e38f;
+                        for (int axis = 0; axis < 3; ++axis) {
+                            if (!(ext3[axis] > 0.0f)) continue;
+                            float box[WN_KDX_BINS * 6];
+                            int bcnt[WN_KDX_BINS];
+                            for (int k = 0; k < WN_KDX_BINS; ++k) {
+                                bcnt[k] = 0;
+                                for (int a = 0; a < 3; ++a) box[k * 6 + a] = 3.4e38f, box[k * 6 + 3 + a] = -3.4e38f;
+                            }
+                            for (int j = 0; j < n; ++j) {
+                                const unsigned t = perm[s0 + j];
+                                const int bin = wn_kdx_bin(wn_kd_quant(cen[3 * (size_t)t + axis], nlo[3 * (size_t)i + axis], ext3[axis]));
+                                ++bcnt[bin];
+                                for (int a = 0; a < 3; ++a) {
+                                    const float x0 = v[3 * tri[3 * t] + a], x1 = v[3 * tri[3 * t + 1] + a], x2 = v[3 * tri[3 * t + 2] + a];
+                                    box[bin * 6 + a] = std::min(box[bin * 6 + a], fminf(x0, fminf(x1, x2)));
+                                    box[bin * 6 + 3 + a] = std::max(box[bin * 6 + 3 + a], fmaxf(x0, fmaxf(x1, x2)));
+                                }
+                            }
+                            const int nl2 = wn_kdx_choose(n, box, bcnt);
+                            // cost of that cut (recomputed: wn_kdx_choose returns the count only)
+                            float pl[3] = {3.4e38f, 3.4e38f, 3.4e38f}, ph[3] = {-3.4e38f, -3.4e38f, -3.4e38f}, sl[3] = {3.4e38f, 3.4e38f, 3.4e38f},
+                                  sh[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+                            int pre = 0, k = 0;
+                            for (; k < WN_KDX_BINS && pre < nl2; ++k) {
+                                pre += bcnt[k];
+                                for (int a = 0; a < 3; ++a) pl[a] = std::min(pl[a], box[k * 6 + a]), ph[a] = std::max(ph[a], box[k * 6 + 3 + a]);
+                            }
+                            if (pre != nl2) continue; // the median fallback: not a bin boundary, skip this axis
+                            for (; k < WN_KDX_BINS; ++k)
+                                for (int a = 0; a < 3; ++a) sl[a] = std::min(sl[a], box[k * 6 + a]), sh[a] = std::max(sh[a], box[k * 6 + 3 + a]);
+                            const float cost = wn_kdx_measure(pl, ph) * nl2 + wn_kdx_measure(sl, sh) * (n - nl2);
+                            if (cost < best_cost) best_cost = cost, forced_axis[i] = axis, forced_left[i] = nl2;
+                        }
+                    }
+                }
                 std::vector<uint64_t> key(nT);
                 for (int p = 0; p < N; ++p) {
                     const unsigned i = node_of[p];
@@ -103,7 +148,7 @@ void* emul_build(const float* v, int64_t nV, const int32_t* tri, int64_t nT, con
                     if ((int)(start[i + 1] - start[i]) > leaf) {
                         float ext3[3];
                         for (int a = 0; a < 3; ++a) ext3[a] = nhi[3 * (size_t)i + a] >= nlo[3 * (size_t)i + a] ? nhi[3 * (size_t)i + a] - nlo[3 * (size_t)i + a] : 0.0f;
-                        const int axis = wn_kd_axis(ext3);
+                        const int axis = forced_axis[i] >= 0 ? forced_axis[i] : wn_kd_axis(ext3);
                         q = wn_kd_quant(cen[3 * (size_t)perm[p] + axis], nlo[3 * (size_t)i + axis], ext3[axis]);
                     }
                     key[p] = ((uint64_t)i << 16) | q;
@@ -147,6 +192,7 @@ void* emul_build(const float* v, int64_t nV, const int32_t* tri, int64_t nT, con
                                 }
                             }
                             left = wn_kdx_choose(n, box, bcnt);
+                            if (forced_axis[i] >= 0) left = forced_left[i];
                         }
                         ++n_split;
                     }
@@ -309,6 +355,60 @@ void* emul_build(const float* v, int64_t nV, const int32_t* tri, int64_t nT, con
         for (int l = 0; l < b.nL; ++l) wn_climb_leaf(b, l);
         if (radius_mode == 1)
             for (int l = 0; l < b.nL; ++l) wn_vertex_radius_leaf(b, l);
+    }
+    // RESEARCH VARIANT (host only, WN_EMUL_WIDE_RULE=1; used with tests/tools/hierarchy_cost.py): choose the records that are
+    // dropped for the 4-ary packing like the reference builder forms its nodes (split in two, then split the
+    // child with the largest area * count again until there are four) instead of by depth parity. The `kids` table written by
+    // wn_pack_node is not valid for this variant (it expands one level only); the depth-first order and the skip links are.
+    if (getenv("WN_EMUL_WIDE_RULE") && atoi(getenv("WN_EMUL_WIDE_RULE")) == 1 && !child_in && hierarchy >= 1 && e->err == 0 && nT >= 2) {
+        e->skip.assign(b.nI, 0);
+        auto weight = [&](int c) {
+            const float* r = reinterpret_cast<const float*>(&e->local[(size_t)c * 9]);
+            const float dx = r[3] - r[0], dy = r[4] - r[1], dz = r[5] - r[2];
+            return (dx * dy + dy * dz + dz * dx) * (float)e->ntri[c];
+        };
+        auto expandable = [&](int c) { return c < b.nI && !e->collapsed[c]; };
+        std::vector<int> queue{0};
+        for (size_t qi = 0; qi < queue.size(); ++qi) {
+            const int X = queue[qi];
+            std::vector<int> S;
+            for (int s2 = 0; s2 < b.W; ++s2)
+                if (e->child[(size_t)X * b.W + s2] >= 0) S.push_back(e->child[(size_t)X * b.W + s2]);
+            for (int rep = 0; rep < 2 && S.size() < 4; ++rep) {
+                int bi = -1;
+                float bw = -1.0f;
+                for (size_t k = 0; k < S.size(); ++k)
+                    if (expandable(S[k]) && weight(S[k]) > bw) bw = weight(S[k]), bi = (int)k;
+                if (bi < 0) break;
+                const int c = S[bi];
+                e->skip[c] = 1;
+                S.erase(S.begin() + bi);
+                for (int s2 = 0; s2 < b.W; ++s2)
+                    if (e->child[(size_t)c * b.W + s2] >= 0) S.push_back(e->child[(size_t)c * b.W + s2]);
+            }
+            for (int c : S)
+                if (expandable(c)) queue.push_back(c);
+        }
+        b.skip = e->skip.data();
+        // sizes again, bottom-up (reverse breadth-first order over the whole binary tree)
+        std::vector<int> order{0};
+        for (size_t qi = 0; qi < order.size(); ++qi) {
+            const int X = order[qi];
+            if (X >= b.nI) continue;
+            for (int s2 = 0; s2 < b.W; ++s2)
+                if (e->child[(size_t)X * b.W + s2] >= 0) order.push_back(e->child[(size_t)X * b.W + s2]);
+        }
+        for (size_t qi = order.size(); qi-- > 0;) {
+            const int X = order[qi];
+            if (X >= b.nI || e->collapsed[X]) {
+                e->size[X] = 1;
+                continue;
+            }
+            int sz = e->skip[X] ? 0 : 1;
+            for (int s2 = 0; s2 < b.W; ++s2)
+                if (e->child[(size_t)X * b.W + s2] >= 0) sz += e->size[e->child[(size_t)X * b.W + s2]];
+            e->size[X] = sz;
+        }
     }
     const int n_entries = (e->err == 0 && nT > 0) ? e->size[0] : 0;
     e->hot.resize((size_t)n_entries * 2);
