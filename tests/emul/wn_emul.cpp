@@ -522,7 +522,7 @@ void emul_query(void* h, const float* q, int64_t n, float beta, float* out, uint
 // out[0] tiles, [1] conditional walk steps (per warp, summed), [2] evaluations executed (per 32-point group), [3] far-set
 // records, [4] direct records, [5] conditional items (plan list length), [6] exact triangle evaluations (per group), [7] warps
 void emul_tile_cost(void* h, const float* origin, const float* spacing, const int64_t* dims, int tile_stride, float beta, float kappa,
-                    double* out)
+                    const int* warp_shape /* points per warp along x, y, z: product 64, each divides 8; {4,4,4} is the kernel's */, double* out)
 {
     Emul* e = static_cast<Emul*>(h);
     const WnTreeView& t = e->view;
@@ -552,14 +552,18 @@ void emul_tile_cost(void* h, const float* origin, const float* spacing, const in
                 }
                 const float ra = sqrtf(r2) * 1.0001f + 1e-30f;
                 acc[0] += 1;
-                for (int sub = 0; sub < 8; ++sub) {
-                    float qx[64], qy[64], qz[64];
-                    int skip[64];
-                    for (int p = 0; p < 64; ++p) {
-                        const int lx = p & 3, ly = (p >> 2) & 3, lz = p >> 4; // lz 0..3: groups k = lz >> 1
-                        qx[p] = wn_lattice_coord(origin[0], spacing[0], bx * 8 + (sub & 1) * 4 + lx);
-                        qy[p] = wn_lattice_coord(origin[1], spacing[1], by * 8 + ((sub >> 1) & 1) * 4 + ly);
-                        qz[p] = wn_lattice_coord(origin[2], spacing[2], bz * 8 + (sub >> 2) * 4 + lz);
+                const int wx = warp_shape[0], wy = warp_shape[1], wz = warp_shape[2];
+                const int nsx = 8 / wx, nsy = 8 / wy, NP = wx * wy * wz, nsub = 512 / NP; // NP = 32 * (queries per lane)
+                for (int sub = 0; sub < nsub; ++sub) {
+                    float qx[256], qy[256], qz[256];
+                    int skip[256];
+                    const int sx = sub % nsx, sy = (sub / nsx) % nsy, sz = sub / (nsx * nsy);
+                    for (int p = 0; p < NP; ++p) {
+                        // x fastest, z slowest: the first 32 points (group k = 0) are the lower half along the slowest dimension
+                        const int lx = p % wx, ly = (p / wx) % wy, lz = p / (wx * wy);
+                        qx[p] = wn_lattice_coord(origin[0], spacing[0], bx * 8 + sx * wx + lx);
+                        qy[p] = wn_lattice_coord(origin[1], spacing[1], by * 8 + sy * wy + ly);
+                        qz[p] = wn_lattice_coord(origin[2], spacing[2], bz * 8 + sz * wz + lz);
                         skip[p] = 0;
                     }
                     acc[7] += 1;
@@ -592,14 +596,14 @@ void emul_tile_cost(void* h, const float* origin, const float* spacing, const in
                         }
                         if (!in_mixed && allnear && leaf) { // exact for everybody, no test
                             const int count = (lk & (WN_MAX_LEAF_SIZE - 1)) + 1;
-                            acc[6] += 2.0 * count;
+                            acc[6] += (NP / 32.0) * count;
                             i = i + 1;
                             continue;
                         }
                         if (!in_mixed && !leaf) mixed_until = lk;
                         if (sub == 0) acc[5] += 1; // (an under-count for items only other sub-blocks reach; fine for a model)
-                        bool any_active = false, anyfar[2] = {false, false}, anynear_k[2] = {false, false};
-                        for (int p = 0; p < 64; ++p) {
+                        bool any_active = false, anyfar[8] = {false}, anynear_k[8] = {false};
+                        for (int p = 0; p < NP; ++p) {
                             if (i < skip[p]) continue;
                             any_active = true;
                             const float rx = qx[p] - f0.x, ry = qy[p] - f0.y, rz = qz[p] - f0.z;
@@ -619,10 +623,15 @@ void emul_tile_cost(void* h, const float* origin, const float* spacing, const in
                             continue;
                         }
                         acc[1] += 1;
-                        acc[2] += (anyfar[0] ? 1 : 0) + (anyfar[1] ? 1 : 0);
-                        const bool anynear = anynear_k[0] || anynear_k[1];
+                        bool anynear = false;
+                        int near_groups = 0;
+                        for (int k = 0; k < NP / 32; ++k) {
+                            acc[2] += anyfar[k] ? 1 : 0;
+                            anynear = anynear || anynear_k[k];
+                            near_groups += anynear_k[k] ? 1 : 0;
+                        }
                         if (leaf) {
-                            if (anynear) acc[6] += ((anynear_k[0] ? 1 : 0) + (anynear_k[1] ? 1 : 0)) * ((lk & (WN_MAX_LEAF_SIZE - 1)) + 1);
+                            if (anynear) acc[6] += near_groups * ((lk & (WN_MAX_LEAF_SIZE - 1)) + 1);
                             i = i + 1;
                         } else {
                             i = anynear ? i + 1 : after;
