@@ -51,7 +51,7 @@ def lib():
         L.emul_inside_from_omega.restype = ctypes.c_int
         L.emul_inside_from_omega.argtypes = [ctypes.c_float]
         L.emul_tile_cost.argtypes = [ctypes.c_void_p, _f32p, _f32p, ctypes.POINTER(ctypes.c_int64), ctypes.c_int, ctypes.c_float, ctypes.c_float,
-                                     _i32p, ctypes.POINTER(ctypes.c_double)]
+                                     _i32p, _i32p, ctypes.POINTER(ctypes.c_double)]
         L.emul_point_tri_dist2.argtypes = [_f32p, _f32p, ctypes.c_int64, _f32p]
         L.emul_lattice_coord.restype = ctypes.c_float
         L.emul_lattice_coord.argtypes = [ctypes.c_float, ctypes.c_float, ctypes.c_int]
@@ -108,27 +108,30 @@ class EmulEngine:
                               order.ctypes.data_as(_u32p))
         return rec, link, tris, order
 
-    def tile_cost(self, origin, spacing, dims, tile_stride=4, beta=2.0, kappa=6.0, warp_shape=(4, 4, 4)):
+    def tile_cost(self, origin, spacing, dims, tile_stride=4, beta=2.0, kappa=6.0, warp_shape=(4, 4, 4), tile_shape=(8, 8, 8)):
         """Cost model of the tiled query path on this tree (see emul_tile_cost). Returns a dict of per-tile averages."""
         o = np.ascontiguousarray(origin, dtype=np.float32)
         s = np.ascontiguousarray(spacing, dtype=np.float32)
         d = np.ascontiguousarray(dims, dtype=np.int64)
         out = np.zeros(8, dtype=np.float64)
         ws = np.ascontiguousarray(warp_shape, dtype=np.int32)
-        assert int(np.prod(ws)) in (32, 64, 128, 256) and all(8 % int(w) == 0 for w in ws)
+        ts = np.ascontiguousarray(tile_shape, dtype=np.int32)
+        assert int(np.prod(ws)) in (32, 64, 128, 256) and all(int(t) % int(w) == 0 for t, w in zip(ts, ws))
         groups = int(np.prod(ws)) // 32
         lib().emul_tile_cost(self._h, o.ctypes.data_as(_f32p), s.ctypes.data_as(_f32p), d.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
-                             int(tile_stride), float(beta), float(kappa), ws.ctypes.data_as(_i32p), out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+                             int(tile_stride), float(beta), float(kappa), ws.ctypes.data_as(_i32p), ts.ctypes.data_as(_i32p),
+                             out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
         tiles = max(out[0], 1.0)
         names = ("tiles", "walk_steps", "evaluations", "far_set", "direct", "conditional_items", "exact_triangle_evals", "warps")
         r = {k: (v if k in ("tiles", "warps") else v / tiles) for k, v in zip(names, out)}
         # warp-instructions per tile: the measured per-step costs of k_tile_query (45 test/control + 37 per evaluation + fixed part
         # per warp) and k_tile_plan (BFS/sort/packets + far-set sampling at 2 x 37 per record and warp + list handling)
-        warps = 512 // int(np.prod(ws))
+        warps = int(np.prod(ts)) // int(np.prod(ws))
         r["query_instr"] = ((25.0 + 10.0 * groups) * r["walk_steps"] + 37.0 * r["evaluations"] + 50.0 * r["exact_triangle_evals"]
                             + warps * (37.0 * groups * r["direct"] + 150.0 + 100.0 * groups))
         r["plan_instr"] = 3000.0 + 95.0 * r["far_set"] + 12.0 * r["conditional_items"]
         r["instr_per_tile"] = r["query_instr"] + r["plan_instr"]
+        r["instr_per_point"] = r["instr_per_tile"] / float(np.prod(ts))
         return r
 
     def solid_angle(self, queries, beta=2.0, counters=False):

@@ -36,7 +36,8 @@ extern "C" {
 void* emul_build(const float* v, int64_t nV, const int32_t* tri, int64_t nT, const int32_t* child_in, int64_t num_nodes, int width,
                  int leaf_size, int order, int radius_mode, int approx_single, int morton_bits, int hierarchy)
 {
-    const bool wide = hierarchy >= 1; // the k-d hierarchies are packed 4-ary (odd-depth internal nodes get no record)
+    // the k-d hierarchies are packed 4-ary (odd-depth internal nodes get no record); WN_EMUL_WIDE=0 (host research) keeps them binary
+    const bool wide = hierarchy >= 1 && !(getenv("WN_EMUL_WIDE") && atoi(getenv("WN_EMUL_WIDE")) == 0);
     Emul* e = new Emul;
     e->v.assign(v, v + nV * 3);
     e->tri.assign(tri, tri + nT * 3);
@@ -522,7 +523,8 @@ void emul_query(void* h, const float* q, int64_t n, float beta, float* out, uint
 // out[0] tiles, [1] conditional walk steps (per warp, summed), [2] evaluations executed (per 32-point group), [3] far-set
 // records, [4] direct records, [5] conditional items (plan list length), [6] exact triangle evaluations (per group), [7] warps
 void emul_tile_cost(void* h, const float* origin, const float* spacing, const int64_t* dims, int tile_stride, float beta, float kappa,
-                    const int* warp_shape /* points per warp along x, y, z: product 64, each divides 8; {4,4,4} is the kernel's */, double* out)
+                    const int* warp_shape /* points per warp along x, y, z ({4,4,4} is the kernel's) */,
+                    const int* tile_shape /* points per tile along x, y, z ({8,8,8} is the kernel's); multiples of warp_shape */, double* out)
 {
     Emul* e = static_cast<Emul*>(h);
     const WnTreeView& t = e->view;
@@ -530,7 +532,8 @@ void emul_tile_cost(void* h, const float* origin, const float* spacing, const in
     const float beta2 = beta * beta;
     for (int k = 0; k < 8; ++k) out[k] = 0.0;
     if (n == 0) return;
-    const int tx = (int)((dims[0] + 7) / 8), ty = (int)((dims[1] + 7) / 8), tz = (int)((dims[2] + 7) / 8);
+    const int TX = tile_shape[0], TY = tile_shape[1], TZ = tile_shape[2];
+    const int tx = (int)((dims[0] + TX - 1) / TX), ty = (int)((dims[1] + TY - 1) / TY), tz = (int)((dims[2] + TZ - 1) / TZ);
     double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma omp parallel for collapse(2) schedule(dynamic, 4) reduction(+ : acc[:8])
     for (int bz = 0; bz < tz; bz += tile_stride)
@@ -538,9 +541,9 @@ void emul_tile_cost(void* h, const float* origin, const float* spacing, const in
             for (int bx = 0; bx < tx; bx += tile_stride) {
                 // tile sphere, as in k_tile_plan
                 float lo[3], hi[3];
-                const int b3[3] = {bx, by, bz};
+                const int b3[3] = {bx, by, bz}, T3[3] = {TX, TY, TZ};
                 for (int a = 0; a < 3; ++a) {
-                    const float l = wn_lattice_coord(origin[a], spacing[a], b3[a] * 8), u = wn_lattice_coord(origin[a], spacing[a], b3[a] * 8 + 7);
+                    const float l = wn_lattice_coord(origin[a], spacing[a], b3[a] * T3[a]), u = wn_lattice_coord(origin[a], spacing[a], b3[a] * T3[a] + T3[a] - 1);
                     lo[a] = std::min(l, u);
                     hi[a] = std::max(l, u);
                 }
@@ -553,7 +556,7 @@ void emul_tile_cost(void* h, const float* origin, const float* spacing, const in
                 const float ra = sqrtf(r2) * 1.0001f + 1e-30f;
                 acc[0] += 1;
                 const int wx = warp_shape[0], wy = warp_shape[1], wz = warp_shape[2];
-                const int nsx = 8 / wx, nsy = 8 / wy, NP = wx * wy * wz, nsub = 512 / NP; // NP = 32 * (queries per lane)
+                const int nsx = TX / wx, nsy = TY / wy, NP = wx * wy * wz, nsub = (TX * TY * TZ) / NP; // NP = 32 * (queries per lane)
                 for (int sub = 0; sub < nsub; ++sub) {
                     float qx[256], qy[256], qz[256];
                     int skip[256];
@@ -561,9 +564,9 @@ void emul_tile_cost(void* h, const float* origin, const float* spacing, const in
                     for (int p = 0; p < NP; ++p) {
                         // x fastest, z slowest: the first 32 points (group k = 0) are the lower half along the slowest dimension
                         const int lx = p % wx, ly = (p / wx) % wy, lz = p / (wx * wy);
-                        qx[p] = wn_lattice_coord(origin[0], spacing[0], bx * 8 + sx * wx + lx);
-                        qy[p] = wn_lattice_coord(origin[1], spacing[1], by * 8 + sy * wy + ly);
-                        qz[p] = wn_lattice_coord(origin[2], spacing[2], bz * 8 + sz * wz + lz);
+                        qx[p] = wn_lattice_coord(origin[0], spacing[0], bx * TX + sx * wx + lx);
+                        qy[p] = wn_lattice_coord(origin[1], spacing[1], by * TY + sy * wy + ly);
+                        qz[p] = wn_lattice_coord(origin[2], spacing[2], bz * TZ + sz * wz + lz);
                         skip[p] = 0;
                     }
                     acc[7] += 1;
