@@ -33,6 +33,18 @@ sys.path.insert(0, ROOT)
 
 METRIC = "winding queries/sec"
 UNIT = "Gqueries/s"
+# host threads of the CPU arm: every core this process may run on, whatever the launcher exported (torchrun sets
+# OMP_NUM_THREADS=1 for its workers, which made the round-1 reference arm single-threaded at N > 1)
+HOST_THREADS = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def config_dict(args, name, n_total):
+    """The same `config` for both arms (the driver compares them key by key)."""
+    return {"workload": name, "queries_per_step": n_total,
+            "sharding": f"tile layers (8 z-planes) round-robin over {args.gpus} rank(s), tree built on rank 0 and broadcast; CPU arm: rank 0 only",
+            "l2": "GPU arm: flushed between timed steps (256 MiB fill); CPU arm: not applicable",
+            "gpu_arm": {"leaf_size": args.leaf_size, "hierarchy": args.hierarchy, "tiled": os.environ.get("WN_TILE", "1") != "0"},
+            "cpu_arm": "oracle restatement of the reference algorithm (reference binary unbuildable here: Eigen/TBB/WindingNumber sources absent)"}
 
 
 def parse_args():
@@ -127,18 +139,18 @@ def cpu_baseline(V, F, lattice, seconds, want_build=True):
     t0 = time.perf_counter()
     ref = oracle.RefEngine(V, F)
     build_s = time.perf_counter() - t0
-    cores = oracle.num_threads()
+    cores = HOST_THREADS
     # pilot to size the sample
     stride0 = max(1, total // 200_000) | 1
     t0 = time.perf_counter()
-    ref.grid(origin, spacing, dims, first=0, stride=stride0)
+    ref.grid(origin, spacing, dims, first=0, stride=stride0, nthreads=cores)
     pilot = time.perf_counter() - t0
     pilot_n = (total + stride0 - 1) // stride0
     rate = pilot_n / max(pilot, 1e-6)
     n = int(min(total, max(pilot_n, rate * seconds)))
     stride = max(1, total // n) | 1
     t0 = time.perf_counter()
-    out = ref.grid(origin, spacing, dims, first=0, stride=stride)
+    out = ref.grid(origin, spacing, dims, first=0, stride=stride, nthreads=cores)
     dt = time.perf_counter() - t0
     n = len(out)
     return ref, {"value": n / dt / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
@@ -160,10 +172,10 @@ def run_reference(args):
     t0 = time.perf_counter()
     ref = oracle.RefEngine(V, F)
     build_s = time.perf_counter() - t0
-    cores = oracle.num_threads()
+    cores = HOST_THREADS
     stride0 = max(1, total // 100_000) | 1
     t0 = time.perf_counter()
-    ref.grid(origin, spacing, dims, stride=stride0)
+    ref.grid(origin, spacing, dims, stride=stride0, nthreads=cores)
     rate = ((total + stride0 - 1) // stride0) / (time.perf_counter() - t0)
     per_step = max(50_000, int(rate * 4.0))  # ~4 s per step
     stride = max(1, total // per_step) | 1
@@ -171,7 +183,7 @@ def run_reference(args):
     n = 0
     for it in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        out = ref.grid(origin, spacing, dims, first=it % stride, stride=stride)
+        out = ref.grid(origin, spacing, dims, first=it % stride, stride=stride, nthreads=cores)
         dt = time.perf_counter() - t0
         n = len(out)
         if it >= args.warmup:
@@ -182,8 +194,7 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": name, "note": "oracle restatement of the reference algorithm on the host CPU (reference binary unbuildable: "
-                                             "Eigen/TBB/WindingNumber sources absent)"},
+        "config": config_dict(args, name, total),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
@@ -254,6 +265,10 @@ def main():
         build_info["build_wall_ms"] = build_wall_ms
     bcast_ms = 0.0
     if world > 1:
+        # warm the communicator first (NCCL sets up its channels lazily on the first collective: ~40-70 ms that are not the
+        # cost of moving a tree), then time the replication itself
+        warm = torch.zeros(1 << 20, dtype=torch.uint8, device="cuda")
+        dist.broadcast(warm, src=0)
         torch.cuda.synchronize()
         dist.barrier()
         t0 = time.perf_counter()
@@ -305,9 +320,10 @@ def main():
     value = n_total / (ms_step * 1e-3) / 1e9
 
     # ---- e2e: the public API with a HOST output buffer (pinned), D2H inside the timed region --------------------------------
-    out_host = torch.empty(max(n_local, 1), dtype=torch.uint8).pin_memory().numpy()
+    # (bit-packed: 1 bit per query, WN_QUERY_OUT_BITS; the copies of finished batches overlap the next batch)
+    out_host = torch.empty(max((n_local + 7) // 8, 1), dtype=torch.uint8).pin_memory().numpy()
     def step_host():
-        eng.query_grid(origin, spacing, dims, want_inside=True, out_inside=out_host, layers=layers)
+        eng.query_grid(origin, spacing, dims, want_inside=True, out_inside=out_host, layers=layers, bits=True)
 
     for _ in range(2):
         step_host()
@@ -318,7 +334,7 @@ def main():
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         step_host()
-        checksum = int(out_host[::4097].sum())  # the caller reads the result
+        checksum = int(out_host[::509].sum())  # the caller reads the result
         e2e_times.append(time.perf_counter() - t0)
     t = torch.tensor([float(np.mean(e2e_times)) * 1e3], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -384,18 +400,17 @@ def main():
     }
 
     cpu = None
-    if not args.no_cpu_baseline and world == 1:
-        _, cpu = cpu_baseline(V, F, (origin, spacing, dims), args.cpu_seconds)
+    if not args.no_cpu_baseline:
+        _, cpu = cpu_baseline(V, F, (origin, spacing, dims), args.cpu_seconds if world == 1 else min(args.cpu_seconds, 6.0))
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": name, "queries_per_step": n_total, "sharding": f"tile layers (8 z-planes) round-robin over {world} rank(s), tree built on rank 0 and broadcast",
-                   "l2": "flushed between timed steps (256 MiB fill); tree %.0f MB" % (build_info.get("tree_bytes", 0) / 1e6),
-                   "leaf_size": args.leaf_size, "hierarchy": args.hierarchy, "tiled": tiled},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 60, "d2h_bytes_per_step": n_total, "ms_per_step": e2e_ms,
-                "api": "FastWindingNumber.query_grid -> wn_query_grid with a pinned HOST output buffer (lattice is implicit: 60-byte descriptor in)"},
+        "config": config_dict(args, name, n_total),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 60, "d2h_bytes_per_step": (n_total + 7) // 8, "ms_per_step": e2e_ms,
+                "api": "FastWindingNumber.query_grid(bits=True) -> wn_query_grid[_strided](WN_QUERY_OUT_BITS) with a pinned HOST output buffer, 1 bit per "
+                       "query (lattice is implicit: 60-byte descriptor in)"},
         # per step and rank: tiled = (k_tile_plan + k_tile_query) per batch of <= 131072 tiles (the probe that picks the path runs
         # once, in the warm-up, and is remembered per lattice); generic = one k_query
         "gpu_launches": args.steps * (2 * max(1, -(-(-(-n_local // 512)) // 131072)) if tiled else 1),

@@ -145,6 +145,9 @@ WN_API wn_status wn_get_info(const wn_engine* e, wn_info* info);
 #define WN_QUERY_DEFAULT 0u
 #define WN_QUERY_PRESORTED 1u /* points are already spatially coherent: skip the Morton sort of the queries (K9) */
 #define WN_QUERY_NO_TILING 2u /* always run the generic per-point traversal (no tile plan, no far-field interpolation) */
+#define WN_QUERY_OUT_BITS 8u  /* out_inside is a bit array: query i -> bit (i & 7) of byte i >> 3, (n + 7) / 8 bytes (numpy:
+                                 unpackbits(bitorder='little')). 8x less device-to-host traffic for host outputs. wn_is_inside,
+                                 wn_query_grid, wn_query_grid_strided */
 
 /* out_omega[i] = solid angle at q_i, in (-4pi k, 4pi k): what FastWindingNumber::solid_angle returns (:69-76). */
 WN_API wn_status wn_solid_angle(const wn_engine* e, const float* q_xyz, int64_t n, float beta, uint32_t flags,

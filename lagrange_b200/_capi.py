@@ -11,6 +11,8 @@ WN_OK = 0
 WN_QUERY_DEFAULT = 0
 WN_QUERY_PRESORTED = 1
 WN_QUERY_NO_TILING = 2
+WN_QUERY_OUT_BITS = 8
+WN_HIERARCHY = {"lbvh": 0, "kd": 1, "kd_sah": 2, "reference": 3}
 WN_RADIUS_BOX_CORNER = 0
 WN_RADIUS_VERTEX = 1
 

@@ -151,6 +151,44 @@ __global__ void __launch_bounds__(kBuildThreads) k_ref23(WnBuild b, int64_t firs
     for (int j = 0; j < 23; ++j) out[k * 23 + j] = o[j];
 }
 
+// Structural check of an adopted packed tree (wn_create_from_packed): every index the traversal, the tile planner or the
+// distance query will dereference must stay inside the arrays.
+__global__ void __launch_bounds__(kBuildThreads) k_validate_packed(WnTreeView t, int* __restrict__ err)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= t.n_entries) return;
+    const float4 f0 = t.hot[2 * (int64_t)i], f1 = t.hot[2 * (int64_t)i + 1];
+    const int lk = __float_as_int(f1.w);
+    const bool leaf = __float_as_int(f0.w) < 0;
+    bool bad = false;
+    if (leaf) {
+        const int first = lk >> WN_LEAF_COUNT_BITS, count = (lk & (WN_MAX_LEAF_SIZE - 1)) + 1;
+        bad = lk < 0 || first < 0 || first + count > t.n_tris;
+    } else {
+        bad = lk <= i || lk > t.n_entries; // skip link: first entry after the subtree
+        const int4 k = t.kids[i];
+        const int kid[4] = {k.x, k.y, k.z, k.w};
+        for (int s = 0; s < 4; ++s) bad = bad || kid[s] < -1 || (kid[s] >= 0 && (kid[s] <= i || kid[s] >= lk || kid[s] >= t.n_entries));
+        bad = bad || (t.n_entries > 1 && i + 1 >= t.n_entries); // an internal entry has at least one entry below it
+    }
+    if (bad) *err = 1;
+}
+
+// WN_QUERY_OUT_BITS: in[i] in {0, 1}, i < n  ->  out[i >> 3] bit (i & 7). One thread per output byte; `in` is 8-byte aligned.
+__global__ void __launch_bounds__(256) k_pack_bits(const uint8_t* __restrict__ in, int64_t n, uint8_t* __restrict__ out)
+{
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b * 8 >= n) return;
+    unsigned long long x;
+    if (b * 8 + 8 <= n) {
+        x = *reinterpret_cast<const unsigned long long*>(in + b * 8);
+    } else {
+        x = 0;
+        for (int k = 0; b * 8 + k < n; ++k) x |= (unsigned long long)in[b * 8 + k] << (8 * k);
+    }
+    out[b] = (uint8_t)((x * 0x0102040810204080ull) >> 56); // bytes are 0/1: byte k lands on bit k
+}
+
 inline int grid_for(int64_t n, int threads = kBuildThreads)
 {
     return (int)((n + threads - 1) / threads);

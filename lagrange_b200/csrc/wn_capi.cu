@@ -131,7 +131,7 @@ size_t align_up(size_t v, size_t a)
 // Position independent packed tree: one device allocation, header first.
 struct PackedHeader
 {
-    uint64_t magic; // 'WNB200T2'
+    uint64_t magic; // 'WNB200T4' (kMagic)
     int64_t total_bytes;
     int64_t n_entries;
     int64_t n_tris;
@@ -196,7 +196,7 @@ struct wn_engine
     mutable cudaEvent_t ev_last = nullptr;
     mutable bool ev_last_valid = false;
     mutable std::mutex sdf_mu; // wn_sdf_grid runs two passes (sign, distance) over shared scratch: one caller at a time
-    mutable DevBuf s_in, s_out_f, s_out_b, s_sort, s_stats, s_partial, s_plan_hdr, s_plan_items, s_plan_samples, s_plan_order, s_sdf_inside;
+    mutable DevBuf s_in, s_out_f, s_out_b, s_out_bits, s_sort, s_stats, s_partial, s_plan_hdr, s_plan_items, s_plan_samples, s_plan_order, s_sdf_inside;
     mutable PinnedBuf p_small;
     mutable cudaStream_t copy_stream = nullptr; // D2H of finished batches while the next batch computes
     mutable int64_t last_plan_tiles = 0;        // tiles of the last k_tile_plan launch (wn_debug_last_plan)
@@ -758,10 +758,14 @@ struct OutBufs
     uint8_t* d_inside = nullptr;
     float* h_omega = nullptr;
     uint8_t* h_inside = nullptr;
+    // WN_QUERY_OUT_BITS: the kernels write one byte per query into d_inside (engine scratch), k_pack_bits folds 8 of them
+    // into one byte of d_bits (the caller's device buffer, or scratch that is then copied to h_inside)
+    bool bits = false;
+    uint8_t* d_bits = nullptr;
 };
 
 // Resolve output residency: device pointers are used directly, host pointers get device staging.
-wn_status prepare_outputs(const wn_engine* e, int64_t n, float* out_omega, uint8_t* out_inside, OutBufs& ob)
+wn_status prepare_outputs(const wn_engine* e, int64_t n, float* out_omega, uint8_t* out_inside, OutBufs& ob, bool bits = false)
 {
     if (out_omega) {
         if (is_device_pointer(out_omega)) {
@@ -772,7 +776,18 @@ wn_status prepare_outputs(const wn_engine* e, int64_t n, float* out_omega, uint8
             ob.h_omega = out_omega;
         }
     }
-    if (out_inside) {
+    if (out_inside && bits) {
+        ob.bits = true;
+        WN_CUDA(e->s_out_b.reserve((size_t)n + 64));
+        ob.d_inside = (uint8_t*)e->s_out_b.p;
+        if (is_device_pointer(out_inside)) {
+            ob.d_bits = out_inside;
+        } else {
+            WN_CUDA(e->s_out_bits.reserve((size_t)(n + 7) / 8 + 64));
+            ob.d_bits = (uint8_t*)e->s_out_bits.p;
+            ob.h_inside = out_inside;
+        }
+    } else if (out_inside) {
         if (is_device_pointer(out_inside)) {
             ob.d_inside = out_inside;
         } else {
@@ -784,6 +799,13 @@ wn_status prepare_outputs(const wn_engine* e, int64_t n, float* out_omega, uint8
     return WN_OK;
 }
 
+// queries [first, first + count) of the batch, first a multiple of 8: bytes -> bits (LSB first: query i = bit i & 7 of byte i >> 3)
+void pack_bits(const OutBufs& ob, int64_t first, int64_t count, cudaStream_t st)
+{
+    const int64_t nbytes = (count + 7) / 8;
+    if (nbytes > 0) wn::k_pack_bits<<<(int)((nbytes + 255) / 256), 256, 0, st>>>(ob.d_inside + first, count, ob.d_bits + first / 8);
+}
+
 wn_status finish_outputs(int64_t n, const OutBufs& ob, cudaStream_t st)
 {
     bool sync = false;
@@ -791,8 +813,15 @@ wn_status finish_outputs(int64_t n, const OutBufs& ob, cudaStream_t st)
         WN_CUDA(cudaMemcpyAsync(ob.h_omega, ob.d_omega, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
         sync = true;
     }
+    if (ob.bits) {
+        pack_bits(ob, 0, n, st);
+        WN_CUDA(cudaGetLastError());
+    }
     if (ob.h_inside) {
-        WN_CUDA(cudaMemcpyAsync(ob.h_inside, ob.d_inside, (size_t)n, cudaMemcpyDeviceToHost, st));
+        if (ob.bits)
+            WN_CUDA(cudaMemcpyAsync(ob.h_inside, ob.d_bits, (size_t)(n + 7) / 8, cudaMemcpyDeviceToHost, st));
+        else
+            WN_CUDA(cudaMemcpyAsync(ob.h_inside, ob.d_inside, (size_t)n, cudaMemcpyDeviceToHost, st));
         sync = true;
     }
     if (sync) WN_CUDA(cudaStreamSynchronize(st));
@@ -987,6 +1016,7 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
                 const int64_t per_layer = (int64_t)a.g.nx * a.g.ny;
                 const int64_t first = 8 * u0 * per_layer;
                 const int64_t count = std::min<int64_t>(8 * nunits, grid_layers - 8 * u0) * per_layer;
+                if (ob->bits) pack_bits(*ob, first, count, st); // first = 8 * u0 * per_layer: byte aligned
                 cudaEvent_t ev;
                 WN_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
                 WN_CUDA(cudaEventRecord(ev, st));
@@ -995,7 +1025,10 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
                 if (ob->h_omega)
                     WN_CUDA(cudaMemcpyAsync(ob->h_omega + first, ob->d_omega + first, (size_t)count * sizeof(float), cudaMemcpyDeviceToHost,
                                             e->copy_stream));
-                if (ob->h_inside)
+                if (ob->h_inside && ob->bits)
+                    WN_CUDA(cudaMemcpyAsync(ob->h_inside + first / 8, ob->d_bits + first / 8, (size_t)(count + 7) / 8, cudaMemcpyDeviceToHost,
+                                            e->copy_stream));
+                else if (ob->h_inside)
                     WN_CUDA(cudaMemcpyAsync(ob->h_inside + first, ob->d_inside + first, (size_t)count, cudaMemcpyDeviceToHost, e->copy_stream));
             }
         }
@@ -1061,7 +1094,7 @@ wn_status points_impl(const wn_engine* e, const float* q_xyz, int64_t n, float b
     // Small host batches (the reference's own calling pattern is one point per call, FastWindingNumber.cpp:60-76): the kernel
     // reads the queries from, and writes the results to, pinned host memory directly (unified addressing), so a call is one
     // launch and one synchronisation instead of two staged copies around it. Same kernel, same arithmetic.
-    if (n <= 256 && !stats && e->view.n_entries > 0 && !is_device_pointer(q_xyz) && (!out_omega || !is_device_pointer(out_omega)) &&
+    if (n <= 256 && !stats && !(flags & WN_QUERY_OUT_BITS) && e->view.n_entries > 0 && !is_device_pointer(q_xyz) && (!out_omega || !is_device_pointer(out_omega)) &&
         (!out_inside || !is_device_pointer(out_inside))) {
         const size_t nq = (size_t)n;
         WN_CUDA(e->p_small.reserve(256 * (3 * sizeof(float) + sizeof(float) + 1)));
@@ -1089,7 +1122,7 @@ wn_status points_impl(const wn_engine* e, const float* q_xyz, int64_t n, float b
     wn_status s = stage_points(e, q_xyz, n, &d_q, st);
     if (s != WN_OK) return s;
     OutBufs ob;
-    s = prepare_outputs(e, n, out_omega, out_inside, ob);
+    s = prepare_outputs(e, n, out_omega, out_inside, ob, (flags & WN_QUERY_OUT_BITS) != 0);
     if (s != WN_OK) return s;
 
     const unsigned* perm = nullptr;
@@ -1148,6 +1181,9 @@ wn_status check_grid(const float* origin, const float* spacing, const int64_t* d
     g.nz = (int)dims[2];
     g.z0 = (int)z0;
     g.z1 = (int)z1;
+    // dims are <= 2^24 each, so the products below cannot overflow int64; the point count itself is bounded explicitly
+    if (dims[0] * dims[1] > ((int64_t)1 << 40) || dims[0] * dims[1] * (z1 - z0) > ((int64_t)1 << 40) || dims[0] * dims[1] * dims[2] > ((int64_t)1 << 42))
+        return fail(WN_ERR_UNSUPPORTED, "lattice too large: at most 2^40 points per call (2^42 in the whole lattice); split it in z slabs");
     n = dims[0] * dims[1] * (z1 - z0);
     return WN_OK;
 }
@@ -1184,7 +1220,7 @@ wn_status grid_impl(const wn_engine* e, const float* origin, const float* spacin
     StreamOrder order(e, st);
     const float b = beta > 0.0f ? beta : e->opt.accuracy_scale;
     OutBufs ob;
-    s = prepare_outputs(e, n, out_omega, out_inside, ob);
+    s = prepare_outputs(e, n, out_omega, out_inside, ob, (flags & WN_QUERY_OUT_BITS) != 0);
     if (s != WN_OK) return s;
     wn::QueryArgs a;
     memset(&a, 0, sizeof(a));
@@ -1351,6 +1387,7 @@ wn_status wn_destroy(wn_engine* e)
         e->s_in.release();
         e->s_out_f.release();
         e->s_out_b.release();
+        e->s_out_bits.release();
         e->s_sort.release();
         e->s_stats.release();
         e->s_partial.release();
@@ -1459,8 +1496,18 @@ wn_status wn_create_from_packed(const void* src, int64_t nbytes, const wn_option
     if (!out) return fail(WN_ERR_INVALID_ARGUMENT, "out is null");
     *out = nullptr;
     if (!src || nbytes < (int64_t)sizeof(PackedHeader)) return fail(WN_ERR_INVALID_ARGUMENT, "packed tree buffer missing or too small");
+    // accuracy_scale <= 0 in the options means "keep the value stored with the tree" (a replica must answer beta <= 0 queries
+    // like the engine it was packed from); everything else in the options is validated as usual.
+    wn_options opt_copy;
+    bool keep_beta = true;
+    if (opt_in) {
+        if (opt_in->struct_size != sizeof(wn_options)) return fail(WN_ERR_INVALID_ARGUMENT, "wn_options.struct_size mismatch (call wn_options_init)");
+        opt_copy = *opt_in;
+        keep_beta = !(opt_copy.accuracy_scale > 0.0f);
+        if (keep_beta) opt_copy.accuracy_scale = 2.0f; // placeholder for validation; replaced by the header's value below
+    }
     wn_options opt;
-    wn_status s = validate_options(opt_in, &opt, false);
+    wn_status s = validate_options(opt_in ? &opt_copy : nullptr, &opt, false);
     if (s != WN_OK) return s;
     int dev = 0;
     s = resolve_device(&opt, &dev);
@@ -1470,14 +1517,20 @@ wn_status wn_create_from_packed(const void* src, int64_t nbytes, const wn_option
     PackedHeader h;
     WN_CUDA(cudaMemcpy(&h, src, sizeof(h), cudaMemcpyDefault));
     if (h.magic != kMagic) return fail(WN_ERR_INVALID_ARGUMENT, "not a packed winding tree (bad magic)");
+    if (h.n_entries < 0 || h.n_entries > INT_MAX / 8 || h.n_tris < 0 || h.n_tris >= WN_MAX_TRIANGLES)
+        return fail(WN_ERR_INVALID_ARGUMENT, "packed tree header is inconsistent (entry / triangle counts out of range)");
     if (h.total_bytes > nbytes) return fail(WN_ERR_INVALID_ARGUMENT, "packed tree truncated: header says %lld bytes, got %lld", (long long)h.total_bytes, (long long)nbytes);
     const PackedHeader ref = make_header(h.n_entries, h.n_tris);
-    if (ref.total_bytes != h.total_bytes || ref.off_tri_order != h.off_tri_order) return fail(WN_ERR_INVALID_ARGUMENT, "packed tree header is inconsistent");
+    if (ref.total_bytes != h.total_bytes || ref.off_hot != h.off_hot || ref.off_cold != h.off_cold || ref.off_kids != h.off_kids ||
+        ref.off_tris != h.off_tris || ref.off_tri_order != h.off_tri_order)
+        return fail(WN_ERR_INVALID_ARGUMENT, "packed tree header is inconsistent");
+    if (h.order < 0 || h.order > 2 || !(h.accuracy_scale > 0.0f) || (h.n_entries == 0) != (h.n_tris == 0))
+        return fail(WN_ERR_INVALID_ARGUMENT, "packed tree header is inconsistent (order / accuracy scale / empty tree)");
     wn_engine* e = new (std::nothrow) wn_engine;
     if (!e) return fail(WN_ERR_OUT_OF_MEMORY, "host allocation failed");
     e->device = dev;
     e->opt = opt;
-    e->opt.accuracy_scale = opt_in ? opt.accuracy_scale : h.accuracy_scale;
+    e->opt.accuracy_scale = keep_beta ? h.accuracy_scale : opt.accuracy_scale;
     e->opt.order = h.order;
     memset(&e->info, 0, sizeof(e->info));
     e->hdr = h;
@@ -1489,6 +1542,26 @@ wn_status wn_create_from_packed(const void* src, int64_t nbytes, const wn_option
         return fail(ce == cudaErrorMemoryAllocation ? WN_ERR_OUT_OF_MEMORY : WN_ERR_CUDA, "adopting packed tree failed: %s", cudaGetErrorString(ce));
     }
     set_view(e);
+    // The records are about to be dereferenced by the traversal: check every link, child index and leaf range once (a
+    // corrupted or mismatched broadcast must be an error, not an out-of-bounds read). One pass over the hot section.
+    if (h.n_entries > 0) {
+        int* d_err = nullptr;
+        ce = cudaMalloc((void**)&d_err, sizeof(int));
+        if (ce == cudaSuccess) ce = cudaMemset(d_err, 0, sizeof(int));
+        int h_err = 0;
+        if (ce == cudaSuccess) {
+            wn::k_validate_packed<<<wn::grid_for(h.n_entries), wn::kBuildThreads>>>(e->view, d_err);
+            ce = cudaMemcpy(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost);
+        }
+        if (d_err) cudaFree(d_err);
+        if (ce != cudaSuccess || h_err) {
+            cudaGetLastError();
+            wn_destroy(e);
+            if (ce != cudaSuccess) return fail(WN_ERR_CUDA, "validating packed tree failed: %s", cudaGetErrorString(ce));
+            return fail(WN_ERR_INVALID_ARGUMENT, "packed tree is corrupt (bad skip link, child index or leaf range)");
+        }
+    }
+    e->hdr.accuracy_scale = e->opt.accuracy_scale;
     fill_info(e);
     e->info.num_leaf_entries = -1;
     *out = e;

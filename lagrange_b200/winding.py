@@ -94,7 +94,9 @@ class FastWindingNumber:
       order           Taylor order 0/1/2 (reference default 2)
       topology        (n_nodes, width) int32 child table to import instead of building the LBVH (oracle-tree mode)
       leaf_size, morton_bits, radius_mode ('box_corner' | 'vertex'), approximate_single_triangles, device
-      hierarchy       'lbvh' (Morton + Karras, fastest build) or 'kd' (balanced object-median splits, faster queries)
+      hierarchy       'lbvh' (Morton + Karras, fastest build), 'kd' (balanced object-median splits), 'kd_sah' (k-d with binned
+                      SAH cuts) or 'reference' (the reference builder's 4-ary top-down SAH tree, reproduced on the GPU: results
+                      match the reference algorithm to float rounding)
     """
 
     def __init__(self, mesh=None, facets=None, *, accuracy_scale=2.0, order=2, topology=None, leaf_size=1, morton_bits=63,
@@ -134,9 +136,9 @@ class FastWindingNumber:
         opt.morton_bits = int(morton_bits)
         opt.radius_mode = {"box_corner": _capi.WN_RADIUS_BOX_CORNER, "vertex": _capi.WN_RADIUS_VERTEX}[radius_mode]
         opt.keep_build_data = 1 if keep_build_data else 0
-        if hierarchy not in ("lbvh", "kd", "kd_sah"):
-            raise Error("hierarchy must be 'lbvh', 'kd' or 'kd_sah'")
-        opt.hierarchy = {"lbvh": 0, "kd": 1, "kd_sah": 2}[hierarchy]
+        if hierarchy not in _capi.WN_HIERARCHY:
+            raise Error("hierarchy must be 'lbvh', 'kd', 'kd_sah' or 'reference'")
+        opt.hierarchy = _capi.WN_HIERARCHY[hierarchy]
         opt.device = -1 if device is None else int(device)
         if approximate_single_triangles is None:
             approximate_single_triangles = topology is not None
@@ -209,12 +211,14 @@ class FastWindingNumber:
         self._check(self._lib.wn_solid_angle(self._handle(), buf.ptr, n, float(accuracy_scale or 0.0), flags, ob.ptr, _current_stream_ptr()))
         return float(res[0]) if single else res
 
-    def is_inside(self, pos, accuracy_scale=None, presorted=False, out=None, tiling=True):
-        """True iff (double)solid_angle / (4 pi) > 0.5 (FastWindingNumber.cpp:66). (3,) -> bool, (n,3) -> uint8 array."""
+    def is_inside(self, pos, accuracy_scale=None, presorted=False, out=None, tiling=True, bits=False):
+        """True iff (double)solid_angle / (4 pi) > 0.5 (FastWindingNumber.cpp:66). (3,) -> bool, (n,3) -> uint8 array.
+        ``bits=True``: the result is a bit array of (n + 7) // 8 bytes (``np.unpackbits(r, bitorder='little')[:n]``)."""
         buf, n, single = self._points(pos)
-        res = _alloc_like(buf, n, np.uint8) if out is None else out
+        bits = bits and not single
+        res = _alloc_like(buf, (n + 7) // 8 if bits else n, np.uint8) if out is None else out
         ob = _Buf(res, np.uint8, writable=True)
-        flags = self._flags(presorted, tiling)
+        flags = self._flags(presorted, tiling) | (_capi.WN_QUERY_OUT_BITS if bits else 0)
         self._check(self._lib.wn_is_inside(self._handle(), buf.ptr, n, float(accuracy_scale or 0.0), flags, ob.ptr, _current_stream_ptr()))
         return bool(res[0]) if single else res
 
@@ -229,16 +233,18 @@ class FastWindingNumber:
         return o, s, d, z0, z1, n
 
     def query_grid(self, origin, spacing, dims, z_range=None, accuracy_scale=None, want_omega=False, want_inside=True, device_output=False,
-                   out_omega=None, out_inside=None, tiling=True, layers=None):
+                   out_omega=None, out_inside=None, tiling=True, layers=None, bits=False):
         """Evaluate the cell-centred lattice p = origin + spacing*(ijk+0.5), x fastest; returns (omega, inside) (None if not wanted).
 
         ``device_output`` allocates torch CUDA outputs (results stay in HBM); otherwise numpy (copied to the host).
         ``layers=(first, step)``: strided multi-GPU sharding -- only the tile layers (8 z-planes each) first, first+step, ...
-        are evaluated and returned compactly in that order (see ``strided_layer_planes``)."""
+        are evaluated and returned compactly in that order (see ``strided_layer_planes``).
+        ``bits=True``: ``inside`` is a bit array, point i -> bit (i & 7) of byte i >> 3 ((n + 7) // 8 bytes; WN_QUERY_OUT_BITS):
+        an eighth of the device-to-host traffic for host outputs."""
         o, s, d, z0, z1, n = self._grid_args(origin, spacing, dims, z_range)
         if layers is not None:
             n = int(dims[0]) * int(dims[1]) * len(self.strided_layer_planes(int(dims[2]), *layers))
-        def mk(dtype, given, want):
+        def mk(dtype, given, want, count):
             if given is not None:
                 return given
             if not want:
@@ -246,17 +252,18 @@ class FastWindingNumber:
             if device_output:
                 import torch
 
-                return torch.empty(n, dtype={np.float32: torch.float32, np.uint8: torch.uint8}[dtype], device="cuda")
-            return np.empty(n, dtype=dtype)
-        om = mk(np.float32, out_omega, want_omega)
-        ins = mk(np.uint8, out_inside, want_inside)
+                return torch.empty(count, dtype={np.float32: torch.float32, np.uint8: torch.uint8}[dtype], device="cuda")
+            return np.empty(count, dtype=dtype)
+        om = mk(np.float32, out_omega, want_omega, n)
+        ins = mk(np.uint8, out_inside, want_inside, (n + 7) // 8 if bits else n)
         pom = _Buf(om, np.float32, writable=True).ptr if om is not None else None
         pin = _Buf(ins, np.uint8, writable=True).ptr if ins is not None else None
+        flags = self._flags(False, tiling) | (_capi.WN_QUERY_OUT_BITS if (bits and ins is not None) else 0)
         if layers is not None:
             self._check(self._lib.wn_query_grid_strided(self._handle(), o, s, d, int(layers[0]), int(layers[1]), float(accuracy_scale or 0.0),
-                                                        self._flags(False, tiling), pom, pin, _current_stream_ptr()))
+                                                        flags, pom, pin, _current_stream_ptr()))
         else:
-            self._check(self._lib.wn_query_grid(self._handle(), o, s, d, z0, z1, float(accuracy_scale or 0.0), self._flags(False, tiling), pom,
+            self._check(self._lib.wn_query_grid(self._handle(), o, s, d, z0, z1, float(accuracy_scale or 0.0), flags, pom,
                                                 pin, _current_stream_ptr()))
         return om, ins
 
@@ -367,8 +374,8 @@ class FastWindingNumber:
         if accuracy_scale is not None or device is not None:
             opt = _capi.wn_options()
             _capi.check(lib.wn_options_init(ctypes.byref(opt)))
-            if accuracy_scale is not None:
-                opt.accuracy_scale = float(accuracy_scale)
+            # <= 0 = keep the accuracy scale stored with the tree (a replica answers like the engine it was packed from)
+            opt.accuracy_scale = float(accuracy_scale) if accuracy_scale is not None else 0.0
             if device is not None:
                 opt.device = int(device)
         st = lib.wn_create_from_packed(b.ptr, b.size, ctypes.byref(opt) if opt is not None else None, ctypes.byref(h))
