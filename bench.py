@@ -57,7 +57,7 @@ def parse_args():
     ap.add_argument("--grid", type=int, default=0, help="override lattice resolution (debug)")
     ap.add_argument("--subdiv", type=int, default=-1, help="override sphere subdivision level (debug)")
     ap.add_argument("--leaf-size", type=int, default=int(os.environ.get("WN_BENCH_LEAF", "4")), help="max triangles per leaf")
-    ap.add_argument("--hierarchy", default=os.environ.get("WN_BENCH_HIERARCHY", "kd_sah"), choices=["lbvh", "kd", "kd_sah"],
+    ap.add_argument("--hierarchy", default=os.environ.get("WN_BENCH_HIERARCHY", "kd_sah"), choices=["lbvh", "kd", "kd_sah", "reference"],
                     help="kd_sah: k-d hierarchy with SAH-guided cuts (fastest queries, 10 ms build); kd: balanced k-d (7 ms); lbvh: Morton/Karras (1.9 ms)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the CPU baseline sample")

@@ -58,8 +58,13 @@ typedef enum wn_hierarchy {
     WN_HIERARCHY_LBVH = 0, /* Morton codes + one radix sort + Karras 2012: fastest build (1.9 ms for 1.3 M triangles) */
     WN_HIERARCHY_KD = 1,   /* balanced k-d: object-median splits along the longest centroid axis, one radix sort per
                               level: compact equal-count patches, ~13 % faster queries, ~4 ms more build time */
-    WN_HIERARCHY_KD_SAH = 2 /* k-d with the split position chosen by the surface-area heuristic among the boundaries of 16
+    WN_HIERARCHY_KD_SAH = 2, /* k-d with the split position chosen by the surface-area heuristic among the boundaries of 16
                               equal-width bins along the axis (the reference builder's rule): fastest queries, ~11 ms build */
+    WN_HIERARCHY_REFERENCE = 3 /* the reference builder's own tree (UT_BVH<4>::init<BOX_AREA>: 4-ary, top-down, binned SAH with its
+                              small-range rules, one triangle per leaf slot), reproduced on the GPU bit for bit against the CPU
+                              restatement: solid_angle then matches the reference algorithm to float rounding (<= 1e-4 * 4 pi)
+                              and is_inside is identical outside |w - 0.5| <= 1e-3. leaf_size is forced to 1 and single
+                              triangles are approximated by their own expansion like the reference does */
 } wn_hierarchy;
 
 typedef struct wn_options {

@@ -21,6 +21,7 @@
 #include "../../include/wn_b200.h"
 #include "wn_query.cuh"
 #include "wn_kd.cuh"
+#include "wn_refbuild.cuh"
 #include "wn_sdf.cuh"
 
 namespace {
@@ -369,7 +370,7 @@ wn_status validate_options(const wn_options* in, wn_options* out, bool imported)
     if (out->leaf_size < 1 || out->leaf_size > WN_MAX_LEAF_SIZE) return fail(WN_ERR_INVALID_ARGUMENT, "leaf_size must be in [1, %d]", WN_MAX_LEAF_SIZE);
     if (out->morton_bits != 30 && out->morton_bits != 63) return fail(WN_ERR_INVALID_ARGUMENT, "morton_bits must be 30 or 63");
     if (out->radius_mode != WN_RADIUS_BOX_CORNER && out->radius_mode != WN_RADIUS_VERTEX) return fail(WN_ERR_INVALID_ARGUMENT, "bad radius_mode");
-    if (out->hierarchy < WN_HIERARCHY_LBVH || out->hierarchy > WN_HIERARCHY_KD_SAH) return fail(WN_ERR_INVALID_ARGUMENT, "bad hierarchy");
+    if (out->hierarchy < WN_HIERARCHY_LBVH || out->hierarchy > WN_HIERARCHY_REFERENCE) return fail(WN_ERR_INVALID_ARGUMENT, "bad hierarchy");
     return WN_OK;
 }
 
@@ -382,12 +383,21 @@ wn_status create_impl(const float* v_xyz, int64_t nV, const int32_t* tri, int64_
     *out = nullptr;
     if (nV < 0 || nT < 0 || (nV > 0 && !v_xyz) || (nT > 0 && !tri)) return fail(WN_ERR_INVALID_ARGUMENT, "null mesh buffers or negative sizes");
     if (nT >= WN_MAX_TRIANGLES || nV > INT_MAX / 4) return fail(WN_ERR_UNSUPPORTED, "at most 2^27-1 triangles are supported");
-    const bool imported = child_in != nullptr;
-    if (imported && (width < 2 || width > WN_MAX_WIDTH || num_nodes < 1 || num_nodes > INT_MAX / 8))
+    if (child_in && (width < 2 || width > WN_MAX_WIDTH || num_nodes < 1 || num_nodes > INT_MAX / 8))
         return fail(WN_ERR_INVALID_ARGUMENT, "topology width must be 2..4 and num_nodes >= 1");
+    // WN_HIERARCHY_REFERENCE: the reference builder's 4-ary tree is built on the device (K3R, wn_refbuild.cuh) and then takes
+    // the same route as a caller-supplied topology (moments, radii, packing): one triangle per leaf slot, single triangles
+    // approximated like the reference does.
+    const bool refh = !child_in && opt_in && opt_in->struct_size == sizeof(wn_options) && opt_in->hierarchy == WN_HIERARCHY_REFERENCE && nT > 0;
+    const bool imported = child_in != nullptr || refh;
+    if (refh) {
+        width = 4;
+        num_nodes = std::max<int64_t>(1, nT - 1); // upper bound; the builder reports the actual count
+    }
     wn_options opt;
     wn_status s = validate_options(opt_in, &opt, imported);
     if (s != WN_OK) return s;
+    if (refh) opt.approximate_single_triangles = 1;
     int dev = 0;
     s = resolve_device(&opt, &dev);
     if (s != WN_OK) return s;
@@ -488,6 +498,11 @@ wn_status create_impl(const float* v_xyz, int64_t nV, const int32_t* tri, int64_
             add((size_t)nI_max * W * 4);
             add((size_t)nN_max * 4);
             add((size_t)nT * 4);
+            if (refh) {
+                add(wn_ref_layout(nT, (size_t)wn::scan_scratch_elems(nT) * 4 + 256).total);
+                add((size_t)wn::sort_scratch_bytes(nT));
+                add(((size_t)nT + 2) * 16);
+            }
         }
         add((size_t)nI_max * W * 4); // child
         add((size_t)nN_max * 4);     // parent
@@ -680,6 +695,60 @@ wn_status create_impl(const float* v_xyz, int64_t nV, const int32_t* tri, int64_
         }
         tm.mark(); // 3: hierarchy
     } else {
+        const int* child_src = child_in;
+        if (refh) {
+            // K3R: triangle boxes, then the level-synchronous top-down build (wn_refbuild_core.cuh); vertex indices are checked first
+            wn::k_centroid_bounds<<<std::min(wn::grid_for(nT), 148 * 8), wn::kBuildThreads, 0, st>>>(d_v, d_tri, (int)nT, (int)nV, d_small, d_small + 6);
+            int h_err = 0;
+            WN_CUDA_C(cudaMemcpyAsync(&h_err, d_small + 6, sizeof(int), cudaMemcpyDeviceToHost, st));
+            WN_CUDA_C(cudaStreamSynchronize(st));
+            if (h_err) return cleanup(fail(WN_ERR_INVALID_ARGUMENT, "triangle references a vertex index outside [0, num_vertices)"));
+            const size_t scan_bytes = (size_t)wn::scan_scratch_elems(nT) * 4 + 256;
+            const WnRefLayout L = wn_ref_layout(nT, scan_bytes);
+            char* base = nullptr;
+            void* sort_scratch = nullptr;
+            int* d_child_out = nullptr;
+            WN_CUDA_C(dalloc((void**)&base, L.total));
+            WN_CUDA_C(dalloc(&sort_scratch, (size_t)wn::sort_scratch_bytes(nT)));
+            WN_CUDA_C(dalloc((void**)&d_child_out, ((size_t)nT + 2) * 16));
+            WnRefState rs;
+            memset(&rs, 0, sizeof(rs));
+            rs.N = (int)nT;
+            rs.tbox = (const float4*)(base + L.tbox);
+            rs.idx = (unsigned*)(base + L.idx);
+            rs.idx_alt = (unsigned*)(base + L.idx_alt);
+            rs.owner = (int*)(base + L.owner);
+            rs.flag = (uint32_t*)(base + L.flag);
+            rs.nodes = (WnRefNode*)(base + L.nodes);
+            rs.next = (WnRefNode*)(base + L.next);
+            rs.tasks = (WnRefTask*)(base + L.tasks);
+            rs.rows = (int*)(base + L.rows);
+            rs.copen = (uint32_t*)(base + L.copen);
+            rs.cnode = (uint32_t*)(base + L.cnode);
+            rs.child_tmp = (int*)(base + L.child_tmp);
+            rs.info_start = (int*)(base + L.info_start);
+            rs.info_depth = (int*)(base + L.info_depth);
+            rs.info_chain = (int*)(base + L.info_chain);
+            rs.cnt_start = (uint32_t*)(base + L.cnt_start);
+            rs.final_of = (int*)(base + L.final_of);
+            rs.keys = (uint64_t*)(base + L.keys);
+            rs.res = (int*)(base + L.res);
+            rs.child_out = d_child_out;
+            wn::RefCudaBackend B;
+            B.st = st;
+            B.scan_scratch = (uint32_t*)(base + L.scan_scratch);
+            B.sort_scratch = sort_scratch;
+            B.keys_alt = (uint64_t*)(base + L.keys_alt);
+            B.for_each(nT, WnRefTriBoxes{d_v, d_tri, (float4*)(base + L.tbox), rs.idx, rs.owner});
+            int n_nodes = 0, n_levels = 0;
+            const bool ok = wn_ref_build_topology(B, rs, &n_nodes, &n_levels);
+            WN_CUDA_C(cudaGetLastError());
+            WN_CUDA_C(B.err);
+            if (!ok) return cleanup(fail(WN_ERR_CUDA, "reference hierarchy build did not terminate"));
+            num_nodes = n_nodes;
+            child_src = d_child_out;
+            if (env_int("WN_VERBOSE", 0)) fprintf(stderr, "[wn_b200] reference hierarchy: %d nodes, %d levels, %d host syncs\n", n_nodes, n_levels, B.syncs);
+        }
         b.W = width;
         b.nI = (int)num_nodes;
         const int64_t nN = (int64_t)b.nI + b.nL;
@@ -691,7 +760,7 @@ wn_status create_impl(const float* v_xyz, int64_t nV, const int32_t* tri, int64_
         WN_CUDA_C(dalloc((void**)&b.child, (size_t)b.nI * b.W * sizeof(int)));
         WN_CUDA_C(dalloc((void**)&b.parent, (size_t)nN * sizeof(int)));
         WN_CUDA_C(dalloc((void**)&b.slot, (size_t)nN));
-        WN_CUDA_C(cudaMemcpyAsync(d_child_in, child_in, (size_t)b.nI * b.W * sizeof(int), cudaMemcpyDefault, st));
+        WN_CUDA_C(cudaMemcpyAsync(d_child_in, child_src, (size_t)b.nI * b.W * sizeof(int), cudaMemcpyDefault, st));
         WN_CUDA_C(cudaMemsetAsync(d_seen, 0, (size_t)nN * sizeof(int), st));
         WN_CUDA_C(cudaMemsetAsync(b.parent, 0xff, (size_t)nN * sizeof(int), st));
         WN_CUDA_C(cudaMemsetAsync(b.slot, 0, (size_t)nN, st));

@@ -267,7 +267,11 @@ struct BvhBuilder
                 nth = min_count;
             else
                 nth = n / 2;
-            std::nth_element(indices, indices + nth, indices + n, [&](int32_t a, int32_t b) {
+            // (+) upstream calls std::nth_element here, whose permutation is implementation-defined (any arrangement with
+            // the nth centre in place, smaller-or-equal ones before it and larger-or-equal ones after it is conforming).
+            // This restatement fixes ONE conforming outcome, the stable-sorted order, so that the tree is a function of the
+            // input alone and a data-parallel builder can reproduce it (lagrange_b200/csrc/wn_refbuild_core.cuh does).
+            std::stable_sort(indices, indices + n, [&](int32_t a, int32_t b) {
                 return boxes[a].center_x2(axis) < boxes[b].center_x2(axis);
             });
             Box lb = boxes[indices[0]];

@@ -20,7 +20,7 @@ _u64p = ctypes.POINTER(ctypes.c_uint64)
 
 
 def build(force=False):
-    deps = [_SRC] + [os.path.join(_CSRC, f) for f in ("wn_device.cuh", "wn_build_core.cuh")]
+    deps = [_SRC] + [os.path.join(_CSRC, f) for f in ("wn_device.cuh", "wn_build_core.cuh", "wn_refbuild_core.cuh")]
     stale = (not os.path.exists(_LIB)) or any(os.path.getmtime(_LIB) < os.path.getmtime(d) for d in deps)
     if force or stale:
         extra = os.environ.get("WN_EMUL_DEFINES", "").split()
@@ -38,6 +38,8 @@ def lib():
         L.emul_build.argtypes = [_f32p, ctypes.c_int64, _i32p, ctypes.c_int64, _i32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
                                  ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
         L.emul_destroy.argtypes = [ctypes.c_void_p]
+        L.emul_ref_topology.restype = ctypes.c_int64
+        L.emul_ref_topology.argtypes = [_f32p, ctypes.c_int64, _i32p, ctypes.c_int64, _i32p, _i32p, _i32p]
         for name in ("emul_error", "emul_max_depth", "emul_width"):
             getattr(L, name).restype = ctypes.c_int
             getattr(L, name).argtypes = [ctypes.c_void_p]
@@ -150,3 +152,23 @@ def point_tri_dist2(points, tris):
     out = np.empty(len(p), dtype=np.float32)
     lib().emul_point_tri_dist2(p.ctypes.data_as(_f32p), t.ctypes.data_as(_f32p), len(p), out.ctypes.data_as(_f32p))
     return out
+
+
+def ref_topology(vertices, facets):
+    """K3R (WN_HIERARCHY_REFERENCE) on the host: the driver of lagrange_b200/csrc/wn_refbuild_core.cuh with a sequential
+    backend. Returns (child table [n_nodes, 4] int32, levels, host synchronisations the GPU backend would make)."""
+    v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 3)
+    f = np.ascontiguousarray(facets, dtype=np.int32).reshape(-1, 3)
+    out = np.full((max(1, len(f)), 4), -1, dtype=np.int32)
+    levels, syncs = ctypes.c_int32(0), ctypes.c_int32(0)
+    n = lib().emul_ref_topology(v.ctypes.data_as(_f32p), len(v), f.ctypes.data_as(_i32p), len(f), out.ctypes.data_as(_i32p),
+                                ctypes.byref(levels), ctypes.byref(syncs))
+    if n < 0:
+        raise RuntimeError("reference hierarchy build did not terminate")
+    return out[:n].copy(), int(levels.value), int(syncs.value)
+
+
+def ref_last_fallback_rounds() -> int:
+    """Rounds of the last ref_topology call in which some range took the order-statistic fallback (one sort each)."""
+    lib().emul_ref_last_sorts.restype = ctypes.c_int
+    return int(lib().emul_ref_last_sorts())

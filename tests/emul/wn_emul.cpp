@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../lagrange_b200/csrc/wn_build_core.cuh"
+#include "../../lagrange_b200/csrc/wn_refbuild_core.cuh"
 
 namespace {
 
@@ -29,6 +30,62 @@ struct Emul
 };
 
 } // namespace
+
+// ---- K3R (WN_HIERARCHY_REFERENCE): the driver of wn_refbuild_core.cuh with a sequential backend ---------------------------
+namespace {
+int g_ref_sorts = 0; // order-statistic fallbacks taken by the last emul_ref_topology call (rounds that needed the sort)
+struct RefHostBackend
+{
+    int syncs = 0;
+    template <class F>
+    void for_each(int64_t n, const F& f)
+    {
+        for (int64_t i = 0; i < n; ++i) f(i);
+    }
+    void bin(const WnRefState& s) { for_each(s.N, WnRefBin{s}); }
+    void root_bounds(const WnRefState& s)
+    {
+        for (int a = 0; a < 6; ++a) s.rows[a] = a < 3 ? 0x7fffffff : (int)0x80000000;
+        for (int t = 0; t < s.N; ++t) {
+            float b[6];
+            wn_ref_tri_box(s.tbox, (unsigned)t, b);
+            for (int a = 0; a < 3; ++a) {
+                s.rows[a] = std::min(s.rows[a], wn_ref_ordered(b[a]));
+                s.rows[3 + a] = std::max(s.rows[3 + a], wn_ref_ordered(b[3 + a]));
+            }
+        }
+    }
+    void scan(uint32_t* d, int64_t n)
+    {
+        uint32_t run = 0;
+        for (int64_t i = 0; i < n; ++i) {
+            const uint32_t v = d[i];
+            d[i] = run;
+            run += v;
+        }
+    }
+    int sort64(uint64_t* keys, unsigned* vals, unsigned*, int64_t n, int end_bit)
+    {
+        ++g_ref_sorts;
+        const uint64_t mask = end_bit >= 64 ? ~0ull : ((1ull << end_bit) - 1ull);
+        std::vector<int64_t> order(n);
+        std::iota(order.begin(), order.end(), (int64_t)0);
+        std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t c) { return (keys[a] & mask) < (keys[c] & mask); });
+        std::vector<unsigned> v2(n);
+        for (int64_t i = 0; i < n; ++i) v2[i] = vals[order[i]];
+        std::copy(v2.begin(), v2.end(), vals);
+        return 0;
+    }
+    void read(int* h, const int* d, int n)
+    {
+        memcpy(h, d, (size_t)n * sizeof(int));
+        ++syncs;
+    }
+    void zero(void* p, size_t bytes) { memset(p, 0, bytes); }
+    void write(void* d, const void* h, size_t bytes) { memcpy(d, h, bytes); }
+};
+} // namespace
+
 
 extern "C" {
 
@@ -433,6 +490,54 @@ void* emul_build(const float* v, int64_t nV, const int32_t* tri, int64_t nT, con
     e->view.n_entries = n_entries;
     e->view.n_tris = (int)nT;
     return e;
+}
+
+// out_child: at least max(1, nT) * 4 ints. Returns the number of nodes (0 for an empty mesh).
+int64_t emul_ref_topology(const float* v, int64_t nV, const int32_t* tri, int64_t nT, int32_t* out_child, int32_t* out_levels, int32_t* out_syncs)
+{
+    (void)nV;
+    g_ref_sorts = 0;
+    if (nT <= 0) return 0;
+    const WnRefLayout L = wn_ref_layout(nT, 64);
+    std::vector<char> mem(L.total + 256);
+    char* base = mem.data() + (256 - ((uintptr_t)mem.data() & 255)) % 256;
+    std::vector<int> child_out(((size_t)nT + 2) * 4, -1);
+    WnRefState rs;
+    memset(&rs, 0, sizeof(rs));
+    rs.N = (int)nT;
+    rs.tbox = (const float4*)(base + L.tbox);
+    rs.idx = (unsigned*)(base + L.idx);
+    rs.idx_alt = (unsigned*)(base + L.idx_alt);
+    rs.owner = (int*)(base + L.owner);
+    rs.flag = (uint32_t*)(base + L.flag);
+    rs.nodes = (WnRefNode*)(base + L.nodes);
+    rs.next = (WnRefNode*)(base + L.next);
+    rs.tasks = (WnRefTask*)(base + L.tasks);
+    rs.rows = (int*)(base + L.rows);
+    rs.copen = (uint32_t*)(base + L.copen);
+    rs.cnode = (uint32_t*)(base + L.cnode);
+    rs.child_tmp = (int*)(base + L.child_tmp);
+    rs.info_start = (int*)(base + L.info_start);
+    rs.info_depth = (int*)(base + L.info_depth);
+    rs.info_chain = (int*)(base + L.info_chain);
+    rs.cnt_start = (uint32_t*)(base + L.cnt_start);
+    rs.final_of = (int*)(base + L.final_of);
+    rs.keys = (uint64_t*)(base + L.keys);
+    rs.res = (int*)(base + L.res);
+    rs.child_out = child_out.data();
+    RefHostBackend B;
+    B.for_each(nT, WnRefTriBoxes{v, tri, (float4*)(base + L.tbox), rs.idx, rs.owner});
+    int n_nodes = 0, n_levels = 0;
+    if (!wn_ref_build_topology(B, rs, &n_nodes, &n_levels)) return -1;
+    memcpy(out_child, child_out.data(), (size_t)n_nodes * 4 * sizeof(int));
+    if (out_levels) *out_levels = n_levels;
+    if (out_syncs) *out_syncs = B.syncs;
+    return n_nodes;
+}
+
+int emul_ref_last_sorts(void)
+{
+    return g_ref_sorts;
 }
 
 void emul_destroy(void* h)
