@@ -27,16 +27,31 @@ struct wn_engine;
 namespace lagrange {
 namespace winding {
 
+/// Hierarchy built on the GPU (wn_hierarchy of the C-ABI, include/wn_b200.h).
+enum class Hierarchy : int {
+    Reference = 3, ///< the reference builder's own 4-ary SAH tree (UT_BVH<4>), reproduced on the GPU: results match the
+                   ///< reference algorithm to float rounding. Default: this class is a drop-in.
+    Lbvh = 0, ///< Morton codes + Karras: fastest build, ~20 % slower queries, results ~1e-3 from the reference's
+    Kd = 1, ///< balanced k-d (object-median splits)
+    KdSah = 2, ///< k-d with binned-SAH cuts and multi-triangle leaves: slightly faster queries than Reference
+};
+
 /// Build / query options that the reference hard-codes (UT_SolidAngle defaults: order 2, accuracy scale 2).
 struct FastWindingNumberOptions
 {
     float accuracy_scale = 2.f; ///< beta: a cluster is expanded when |q - P| > beta * R
     int order = 2; ///< Taylor order of the far field (0, 1, 2)
-    int leaf_size = 1; ///< max triangles per LBVH leaf (1..16)
-    int morton_bits = 63; ///< 30 or 63
-    bool vertex_radius = false; ///< exact cluster radius instead of the reference's box-corner bound
-    bool balanced_hierarchy = false; ///< balanced k-d tree (faster queries, slower build) instead of the Morton LBVH
+    Hierarchy hierarchy = Hierarchy::Reference;
+    int leaf_size = 1; ///< max triangles per leaf (1..16); ignored by Hierarchy::Reference (one triangle per leaf slot)
+    int morton_bits = 63; ///< Hierarchy::Lbvh: 30 or 63
+    bool vertex_radius = false; ///< exact cluster radius instead of the reference's box-corner bound (changes results)
+    bool balanced_hierarchy = false; ///< deprecated spelling of hierarchy = Hierarchy::Kd
     int device = -1; ///< CUDA device, -1 = current
+    /// The reference-surface single-point overloads is_inside(pos) / solid_angle(pos) are called once per voxel from many
+    /// host threads (modules/volume/src/mesh_to_volume.cpp:175-183). true (default): they walk a HOST copy of the packed
+    /// tree (made on first use, lock-free afterwards, ~1-3 us per call and thread). false: every call is a kernel launch
+    /// (~85 us, serialised per engine). Batched overloads always run on the GPU.
+    bool host_single_point = true;
 };
 
 /// Lattice p(i,j,k) = origin + spacing * ((i,j,k) + 1/2), x fastest: the samples mesh_to_volume evaluates
@@ -75,6 +90,9 @@ public:
     /// Whole lattice or the z-slab [z_begin, z_end); outputs hold dims[0]*dims[1]*(z_end - z_begin) values.
     void is_inside(const Lattice& lattice, uint8_t* out, int64_t z_begin = 0, int64_t z_end = -1) const;
     void solid_angle(const Lattice& lattice, float* out, int64_t z_begin = 0, int64_t z_end = -1) const;
+    /// Same classification, one BIT per lattice point: point i -> bit (i & 7) of out[i >> 3]; out holds
+    /// (dims[0]*dims[1]*(z_end - z_begin) + 7) / 8 bytes. An eighth of the device-to-host traffic of the byte overload.
+    void is_inside_bits(const Lattice& lattice, uint8_t* out, int64_t z_begin = 0, int64_t z_end = -1) const;
     /// Narrow-band signed distance at the lattice's cell centres: min(distance to the mesh, band), negative where is_inside
     /// holds; what volume::mesh_to_volume asks of OpenVDB with Sign::WindingNumber (mesh_to_volume.cpp:160-183, band = 3 voxels).
     /// Returns the number of cells with distance < band. signed_distance = false skips the predicate.

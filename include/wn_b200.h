@@ -80,7 +80,7 @@ typedef struct wn_options {
                                              always evaluated exactly (cheaper and more accurate). Imported topologies
                                              default to 1, the LBVH build to 0 */
     int32_t keep_build_data;  /* 1 = keep per-node raw moments for wn_debug_node_moments */
-    int32_t hierarchy;        /* wn_hierarchy; ignored by wn_create_from_topology */
+    int32_t hierarchy;        /* wn_hierarchy (default WN_HIERARCHY_REFERENCE); ignored by wn_create_from_topology */
     int32_t reserved[6];
 } wn_options;
 

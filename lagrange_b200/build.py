@@ -51,11 +51,15 @@ def build_cuda(force=False, verbose=False):
 def build_host(force=False):
     src = os.path.join(ROOT, "src", "FastWindingNumber.cpp")
     hdrs = [os.path.join(ROOT, "include", "lagrange", "winding", "FastWindingNumber.h"),
-            os.path.join(ROOT, "include", "lagrange", "SurfaceMesh.h"), os.path.join(ROOT, "include", "wn_b200.h")]
+            os.path.join(ROOT, "include", "lagrange", "SurfaceMesh.h"), os.path.join(ROOT, "include", "wn_b200.h"),
+            os.path.join(CSRC, "wn_device.cuh"), os.path.join(CSRC, "wn_packed.h")]
     if not os.path.exists(src):
         return None
     if force or _newer(LIB_HOST, [src, LIB_CUDA] + hdrs):
-        cmd = [HOST_CXX, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-I", os.path.join(ROOT, "include"), "-o", LIB_HOST, src,
+        # x86-64-v3 (AVX2 + FMA: any host that carries a B200 has it) so that the single-point host traversal's fmaf() is one
+        # instruction; no contraction, so its accept test rounds like the device's unfused one
+        cmd = [HOST_CXX, "-O2", "-march=x86-64-v3", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", "-Wall", "-I", os.path.join(ROOT, "include"),
+               "-o", LIB_HOST, src,
                "-L", LIBDIR, "-lwn_b200", "-Wl,-rpath,$ORIGIN"]
         subprocess.run(cmd, check=True)
     test_src = os.path.join(ROOT, "tests", "cpp", "test_fast_winding_number.cpp")

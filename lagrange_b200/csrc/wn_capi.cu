@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "../../include/wn_b200.h"
+#include "wn_packed.h"
 #include "wn_query.cuh"
 #include "wn_kd.cuh"
 #include "wn_refbuild.cuh"
@@ -129,49 +130,11 @@ size_t align_up(size_t v, size_t a)
     return (v + a - 1) / a * a;
 }
 
-// Position independent packed tree: one device allocation, header first.
-struct PackedHeader
-{
-    uint64_t magic; // 'WNB200T4' (kMagic)
-    int64_t total_bytes;
-    int64_t n_entries;
-    int64_t n_tris;
-    int64_t off_hot;  // float4[2 * n_entries]: (P, R2 | leaf), (N, link bits)
-    int64_t off_cold; // float4[4 * n_entries]: quadratic + cubic form
-    int64_t off_kids;
-    int64_t off_tris;
-    int64_t off_tri_order;
-    int32_t width;
-    int32_t order;
-    float accuracy_scale;
-    int32_t max_depth;
-    int64_t n_leaf_entries;
-    int64_t num_vertices;
-    int64_t num_tree_nodes;
-    int64_t reserved[3];
-};
-constexpr uint64_t kMagic = 0x3454303032424e57ull; // 'WNB200T4' (T4: paired coefficient order, wn_pack_record)
-
+using PackedHeader = WnPackedHeader; // wn_packed.h: shared with the C++ host layer (single-point queries on a host copy)
+constexpr uint64_t kMagic = WN_PACKED_MAGIC;
 PackedHeader make_header(int64_t n_entries, int64_t n_tris)
 {
-    PackedHeader h;
-    memset(&h, 0, sizeof(h));
-    h.magic = kMagic;
-    size_t off = align_up(sizeof(PackedHeader), 256);
-    h.off_hot = (int64_t)off;
-    off = align_up(off + (size_t)n_entries * 2 * sizeof(float4), 256);
-    h.off_cold = (int64_t)off;
-    off = align_up(off + (size_t)n_entries * 4 * sizeof(float4), 256);
-    h.off_kids = (int64_t)off;
-    off = align_up(off + (size_t)n_entries * sizeof(int4), 256);
-    h.off_tris = (int64_t)off;
-    off = align_up(off + (size_t)n_tris * 3 * sizeof(float4), 256);
-    h.off_tri_order = (int64_t)off;
-    off = align_up(off + (size_t)n_tris * sizeof(unsigned), 256);
-    h.total_bytes = (int64_t)off;
-    h.n_entries = n_entries;
-    h.n_tris = n_tris;
-    return h;
+    return wn_packed_make_header(n_entries, n_tris);
 }
 
 } // namespace
@@ -388,7 +351,7 @@ wn_status create_impl(const float* v_xyz, int64_t nV, const int32_t* tri, int64_
     // WN_HIERARCHY_REFERENCE: the reference builder's 4-ary tree is built on the device (K3R, wn_refbuild.cuh) and then takes
     // the same route as a caller-supplied topology (moments, radii, packing): one triangle per leaf slot, single triangles
     // approximated like the reference does.
-    const bool refh = !child_in && opt_in && opt_in->struct_size == sizeof(wn_options) && opt_in->hierarchy == WN_HIERARCHY_REFERENCE && nT > 0;
+    const bool refh = !child_in && nT > 0 && (!opt_in || (opt_in->struct_size == sizeof(wn_options) && opt_in->hierarchy == WN_HIERARCHY_REFERENCE));
     const bool imported = child_in != nullptr || refh;
     if (refh) {
         width = 4;
@@ -703,6 +666,8 @@ wn_status create_impl(const float* v_xyz, int64_t nV, const int32_t* tri, int64_
             WN_CUDA_C(cudaMemcpyAsync(&h_err, d_small + 6, sizeof(int), cudaMemcpyDeviceToHost, st));
             WN_CUDA_C(cudaStreamSynchronize(st));
             if (h_err) return cleanup(fail(WN_ERR_INVALID_ARGUMENT, "triangle references a vertex index outside [0, num_vertices)"));
+            tm.mark(); // 1: vertex indices checked
+            tm.mark(); // 2: (no sort in this builder)
             const size_t scan_bytes = (size_t)wn::scan_scratch_elems(nT) * 4 + 256;
             const WnRefLayout L = wn_ref_layout(nT, scan_bytes);
             char* base = nullptr;
@@ -766,10 +731,12 @@ wn_status create_impl(const float* v_xyz, int64_t nV, const int32_t* tri, int64_
         WN_CUDA_C(cudaMemsetAsync(b.slot, 0, (size_t)nN, st));
         b.err = d_small + 6;
         // vertex index validation (the LBVH path does it in k_centroid_bounds)
-        wn::k_centroid_bounds<<<std::min(wn::grid_for(nT), 148 * 8), wn::kBuildThreads, 0, st>>>(d_v, d_tri, (int)nT, (int)nV, d_small, d_small + 6);
-        tm.mark(); // 1
+        if (!refh) {
+            wn::k_centroid_bounds<<<std::min(wn::grid_for(nT), 148 * 8), wn::kBuildThreads, 0, st>>>(d_v, d_tri, (int)nT, (int)nV, d_small, d_small + 6);
+            tm.mark(); // 1
+        }
         wn::k_iota<<<wn::grid_for(nT), wn::kBuildThreads, 0, st>>>(d_prim, (int)nT);
-        tm.mark(); // 2
+        if (!refh) tm.mark(); // 2
         wn::k_import_topology<<<wn::grid_for(b.nI), wn::kBuildThreads, 0, st>>>(b, d_child_in, d_seen);
         wn::k_import_check<<<wn::grid_for(nN), wn::kBuildThreads, 0, st>>>(b, d_seen);
         WN_CUDA_C(cudaGetLastError());
@@ -1430,7 +1397,7 @@ wn_status wn_options_init(wn_options* opt)
     opt->radius_mode = WN_RADIUS_BOX_CORNER;
     opt->approximate_single_triangles = 0;
     opt->keep_build_data = 0;
-    opt->hierarchy = WN_HIERARCHY_LBVH;
+    opt->hierarchy = WN_HIERARCHY_REFERENCE; // the drop-in default: the reference builder's own tree, results match the reference algorithm
     return WN_OK;
 }
 

@@ -100,7 +100,7 @@ class FastWindingNumber:
     """
 
     def __init__(self, mesh=None, facets=None, *, accuracy_scale=2.0, order=2, topology=None, leaf_size=1, morton_bits=63,
-                 radius_mode="box_corner", approximate_single_triangles=None, keep_build_data=False, device=None, hierarchy="lbvh",
+                 radius_mode="box_corner", approximate_single_triangles=None, keep_build_data=False, device=None, hierarchy="reference",
                  _handle=None):
         self._h = None
         self._lib = _capi.lib()

@@ -7,7 +7,14 @@
 
 #include <wn_b200.h>
 
+// The single-point overloads of the reference surface walk a host copy of the packed tree with the engine's own per-point
+// traversal (wn_traverse_point: the definition the warp kernels mirror lane-wise), compiled here for the host. This is the
+// library's code, not the test oracle; everything batched runs on the GPU and fails loudly without one.
+#include "../lagrange_b200/csrc/wn_device.cuh"
+#include "../lagrange_b200/csrc/wn_packed.h"
+
 #include <limits>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -25,7 +32,51 @@ struct FastWindingNumber::Impl
 {
     wn_engine* engine = nullptr;
     float beta = 2.f;
+    bool host_single_point = true;
+    // host copy of the packed tree for the single-point overloads: made once, on first use, read-only afterwards
+    mutable std::once_flag host_once;
+    mutable std::vector<char> host_blob;
+    mutable WnTreeView host_view{};
+    mutable std::string host_error;
     ~Impl() { wn_destroy(engine); }
+
+    const WnTreeView* host_tree() const
+    {
+        std::call_once(host_once, [this]() {
+            int64_t nbytes = 0;
+            if (wn_tree_packed_size(engine, &nbytes) != WN_OK || nbytes < (int64_t)sizeof(WnPackedHeader)) {
+                host_error = wn_last_error();
+                return;
+            }
+            host_blob.resize(static_cast<size_t>(nbytes) + 64);
+            char* base = host_blob.data() + (64 - (reinterpret_cast<uintptr_t>(host_blob.data()) & 63)) % 64; // float4 loads want 16-byte alignment
+            if (wn_tree_pack(engine, base, nbytes, nullptr) != WN_OK) {
+                host_error = wn_last_error();
+                host_blob.clear();
+                return;
+            }
+            WnPackedHeader h;
+            memcpy(&h, base, sizeof(h));
+            if (h.magic != WN_PACKED_MAGIC || h.total_bytes > nbytes) {
+                host_error = "packed tree header mismatch";
+                host_blob.clear();
+                return;
+            }
+            host_view.hot = reinterpret_cast<const float4*>(base + h.off_hot);
+            host_view.cold = reinterpret_cast<const float4*>(base + h.off_cold);
+            host_view.kids = reinterpret_cast<const int4*>(base + h.off_kids);
+            host_view.tri = reinterpret_cast<const float4*>(base + h.off_tris);
+            host_view.n_entries = static_cast<int>(h.n_entries);
+            host_view.n_tris = static_cast<int>(h.n_tris);
+        });
+        if (host_blob.empty()) throw Error(std::string("FastWindingNumber: cannot copy the tree to the host: ") + host_error);
+        return &host_view;
+    }
+    float host_solid_angle(const std::array<float, 3>& pos) const
+    {
+        const WnTreeView* t = host_tree();
+        return wn_traverse_point(*t, pos[0], pos[1], pos[2], beta * beta, nullptr);
+    }
 };
 
 void FastWindingNumber::initialize(const float* vertices, int64_t num_vertices, const int32_t* triangles, int64_t num_triangles,
@@ -37,11 +88,12 @@ void FastWindingNumber::initialize(const float* vertices, int64_t num_vertices, 
     opt.order = options.order;
     opt.leaf_size = options.leaf_size;
     opt.morton_bits = options.morton_bits;
-    opt.hierarchy = options.balanced_hierarchy ? WN_HIERARCHY_KD : WN_HIERARCHY_LBVH;
+    opt.hierarchy = options.balanced_hierarchy ? WN_HIERARCHY_KD : static_cast<int>(options.hierarchy);
     opt.radius_mode = options.vertex_radius ? WN_RADIUS_VERTEX : WN_RADIUS_BOX_CORNER;
     opt.device = options.device;
     m_impl = std::make_unique<Impl>();
     m_impl->beta = options.accuracy_scale;
+    m_impl->host_single_point = options.host_single_point;
     check(wn_create(vertices, num_vertices, triangles, num_triangles, &opt, &m_impl->engine));
 }
 
@@ -83,6 +135,7 @@ const wn_engine* FastWindingNumber::engine() const
 bool FastWindingNumber::is_inside(const std::array<float, 3>& pos) const
 {
     const wn_engine* e = engine(); // throws on an empty engine before m_impl is touched
+    if (m_impl->host_single_point) return wn_inside_from_omega(m_impl->host_solid_angle(pos));
     uint8_t r = 0;
     check(wn_is_inside(e, pos.data(), 1, m_impl->beta, WN_QUERY_PRESORTED, &r, nullptr));
     return r != 0;
@@ -91,6 +144,7 @@ bool FastWindingNumber::is_inside(const std::array<float, 3>& pos) const
 float FastWindingNumber::solid_angle(const std::array<float, 3>& pos) const
 {
     const wn_engine* e = engine();
+    if (m_impl->host_single_point) return m_impl->host_solid_angle(pos);
     float r = 0;
     check(wn_solid_angle(e, pos.data(), 1, m_impl->beta, WN_QUERY_PRESORTED, &r, nullptr));
     return r;
@@ -113,6 +167,13 @@ void FastWindingNumber::is_inside(const Lattice& l, uint8_t* out, int64_t z_begi
     const wn_engine* e = engine();
     check(wn_query_grid(e, l.origin.data(), l.spacing.data(), l.dims.data(), z_begin, z_end < 0 ? l.dims[2] : z_end, m_impl->beta, WN_QUERY_DEFAULT, nullptr,
                         out, nullptr));
+}
+
+void FastWindingNumber::is_inside_bits(const Lattice& l, uint8_t* out, int64_t z_begin, int64_t z_end) const
+{
+    const wn_engine* e = engine();
+    check(wn_query_grid(e, l.origin.data(), l.spacing.data(), l.dims.data(), z_begin, z_end < 0 ? l.dims[2] : z_end, m_impl->beta, WN_QUERY_OUT_BITS,
+                        nullptr, out, nullptr));
 }
 
 void FastWindingNumber::solid_angle(const Lattice& l, float* out, int64_t z_begin, int64_t z_end) const

@@ -225,6 +225,77 @@ int main()
         CHECK(bad == 0);
     }
 
+    // --- the reference's production calling pattern: one is_inside per voxel from many worker threads (OpenVDB's TBB pool,
+    //     modules/volume/src/mesh_to_volume.cpp:175-183). The single-point overloads walk a host copy of the packed tree: no
+    //     launch, no lock. 16 threads x 10 000 calls; and the answers are those of the batched GPU traversal. ------------------
+    {
+        const int T = 16;
+        const size_t per = 10000;
+        std::vector<std::vector<std::array<float, 3>>> pts(T);
+        for (int t = 0; t < T; ++t) {
+            std::mt19937 gen(1234u + t);
+            pts[t].resize(per);
+            for (auto& s : pts[t]) s = {px(gen), py(gen), pz(gen)};
+        }
+        engine.is_inside(pts[0][0]); // first use copies the tree to the host
+        std::vector<size_t> inside(T, 0);
+        const auto a0 = std::chrono::steady_clock::now();
+        std::vector<std::thread> pool;
+        for (int t = 0; t < T; ++t)
+            pool.emplace_back([&, t]() {
+                size_t c = 0;
+                for (const auto& s : pts[t]) c += engine.is_inside(s);
+                inside[t] = c;
+            });
+        for (auto& th : pool) th.join();
+        const auto a1 = std::chrono::steady_clock::now();
+        const double sec = std::chrono::duration<double>(a1 - a0).count();
+        const double rate = double(T) * double(per) / sec;
+        std::printf("single-point overload from %d host threads (%u hardware threads): %zu calls in %.2f ms = %.2f M calls/s aggregate\n", T,
+                    std::thread::hardware_concurrency(), size_t(T) * per, 1e3 * sec, rate / 1e6);
+        CHECK(rate > 1.0e6);
+        // same points through the batched overload (GPU, per-point traversal semantics)
+        size_t differ = 0, near_half = 0;
+        double worst = 0;
+        for (int t = 0; t < 2; ++t) {
+            std::vector<uint8_t> b(per);
+            std::vector<float> om(per);
+            engine.is_inside(pts[t][0].data(), per, b.data());
+            engine.solid_angle(pts[t][0].data(), per, om.data());
+            for (size_t i = 0; i < per; ++i) {
+                const float h = engine.solid_angle(pts[t][i]);
+                worst = std::max(worst, double(std::fabs(h - om[i])) / four_pi);
+                if (engine.is_inside(pts[t][i]) != (b[i] != 0)) {
+                    ++differ;
+                    near_half += std::fabs(om[i] / four_pi - 0.5f) < 1e-4f;
+                }
+            }
+        }
+        std::printf("host single-point vs batched GPU traversal: max |dw| = %.3e, is_inside differs on %zu points (%zu of them within 1e-4 of w = 1/2)\n",
+                    worst, differ, near_half);
+        CHECK(worst < 2e-5);
+        CHECK(differ == near_half);
+        // the launch-per-call variant still exists (options.host_single_point = false) and agrees
+        lagrange::winding::FastWindingNumberOptions o2;
+        o2.host_single_point = false;
+        lagrange::winding::FastWindingNumber launch_engine(mesh, o2);
+        size_t d2 = 0;
+        for (size_t i = 0; i < 200; ++i) d2 += launch_engine.is_inside(pts[0][i]) != engine.is_inside(pts[0][i]);
+        CHECK(d2 == 0);
+        // bit-packed lattice overload
+        lagrange::winding::Lattice lat;
+        lat.origin = {-6.5f, -1.5f, -6.5f};
+        lat.spacing = {13.f / 37, 3.f / 13, 13.f / 41};
+        lat.dims = {37, 13, 41};
+        const size_t n = 37 * 13 * 41;
+        std::vector<uint8_t> bytes(n), bits((n + 7) / 8);
+        engine.is_inside(lat, bytes.data());
+        engine.is_inside_bits(lat, bits.data());
+        size_t bitdiff = 0;
+        for (size_t i = 0; i < n; ++i) bitdiff += ((bits[i >> 3] >> (i & 7)) & 1) != bytes[i];
+        CHECK(bitdiff == 0);
+    }
+
     std::printf(g_failures ? "FAILED (%d)\n" : "ALL PASSED\n", g_failures);
     return g_failures ? 1 : 0;
 }

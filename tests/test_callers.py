@@ -98,7 +98,7 @@ def test_fix_orientation_gpu_equals_oracle(prim, oracle_mod):
 
     V, F = prim.generate_torus(5, 1, 60, 30)
     G, flipped = flipped_copy(F, 0.1, 7)
-    eng = lb.FastWindingNumber(V, F)
+    eng = lb.FastWindingNumber(V, F, hierarchy="lbvh")
     got_F, got_c, counts = callers.fix_orientation(V, G, eng)
     want_F, want_c, _ = callers.fix_orientation(V, G, oracle_mod.RefEngine(V, F))
     assert np.array_equal(got_F, F) and np.array_equal(got_F, want_F)
@@ -115,7 +115,7 @@ def test_sample_points_in_mesh_gpu(prim, oracle_mod):
 
     V, F = prim.generate_torus(5, 1, 60, 30)
     lo, hi = V.min(axis=0), V.max(axis=0)
-    eng = lb.FastWindingNumber(V, F)
+    eng = lb.FastWindingNumber(V, F, hierarchy="lbvh")
     pts = callers.sample_points_in_mesh(eng, lo, hi, 10000)
     ref_pts = callers.sample_points_in_mesh(oracle_mod.RefEngine(V, F), lo, hi, 10000)
     # same stream, same predicate: the kept sets can differ only for samples within the trees' error of w = 0.5

@@ -35,7 +35,7 @@ def test_cfg2_full_size_oracle_tree_parity(lb, oracle_mod, prim):
     assert np.array_equal(ins[m], ins_ref[m])
     assert int((ins != ins_ref).sum()) <= 8  # only inside the 1e-3 band around w = 1/2
     # the product build (LBVH) on the same lattice: classification agrees away from the surface shell
-    eng2 = lb.FastWindingNumber(V, F)
+    eng2 = lb.FastWindingNumber(V, F, hierarchy="lbvh")
     ins2 = eng2.query_grid(o, s, d)[1]
     assert np.array_equal(ins2[m], ins_ref[m]) or int((ins2[m] != ins_ref[m]).sum()) <= 16
     # analytic: the unit sphere
@@ -58,7 +58,7 @@ def test_cfg3_full_size_open_soup(lb, oracle_mod, prim):
     m = band_mask(w_ref)
     assert np.array_equal(ins_t[m], ins_ref[m])
     # product build: different tree => both are ~1e-3 from the exact winding number; agreement outside the widened band
-    eng = lb.FastWindingNumber(V, F)
+    eng = lb.FastWindingNumber(V, F, hierarchy="lbvh")
     om, ins = eng.query_grid(o, s, d, want_omega=True)
     sub = slice(None, None, 4099)
     P = prim.lattice_points(o, s, d)[sub]
@@ -76,7 +76,7 @@ def test_cfg4_full_size_deep_traversal(lb, oracle_mod, prim):
     V, F = prim.config_mesh(4)
     assert len(F) == 8 * 4**10
     q = prim.near_surface_points(V, F, 64 << 20, seed=0xC0FFEE04)
-    eng = lb.FastWindingNumber(V, F)
+    eng = lb.FastWindingNumber(V, F, hierarchy="lbvh")
     info = eng.info
     assert info["num_entries"] == 2 * len(F) - 1
     ins = eng.is_inside(q)
@@ -105,7 +105,7 @@ def test_cfg5_full_size_exact_vs_tree_sweep(lb, oracle_mod, prim):
     V, F = prim.config_mesh(5)
     assert len(F) == 100_000
     q = prim.uniform_points_in_bbox(*prim.mesh_bbox(V), 1 << 24, seed=0xC0FFEE05)
-    eng = lb.FastWindingNumber(V, F)
+    eng = lb.FastWindingNumber(V, F, hierarchy="lbvh")
     dq = torch.from_numpy(q).cuda()
     exact = eng.exact_solid_angle(dq)  # 1.7e12 triangle-point pairs on the device
     ex64 = oracle_mod.exact64(V, F, q[:: 1 << 14])
@@ -124,13 +124,15 @@ def test_cfg5_full_size_exact_vs_tree_sweep(lb, oracle_mod, prim):
     assert torch.equal(ins[m], ins_exact[m])
 
 
-def test_cfg2_full_size_bench_configuration(lb, oracle_mod, prim):
-    """What bench.py measures, at full size: k-d hierarchy with SAH-guided cuts, 4-triangle leaves, tiled path, 512^3 lattice.
-    Against the restatement on every lattice point (different trees: agreement outside the band widened by both trees'
-    error), against the exact winding number on a sample, and against the analytic volume of the unit sphere."""
+@pytest.mark.parametrize("hierarchy,leaf", [("reference", 1), ("kd_sah", 4)])
+def test_cfg2_full_size_bench_configuration(lb, oracle_mod, prim, hierarchy, leaf):
+    """What bench.py measures, at full size (512^3 lattice, tiled path). bench.py's default is the reference hierarchy; kd_sah with
+    4-triangle leaves (round 1's bench configuration) is kept as the alternative. Against the restatement on EVERY lattice point
+    with the strict 1e-3 band of BASELINE.json (the mismatch count is printed and asserted), against the exact winding number on
+    a sample, and against the analytic volume of the unit sphere. Parity is against this repo's restatement, not the upstream binary."""
     V, F = prim.config_mesh(2)
     _, (o, s, d) = prim.config_queries(2, V, F)
-    eng = lb.FastWindingNumber(V, F, hierarchy="kd_sah", leaf_size=4)
+    eng = lb.FastWindingNumber(V, F, hierarchy=hierarchy, leaf_size=leaf)
     om, ins = eng.query_grid(o, s, d, want_omega=True, want_inside=True)
     # same engine, per-point traversal instead of tiles: the far-set interpolation is the only difference
     om_g = eng.query_grid(o, s, d, want_omega=True, want_inside=False, tiling=False)[0]
@@ -145,13 +147,47 @@ def test_cfg2_full_size_bench_configuration(lb, oracle_mod, prim):
     w_ex = eng.exact_solid_angle(P) / FOUR_PI
     err = np.abs(om[sub] / FOUR_PI - w_ex)
     assert err.max() < 6e-3 and err.mean() < 1e-3, (err.max(), err.mean())
-    clear = band_mask(w_ex, band=1e-3 + 2.0 * err.max())
-    assert np.array_equal(ins[sub][clear].astype(bool), (w_ex > 0.5)[clear])
-    # the restatement on every lattice point
+    # the restatement on every lattice point, strict band
     ref = oracle_mod.RefEngine(V, F)
     ins_ref, om_ref = ref.grid(o, s, d, want_omega=True)
-    err_ref = np.abs(om_ref[sub] / FOUR_PI - w_ex).max()
-    wide = band_mask(om_ref / FOUR_PI, band=1e-3 + 2.0 * (err.max() + err_ref))
-    assert np.array_equal(ins[wide], ins_ref[wide])
-    assert np.mean(ins != ins_ref) < 1e-4
+    strict = band_mask(om_ref / FOUR_PI, 1e-3)
+    mism = int((ins[strict] != ins_ref[strict]).sum())
+    domega = float(np.abs(om - om_ref).max()) / FOUR_PI
+    print(f"cfg2 {hierarchy}/leaf {leaf}: is_inside mismatches vs the restatement outside |w-0.5|<=1e-3: {mism} of {int(strict.sum())} "
+          f"(anywhere: {int((ins != ins_ref).sum())}); max |dOmega| = {domega:.2e} * 4pi; error vs exact: max {err.max():.2e} mean {err.mean():.2e}")
+    if hierarchy == "reference":
+        assert mism == 0 and domega < 1e-4
+    else:
+        # a different tree: both trees are ~1e-3 from the exact winding number, so the strict band is not a guarantee; the count
+        # is reported and bounded here
+        assert mism <= 64
+        err_ref = np.abs(om_ref[sub] / FOUR_PI - w_ex).max()
+        wide = band_mask(om_ref / FOUR_PI, band=1e-3 + 2.0 * (err.max() + err_ref))
+        assert np.array_equal(ins[wide], ins_ref[wide])
     assert abs(float(ins.sum()) * float(np.prod(s)) - 4.0 / 3.0 * np.pi) < 2e-3
+
+
+@pytest.mark.parametrize("cfg", [3, 4, 5])
+def test_kd_sah_leaf4_full_size_strict_band_counts(lb, oracle_mod, prim, cfg):
+    """the alternative hierarchy (kd_sah, 4-triangle leaves) at full size on cfg3 / cfg4 / cfg5 — strict-band
+    mismatch counts against the restatement (bounded samples for the point-set configs), printed and bounded."""
+    V, F = prim.config_mesh(cfg)
+    eng = lb.FastWindingNumber(V, F, hierarchy="kd_sah", leaf_size=4)
+    ref = oracle_mod.RefEngine(V, F)
+    if cfg == 3:
+        _, (o, s, d) = prim.config_queries(cfg, V, F)
+        ins = eng.query_grid(o, s, d)[1]
+        ins_ref, om_ref = ref.grid(o, s, d, want_omega=True)
+    else:
+        q = prim.near_surface_points(V, F, 1 << 20, seed=0xC0FFEE04) if cfg == 4 else prim.uniform_points_in_bbox(*prim.mesh_bbox(V), 1 << 21, seed=0xC0FFEE05)
+        ins = eng.is_inside(q)
+        om_ref = ref.solid_angle(q)
+        ins_ref = ref.is_inside(q)
+    w_ref = om_ref / FOUR_PI
+    strict = band_mask(w_ref, 1e-3)
+    mism = int((ins[strict] != ins_ref[strict]).sum())
+    wide = band_mask(w_ref, 2e-2)
+    print(f"cfg{cfg} kd_sah/leaf 4: strict-band mismatches vs the restatement {mism} of {int(strict.sum())}; outside |w-0.5|<=2e-2: "
+          f"{int((ins[wide] != ins_ref[wide]).sum())}")
+    assert np.array_equal(ins[wide], ins_ref[wide])
+    assert mism <= 1e-4 * len(ins)

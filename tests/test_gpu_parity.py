@@ -107,7 +107,7 @@ def test_golden_fixtures(lb, path):
 @pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5])
 def test_lbvh_build_matches_host_emulation_and_exact(lb, oracle_mod, emul_mod, prim, cfg):
     V, F, q, lattice = small_config(prim, cfg)
-    eng = lb.FastWindingNumber(V, F, keep_build_data=True)
+    eng = lb.FastWindingNumber(V, F, hierarchy="lbvh", keep_build_data=True)
     em = emul_mod.EmulEngine(V, F)
     # K1-K3: same Morton order and Karras topology as the sequential emulation of the same source
     assert np.array_equal(eng.debug_topology(), em.topology())
@@ -140,7 +140,7 @@ def test_lbvh_build_matches_host_emulation_and_exact(lb, oracle_mod, emul_mod, p
                                   dict(order=1), dict(order=0), dict(approximate_single_triangles=True)])
 def test_lbvh_options_match_host_emulation(lb, emul_mod, prim, opts):
     V, F, q, _ = small_config(prim, 1)
-    eng = lb.FastWindingNumber(V, F, **opts)
+    eng = lb.FastWindingNumber(V, F, hierarchy="lbvh", **opts)
     ekw = dict(opts)
     if "radius_mode" in ekw:
         ekw["radius_mode"] = 1
@@ -158,7 +158,7 @@ TOL_TILE = 3e-5 * FOUR_PI  # far-field interpolation of the tiled path (measured
 def test_results_do_not_depend_on_batch_composition(lb, prim):
     """Generic traversal: a point's result is bit-identical whatever else is in its warp / batch."""
     V, F = prim.generate_torus(5, 1, 60, 30)
-    eng = lb.FastWindingNumber(V, F)
+    eng = lb.FastWindingNumber(V, F, hierarchy="lbvh")
     q = prim.uniform_points_in_bbox(*prim.mesh_bbox(V), 50000, seed=11)
     base = eng.solid_angle(q, tiling=False)  # Morton-sorted internally
     assert np.array_equal(eng.solid_angle(q, presorted=True, tiling=False), base)  # original (incoherent) order, no sort
@@ -184,7 +184,7 @@ def test_results_do_not_depend_on_batch_composition(lb, prim):
 
 def test_grid_overload_equals_points_and_slabs_tile(lb, prim):
     V, F = prim.generate_torus(5, 1, 50, 24)
-    eng = lb.FastWindingNumber(V, F)
+    eng = lb.FastWindingNumber(V, F, hierarchy="lbvh")
     o, s, d = prim.lattice_for_bbox(*prim.mesh_bbox(V), (37, 11, 29))
     P = prim.lattice_points(o, s, d)
     om, ins = eng.query_grid(o, s, d, want_omega=True, want_inside=True, tiling=False)
@@ -216,7 +216,7 @@ def test_grid_overload_equals_points_and_slabs_tile(lb, prim):
 def test_strided_layers_tile_the_lattice(lb, prim):
     """Multi-GPU sharding primitive: layers r, r+N, ... of every rank together are the whole lattice, bit for bit."""
     V, F = prim.generate_subdivided_sphere("icosahedron", 4)
-    eng = lb.FastWindingNumber(V, F)
+    eng = lb.FastWindingNumber(V, F, hierarchy="lbvh")
     o, s, d = prim.lattice_for_bbox([-1.0] * 3, [1.0] * 3, (40, 24, 53))  # nz not a multiple of 8: partial last layer
     per = 40 * 24
     for tiling_env in ("0", "1"):
@@ -246,7 +246,7 @@ def test_tiled_path_matches_generic_traversal(lb, oracle_mod, prim, cfg, tree):
     if tree == "oracle":
         eng = lb.FastWindingNumber(V, F, topology=oracle_mod.RefEngine(V, F).topology())
     else:
-        eng = lb.FastWindingNumber(V, F, leaf_size=8 if tree == "lbvh_leaf8" else 1)
+        eng = lb.FastWindingNumber(V, F, hierarchy="lbvh", leaf_size=8 if tree == "lbvh_leaf8" else 1)
     os.environ["WN_TILE"] = "1"
     try:
         for beta in (2.0, 3.5):
@@ -273,7 +273,7 @@ def test_tiled_path_matches_generic_traversal(lb, oracle_mod, prim, cfg, tree):
 
 def test_tiled_path_survives_degenerate_tiles(lb, prim):
     V, F = prim.generate_torus(5, 1, 40, 20)
-    eng = lb.FastWindingNumber(V, F)
+    eng = lb.FastWindingNumber(V, F, hierarchy="lbvh")
     os.environ["WN_TILE"] = "1"
     try:
         # all points identical / collinear / containing NaN / a single point / exactly one tile + 1
@@ -303,7 +303,7 @@ def test_tiled_path_survives_degenerate_tiles(lb, prim):
 @pytest.mark.parametrize("n", [1, 100, 5000])
 def test_exact_mode_is_ground_truth(lb, oracle_mod, prim, n):
     V, F = prim.generate_torus(5, 1, 120, 50)  # 24 000 triangles: several chunks and tiles
-    eng = lb.FastWindingNumber(V, F)
+    eng = lb.FastWindingNumber(V, F, hierarchy="lbvh")
     q = prim.uniform_points_in_bbox(*prim.mesh_bbox(V), n, seed=n)
     ex = oracle_mod.exact64(V, F, q)
     om = eng.exact_solid_angle(q)
@@ -314,7 +314,7 @@ def test_exact_mode_is_ground_truth(lb, oracle_mod, prim, n):
 
 # ---- edge cases the reference's surface defines ------------------------------------------------------------------------------
 def test_edge_cases(lb, oracle_mod):
-    empty = lb.FastWindingNumber(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.int32))
+    empty = lb.FastWindingNumber(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.int32), hierarchy="lbvh")
     q = np.array([[0, 0, 0], [1, 2, 3]], dtype=np.float32)
     assert np.all(empty.solid_angle(q) == 0) and not empty.is_inside(q).any() and np.all(empty.exact_solid_angle(q) == 0)
     assert empty.solid_angle(np.zeros((0, 3), np.float32)).shape == (0,)
@@ -323,19 +323,19 @@ def test_edge_cases(lb, oracle_mod):
     qq = np.array([[0.1, 0.1, 0.1], [3, 3, 3], [0, 0, 0], [1, 0, 0], [0.25, 0.25, 0], [-1, 0.5, 0.2]], dtype=np.float32)
     ex = oracle_mod.exact64(V, F, qq)
     for kw in ({}, {"leaf_size": 4}, {"topology": oracle_mod.RefEngine(V, F).topology()}):
-        eng = lb.FastWindingNumber(V, F, **kw)
+        eng = lb.FastWindingNumber(V, F, hierarchy="lbvh", **kw)
         assert np.abs(eng.solid_angle(qq, accuracy_scale=50.0) - ex).max() < 1e-4
         assert np.abs(eng.exact_solid_angle(qq) - ex).max() < 1e-5
-    one = lb.FastWindingNumber(V, F[4:5])
+    one = lb.FastWindingNumber(V, F[4:5], hierarchy="lbvh")
     assert abs(one.solid_angle([0.1, 0.1, 0.1]) - oracle_mod.exact64(V, F[4:5], qq[:1])[0]) < 1e-5
     with pytest.raises(lb.Error, match="vertex index"):
-        lb.FastWindingNumber(V, np.array([[0, 1, 7]], dtype=np.int32))
+        lb.FastWindingNumber(V, np.array([[0, 1, 7]], dtype=np.int32), hierarchy="lbvh")
     with pytest.raises(lb.Error, match="topology"):
         lb.FastWindingNumber(V, F[:2], topology=np.array([[-2, -2, -1, -1]], dtype=np.int32))
     with pytest.raises(lb.Error):
-        lb.FastWindingNumber(V, F).solid_angle(np.zeros((4, 2), np.float32))
+        lb.FastWindingNumber(V, F, hierarchy="lbvh").solid_angle(np.zeros((4, 2), np.float32))
     # non-finite queries must not hang or poison their neighbours
-    eng = lb.FastWindingNumber(V, F)
+    eng = lb.FastWindingNumber(V, F, hierarchy="lbvh")
     bad = np.array([[np.nan, 0, 0], [0.1, 0.1, 0.1], [np.inf, 0, 0]], dtype=np.float32)
     r = eng.solid_angle(bad)
     assert abs(r[1] - eng.solid_angle([0.1, 0.1, 0.1])) == 0
@@ -345,7 +345,7 @@ def test_device_pointers_and_pack_roundtrip(lb, prim):
     import torch
 
     V, F = prim.generate_subdivided_sphere("icosahedron", 4)
-    eng = lb.FastWindingNumber(torch.from_numpy(V).cuda(), torch.from_numpy(F).cuda())  # device-resident mesh
+    eng = lb.FastWindingNumber(torch.from_numpy(V).cuda(), torch.from_numpy(F).cuda(), hierarchy="lbvh")  # device-resident mesh
     q = prim.uniform_points_in_bbox([-1.2] * 3, [1.2] * 3, 20000, seed=5)
     host = eng.solid_angle(q)
     dq = torch.from_numpy(q).cuda()
@@ -389,7 +389,7 @@ def test_cfg1_full_size_against_the_oracle(lb, oracle_mod, prim):
     _, lattice = prim.config_queries(1, V, F)
     ref = oracle_mod.RefEngine(V, F)
     eng_ref_tree = lb.FastWindingNumber(V, F, topology=ref.topology())
-    eng = lb.FastWindingNumber(V, F)
+    eng = lb.FastWindingNumber(V, F, hierarchy="lbvh")
     ins_ref, om_ref = ref.grid(*lattice, want_omega=True)
     om_t, ins_t = eng_ref_tree.query_grid(*lattice, want_omega=True)
     assert np.abs(om_t - om_ref).max() < TOL_OMEGA
@@ -410,7 +410,7 @@ def test_cfg2_full_size_sphere_properties(lb, prim):
 
     V, F = prim.config_mesh(2)
     assert len(F) == 1310720
-    eng = lb.FastWindingNumber(V, F)
+    eng = lb.FastWindingNumber(V, F, hierarchy="lbvh")
     info = eng.info
     assert info["num_entries"] == 2 * len(F) - 1 and info["build_ms"] > 0
     kind, (o, s, d) = prim.config_queries(2, V, F)
@@ -451,7 +451,7 @@ def test_kd_hierarchy_error_class_and_tiled_path(prim, oracle_mod):
 
     V, F, q, lattice = small_config(prim, 1)
     kd = lb.FastWindingNumber(V, F, hierarchy="kd")
-    lbvh = lb.FastWindingNumber(V, F)
+    lbvh = lb.FastWindingNumber(V, F, hierarchy="lbvh")
     w_exact = oracle_mod.exact64(V, F, q) / FOUR_PI
     e_kd = np.abs(kd.solid_angle(q) / FOUR_PI - w_exact)
     e_lb = np.abs(lbvh.solid_angle(q) / FOUR_PI - w_exact)
@@ -477,7 +477,7 @@ def test_kd_hierarchy_degenerate_inputs(prim):
     V = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], dtype=np.float32)
     for copies in (2, 3, 37):
         F = np.tile(np.array([[0, 1, 2]], dtype=np.int32), (copies, 1))
-        ref = lb.FastWindingNumber(V, F)
+        ref = lb.FastWindingNumber(V, F, hierarchy="lbvh")
         q = np.array([[0.2, 0.2, 0.5], [0.2, 0.2, -0.5], [3, 3, 3]], dtype=np.float32)
         for hierarchy in ("kd", "kd_sah"):
             eng = lb.FastWindingNumber(V, F, hierarchy=hierarchy)

@@ -67,7 +67,7 @@ def test_bit_packed_lattice_output_equals_bytes(lb, prim, dims, tiling):
 
 def test_bit_packed_point_output(lb, prim):
     V, F, P, _ = small_config(prim, 5)
-    eng = lb.FastWindingNumber(V, F)
+    eng = lb.FastWindingNumber(V, F, hierarchy="lbvh")
     for n in (1, 7, 8, 9, 1000, 4099, len(P)):
         ref = eng.is_inside(P[:n])
         bits = eng.is_inside(P[:n], bits=True)
@@ -92,7 +92,7 @@ def test_from_packed_keeps_the_accuracy_scale_of_the_tree(lb, prim):
     """a replica adopted with options (device=...) must keep the packed engine's beta, so that
     beta <= 0 queries answer identically on the source and on every replica."""
     V, F, P, _ = small_config(prim, 1)
-    src = lb.FastWindingNumber(V, F, accuracy_scale=3.0)
+    src = lb.FastWindingNumber(V, F, hierarchy="lbvh", accuracy_scale=3.0)
     blob = src.pack()
     rep = lb.FastWindingNumber.from_packed(blob, device=0)  # options given, accuracy_scale not
     assert rep.info["accuracy_scale"] == pytest.approx(3.0)
@@ -108,7 +108,7 @@ def test_from_packed_keeps_the_accuracy_scale_of_the_tree(lb, prim):
 def test_corrupted_packed_tree_is_rejected(lb, prim):
     """links / child indices / leaf ranges inside an adopted blob are validated on the device."""
     V, F = prim.generate_torus(5.0, 1.0, 24, 12)
-    src = lb.FastWindingNumber(V, F)
+    src = lb.FastWindingNumber(V, F, hierarchy="lbvh")
     blob = src.pack()
     hdr = np.frombuffer(blob[:128].tobytes(), dtype=np.int64)
     n_entries, off_hot, off_kids = int(hdr[2]), int(hdr[4]), int(hdr[6])
@@ -145,7 +145,7 @@ def test_corrupted_packed_tree_is_rejected(lb, prim):
 def test_oversized_lattices_are_rejected_not_wrapped(lb, prim):
     """dims up to 2^24 each used to overflow the point count."""
     V, F = prim.generate_torus(5.0, 1.0, 24, 12)
-    eng = lb.FastWindingNumber(V, F)
+    eng = lb.FastWindingNumber(V, F, hierarchy="lbvh")
     from lagrange_b200 import _capi
 
     L = _capi.lib()

@@ -52,7 +52,7 @@ def test_sdf_grid_matches_brute_force(prim, oracle_mod, leaf_size):
     import lagrange_b200 as lb
 
     V, F = prim.generate_torus(5, 1, 40, 20)
-    eng = lb.FastWindingNumber(V, F, leaf_size=leaf_size)
+    eng = lb.FastWindingNumber(V, F, hierarchy="lbvh", leaf_size=leaf_size)
     origin, spacing, dims = prim.lattice_for_bbox(V.min(axis=0), V.max(axis=0), (37, 19, 41), inflate=0.1)
     band = 4.5 * float(spacing[0])
     sdf, active = eng.sdf_grid(origin, spacing, dims, band)
@@ -76,7 +76,7 @@ def test_sdf_grid_open_soup_and_device_output(prim, oracle_mod):
     import lagrange_b200 as lb
 
     V, F = prim.config_mesh(3, small=True)  # open, non-manifold soup
-    eng = lb.FastWindingNumber(V, F)
+    eng = lb.FastWindingNumber(V, F, hierarchy="lbvh")
     origin, spacing, dims = prim.lattice_for_bbox(V.min(axis=0), V.max(axis=0), (33, 17, 29), inflate=0.05)
     band = 3.0 * float(max(spacing))
     out = torch.empty(int(np.prod(dims)), dtype=torch.float32, device="cuda")
