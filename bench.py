@@ -1,20 +1,24 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the FastWindingNumber hot path (BASELINE.json: winding queries/s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config 2]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config {1..5}] [--mode {tree,exact}]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1]): is_inside classification of the 512^3 cell-centred lattice over
-[-1.1, 1.1]^3 (134 217 728 queries) against an icosahedron midpoint-subdivided 8x (1 310 720 triangles), beta = 2,
-order 2. One "step" = one pass of the query path over the whole lattice (the tree is built once, before the timed
-region; its build time is reported beside the throughput). With N GPUs the lattice is cut into N z-slabs, the tree is
-built on rank 0 and broadcast once with NCCL; there is no collective on the query path (weak/strong: total work fixed).
+Default workload (BASELINE.json configs[1]): is_inside classification of the 512^3 cell-centred lattice over
+[-1.1, 1.1]^3 (134 217 728 queries) against an icosahedron midpoint-subdivided 8x (1 310 720 triangles), beta = 2, order 2,
+on the reference builder's own hierarchy built on the GPU (WN_HIERARCHY_REFERENCE: results match the reference algorithm).
+One "step" = one pass of the query path over the whole query set (the tree is built once, before the timed region; its build
+time is reported beside the throughput). With N GPUs the queries are sharded (lattices: tile layers round-robin; point sets:
+index ranges), the tree is built on rank 0 and broadcast once with NCCL; there is no collective on the query path.
+--config 1/3/4/5 run the other BASELINE configs through the same flow (cfg4/cfg5 are point sets: device-resident points for
+`value`, pinned host points + H2D inside the timed region for `e2e`); --mode exact times the brute-force all-pairs mode (cfg5's
+mesh, a bounded number of queries per step).
 
-The JSON line carries: value (device-resident, CUDA-event timed, max over ranks), e2e (through the public API with a
-host output buffer, D2H inside the timed region), roofline (FP32 FMA pipe: algorithmic flops from the traversal's own
-counters / measured FMA peak; plus HBM GB/s), cpu_baseline (the oracle restatement on the host cores, bounded sample),
-clocks, gpu_launches.  `--impl reference` times the oracle restatement (the reference binary cannot be built here, see
-DESIGN.md) on all host threads.
+The JSON line carries: value (device-resident, CUDA-event timed, max over ranks), e2e (through the public API with HOST
+buffers, copies inside the timed region, bit-packed result), roofline (FP32 FMA pipe: flops executed by the timed kernels from
+their own counters / FMA peak measured live; plus HBM GB/s), cpu_baseline (the oracle restatement on the host cores, bounded
+sample), clocks, gpu_launches, parity (strict-band check of the timed configuration against the restatement on a sample).
+`--impl reference` times the oracle restatement (the reference binary cannot be built here) on all host threads.
 """
 from __future__ import annotations
 
@@ -36,15 +40,7 @@ UNIT = "Gqueries/s"
 # host threads of the CPU arm: every core this process may run on, whatever the launcher exported (torchrun sets
 # OMP_NUM_THREADS=1 for its workers, which made the round-1 reference arm single-threaded at N > 1)
 HOST_THREADS = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-
-
-def config_dict(args, name, n_total):
-    """The same `config` for both arms (the driver compares them key by key)."""
-    return {"workload": name, "queries_per_step": n_total,
-            "sharding": f"tile layers (8 z-planes) round-robin over {args.gpus} rank(s), tree built on rank 0 and broadcast; CPU arm: rank 0 only",
-            "l2": "GPU arm: flushed between timed steps (256 MiB fill); CPU arm: not applicable",
-            "gpu_arm": {"leaf_size": args.leaf_size, "hierarchy": args.hierarchy, "tiled": os.environ.get("WN_TILE", "1") != "0"},
-            "cpu_arm": "oracle restatement of the reference algorithm (reference binary unbuildable here: Eigen/TBB/WindingNumber sources absent)"}
+FOUR_PI = 4.0 * np.pi
 
 
 def parse_args():
@@ -53,9 +49,11 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", type=int, default=2, help="BASELINE config (2 = headline)")
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5], help="BASELINE config (2 = headline)")
+    ap.add_argument("--mode", default="tree", choices=["tree", "exact"], help="exact: brute-force all-pairs mode (cfg5 mesh)")
     ap.add_argument("--grid", type=int, default=0, help="override lattice resolution (debug)")
     ap.add_argument("--subdiv", type=int, default=-1, help="override sphere subdivision level (debug)")
+    ap.add_argument("--points", type=int, default=0, help="override the number of query points of cfg4 / cfg5 / exact mode (debug)")
     ap.add_argument("--leaf-size", type=int, default=int(os.environ.get("WN_BENCH_LEAF", "4")), help="max triangles per leaf (ignored by the reference hierarchy)")
     ap.add_argument("--hierarchy", default=os.environ.get("WN_BENCH_HIERARCHY", "reference"), choices=["lbvh", "kd", "kd_sah", "reference"],
                     help="reference (default): the reference builder's own tree built on the GPU, results match the reference algorithm to float "
@@ -63,20 +61,56 @@ def parse_args():
                          "kd: balanced k-d; lbvh: Morton/Karras (1.9 ms build)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the CPU baseline sample")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.mode == "exact":
+        args.config = 5
+    return args
 
 
 def workload(args):
+    """{name, V, F, kind: 'grid'|'points', lattice | points, n_total} of the selected BASELINE config."""
     from lagrange_b200 import primitive as prim
 
-    level = args.subdiv if args.subdiv >= 0 else 8
-    n = args.grid or 512
-    V, F = prim.generate_subdivided_sphere("icosahedron", level)
-    origin = np.full(3, -1.1, dtype=np.float32)
-    spacing = np.full(3, 2.2 / n, dtype=np.float32)
-    dims = np.array([n, n, n], dtype=np.int64)
-    name = f"cfg2: icosphere L{level} ({len(F)} tris), {n}^3 cell-centred lattice over [-1.1,1.1]^3, is_inside, beta=2, order 2"
-    return V, F, (origin, spacing, dims), name
+    cfg = args.config
+    if cfg == 2:
+        level = args.subdiv if args.subdiv >= 0 else 8
+        n = args.grid or 512
+        V, F = prim.generate_subdivided_sphere("icosahedron", level)
+        lattice = (np.full(3, -1.1, dtype=np.float32), np.full(3, 2.2 / n, dtype=np.float32), np.array([n, n, n], dtype=np.int64))
+        name = f"cfg2: icosphere L{level} ({len(F)} tris), {n}^3 cell-centred lattice over [-1.1,1.1]^3, is_inside, beta=2, order 2"
+        return {"name": name, "V": V, "F": F, "kind": "grid", "lattice": lattice, "n_total": n ** 3}
+    V, F = prim.config_mesh(cfg)
+    if cfg in (1, 3):
+        n = args.grid or (100 if cfg == 1 else 256)
+        lattice = prim.lattice_for_bbox(*prim.mesh_bbox(V), n)
+        what = "torus 100x50 centroid-fan" if cfg == 1 else "open non-manifold soup (torus 250x200 with holes, duplicates, flips)"
+        name = f"cfg{cfg}: {what} ({len(F)} tris), {n}^3 cell-centred lattice over the bbox + 5 %, is_inside, beta=2, order 2"
+        return {"name": name, "V": V, "F": F, "kind": "grid", "lattice": lattice, "n_total": n ** 3}
+    if args.mode == "exact":
+        n = args.points or (1 << 20)
+        pts = prim.uniform_points_in_bbox(*prim.mesh_bbox(V), n, seed=0xC0FFEE05)
+        name = f"cfg5 exact mode: torus 250x100 ({len(F)} tris) x {n} uniform points per step, brute-force all-pairs solid angle (75 flop per pair)"
+        return {"name": name, "V": V, "F": F, "kind": "points", "points": pts, "n_total": n}
+    if cfg == 4:
+        n = args.points or (64 << 20)
+        pts = prim.near_surface_points(V, F, n, seed=0xC0FFEE04)
+        name = f"cfg4: octasphere L10 ({len(F)} tris), {n} near-surface jittered points in random order, is_inside, beta=2, order 2"
+    else:
+        n = args.points or (1 << 24)
+        pts = prim.uniform_points_in_bbox(*prim.mesh_bbox(V), n, seed=0xC0FFEE05)
+        name = f"cfg5: torus 250x100 ({len(F)} tris), {n} uniform points in the bbox + 5 %, is_inside, beta=2, order 2"
+    return {"name": name, "V": V, "F": F, "kind": "points", "points": pts, "n_total": n}
+
+
+def config_dict(args, name, n_total):
+    """The same `config` for both arms (the driver compares them key by key)."""
+    return {"workload": name, "queries_per_step": n_total, "mode": args.mode,
+            "sharding": f"lattices: tile layers (8 z-planes) round-robin over {args.gpus} rank(s); point sets: index ranges; tree built on rank 0 "
+                        "and broadcast; CPU arm: rank 0 only",
+            "l2": "GPU arm: flushed between timed steps (256 MiB fill); CPU arm: not applicable",
+            "gpu_arm": {"hierarchy": args.hierarchy, "leaf_size": 1 if args.hierarchy == "reference" else args.leaf_size,
+                        "tiled": os.environ.get("WN_TILE", "1") != "0"},
+            "cpu_arm": "oracle restatement of the reference algorithm (reference binary unbuildable here: Eigen/TBB/WindingNumber sources absent)"}
 
 
 class ClockSampler:
@@ -132,96 +166,105 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
-def cpu_baseline(V, F, lattice, seconds, want_build=True):
-    """The oracle restatement (oracle/wn_oracle.cpp) on the host cores, bounded strided sample of the same lattice."""
-    import oracle
+# ---- the CPU arm: the oracle restatement on the host cores --------------------------------------------------------------------
+class CpuArm:
+    """Times `count` queries of the workload (every stride-th one) with the restatement, all host threads."""
 
-    origin, spacing, dims = lattice
-    total = int(dims[0] * dims[1] * dims[2])
-    t0 = time.perf_counter()
-    ref = oracle.RefEngine(V, F)
-    build_s = time.perf_counter() - t0
-    cores = HOST_THREADS
-    # pilot to size the sample
-    stride0 = max(1, total // 200_000) | 1
-    t0 = time.perf_counter()
-    ref.grid(origin, spacing, dims, first=0, stride=stride0, nthreads=cores)
-    pilot = time.perf_counter() - t0
-    pilot_n = (total + stride0 - 1) // stride0
-    rate = pilot_n / max(pilot, 1e-6)
-    n = int(min(total, max(pilot_n, rate * seconds)))
-    stride = max(1, total // n) | 1
-    t0 = time.perf_counter()
-    out = ref.grid(origin, spacing, dims, first=0, stride=stride, nthreads=cores)
-    dt = time.perf_counter() - t0
-    n = len(out)
-    return ref, {"value": n / dt / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
-                 "sample": f"{n} of {total} lattice points (every {stride}-th in x-fastest order) in {dt:.2f} s; oracle restatement of the "
-                           f"reference algorithm (4-ary SAH BVH, float32), OpenMP over queries; tree build {build_s:.2f} s on 1 thread",
-                 "build_s": build_s, "seconds": dt}
+    def __init__(self, wl, mode):
+        import oracle
+
+        self.oracle = oracle
+        self.wl = wl
+        self.mode = mode
+        t0 = time.perf_counter()
+        self.ref = oracle.RefEngine(wl["V"], wl["F"]) if mode == "tree" else None
+        self.build_s = time.perf_counter() - t0
+        self.cores = HOST_THREADS
+
+    def run(self, first, stride):
+        wl = self.wl
+        t0 = time.perf_counter()
+        if self.mode == "exact":
+            q = wl["points"][first::stride]
+            self.oracle.exact32(wl["V"], wl["F"], q, nthreads=self.cores)
+            n = len(q)
+        elif wl["kind"] == "grid":
+            n = len(self.ref.grid(*wl["lattice"], first=first, stride=stride, nthreads=self.cores))
+        else:
+            q = wl["points"][first::stride]
+            n = len(self.ref.is_inside(q, nthreads=self.cores))
+        return n, time.perf_counter() - t0
+
+    def sized_stride(self, seconds):
+        total = self.wl["n_total"]
+        pilot_n = 2_000 if self.mode == "exact" else 200_000
+        stride0 = max(1, total // pilot_n) | 1
+        n, dt = self.run(0, stride0)
+        rate = n / max(dt, 1e-6)
+        want = int(min(total, max(n, rate * seconds)))
+        stride = max(1, total // max(1, want))
+        return stride | 1 if stride > 1 else 1
+
+    def describe(self):
+        kind = "float32 brute force with the reference's triangle formula (exact32)" if self.mode == "exact" else \
+            "restatement of the reference algorithm (4-ary SAH BVH, float32, beta = 2)"
+        return f"{kind}, OpenMP over queries on {self.cores} threads; tree build {self.build_s:.2f} s on 1 thread"
+
+
+def cpu_baseline(wl, mode, seconds):
+    arm = CpuArm(wl, mode)
+    stride = arm.sized_stride(seconds)
+    n, dt = arm.run(0, stride)
+    return {"value": n / dt / 1e9, "unit": UNIT, "cores": arm.cores, "kind": "port",
+            "sample": f"{n} of {wl['n_total']} queries (every {stride}-th) in {dt:.2f} s; {arm.describe()}"}
 
 
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm (oracle restatement; the reference binary is unbuildable here)."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    V, F, lattice, name = workload(args)
-    import oracle
-
-    origin, spacing, dims = lattice
-    total = int(dims[0] * dims[1] * dims[2])
-    t0 = time.perf_counter()
-    ref = oracle.RefEngine(V, F)
-    build_s = time.perf_counter() - t0
-    cores = HOST_THREADS
-    stride0 = max(1, total // 100_000) | 1
-    t0 = time.perf_counter()
-    ref.grid(origin, spacing, dims, stride=stride0, nthreads=cores)
-    rate = ((total + stride0 - 1) // stride0) / (time.perf_counter() - t0)
-    per_step = max(50_000, int(rate * 4.0))  # ~4 s per step
-    stride = max(1, total // per_step) | 1
-    times = []
-    n = 0
+    wl = workload(args)
+    arm = CpuArm(wl, args.mode)
+    stride = arm.sized_stride(4.0)  # ~4 s per step
+    times, n = [], 0
     for it in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        out = ref.grid(origin, spacing, dims, first=it % stride, stride=stride, nthreads=cores)
-        dt = time.perf_counter() - t0
-        n = len(out)
+        n, dt = arm.run(it % stride, stride)
         if it >= args.warmup:
             times.append(dt)
     ms = 1e3 * float(np.mean(times))
     value = n / (ms * 1e-3) / 1e9
-    sample = f"{n} of {total} lattice points per step (stride {stride}), {cores} OpenMP threads; tree build {build_s:.2f} s"
+    sample = f"{n} of {wl['n_total']} queries per step (stride {stride}); {arm.describe()}"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": config_dict(args, name, total),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": config_dict(args, wl["name"], wl["n_total"]),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
 
 def profile_traffic():
-    """DRAM bytes (read + write) per launch of the dominant kernel, k_tile_query, from the committed `ncu --set full` summary
-    (profiles/r1q_tile_plan_query_ncu_full.txt: one launch = 131072 tiles = 67.1 M queries). The tree (158 MB with 4-triangle leaves) is part of it:
-    every launch streams the records it touches from HBM once; the algorithmic output is 1 byte per query."""
-    path = os.path.join(ROOT, "profiles", "r1q_tile_plan_query_ncu_full.txt")
-    try:
-        rd = wr = None
-        in_query = False
-        for ln in open(path):
-            if ln.startswith("## "):
-                in_query = "k_tile_query" in ln
-            elif in_query and ln.startswith("dram__bytes_read.sum "):
-                rd = float(ln.split()[-1]) * 1e6
-            elif in_query and ln.startswith("dram__bytes_write.sum "):
-                wr = float(ln.split()[-1]) * 1e6
-        return None if rd is None or wr is None else {"bytes_per_launch": rd + wr, "queries_per_launch": 131072 * 512,
-                                                      "source": "profiles/r1q_tile_plan_query_ncu_full.txt (k_tile_query)"}
-    except Exception:
-        return None
-
+    """DRAM bytes (read + write) per launch of the dominant kernel, k_tile_query, from the newest committed `ncu --set full` summary
+    under profiles/ (STATIC: captured on the commit named in the file, not in this run; one launch = 131072 tiles = 67.1 M queries
+    of cfg2). The tree is part of it: every launch streams the records it touches from HBM once; the algorithmic output is 1 byte per query."""
+    for fn in ("r2_tile_plan_query_ncu_full.txt", "r1q_tile_plan_query_ncu_full.txt"):
+        path = os.path.join(ROOT, "profiles", fn)
+        try:
+            rd = wr = None
+            in_query = False
+            for ln in open(path):
+                if ln.startswith("## "):
+                    in_query = "k_tile_query" in ln
+                elif in_query and ln.startswith("dram__bytes_read.sum "):
+                    rd = float(ln.split()[-1]) * 1e6
+                elif in_query and ln.startswith("dram__bytes_write.sum "):
+                    wr = float(ln.split()[-1]) * 1e6
+            if rd is not None and wr is not None:
+                return {"bytes_per_launch": rd + wr, "queries_per_launch": 131072 * 512, "source": f"profiles/{fn} (k_tile_query)",
+                        "static": True}
+        except Exception:
+            continue
+    return None
 
 
 def main():
@@ -232,7 +275,7 @@ def main():
     import torch
 
     import lagrange_b200 as lb
-    from lagrange_b200.distributed import interleaved_layers, replicate_engine
+    from lagrange_b200.distributed import interleaved_layers, replicate_engine, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -246,25 +289,22 @@ def main():
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    V = F = None
-    origin = np.full(3, -1.1, dtype=np.float32)
-    n = args.grid or 512
-    spacing = np.full(3, 2.2 / n, dtype=np.float32)
-    dims = np.array([n, n, n], dtype=np.int64)
-    name = None
+    wl = workload(args)  # every rank generates the (deterministic) workload; only rank 0 builds the tree
+    exact = args.mode == "exact"
+    grid = wl["kind"] == "grid"
+    n_total = wl["n_total"]
     eng = None
     build_info = {}
+    ekw = dict(hierarchy=args.hierarchy, leaf_size=args.leaf_size)
     if rank == 0:
-        V, F, (origin, spacing, dims), name = workload(args)
         # warm-up build on a small mesh: loads the build kernels (CUDA lazy module loading) so that build_ms is kernel time
-        lb.FastWindingNumber(*lb.primitive.generate_subdivided_sphere("icosahedron", 4), leaf_size=args.leaf_size, hierarchy=args.hierarchy).close()
+        lb.FastWindingNumber(*lb.primitive.generate_subdivided_sphere("icosahedron", 4), **ekw).close()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        eng = lb.FastWindingNumber(V, F, leaf_size=args.leaf_size, hierarchy=args.hierarchy)
+        eng = lb.FastWindingNumber(wl["V"], wl["F"], **ekw)
         torch.cuda.synchronize()
-        build_wall_ms = 1e3 * (time.perf_counter() - t0)
         build_info = eng.info
-        build_info["build_wall_ms"] = build_wall_ms
+        build_info["build_wall_ms"] = 1e3 * (time.perf_counter() - t0)
     bcast_ms = 0.0
     if world > 1:
         # warm the communicator first (NCCL sets up its channels lazily on the first collective: ~40-70 ms that are not the
@@ -279,26 +319,45 @@ def main():
         dist.barrier()
         bcast_ms = 1e3 * (time.perf_counter() - t0)
 
-    nz = int(dims[2])
-    # rank r classifies the tile layers r, r+N, r+2N, ... (8 z-planes each) in ONE strided call: same mix of work on every
-    # rank (contiguous z-slabs of a sphere load-imbalance: measured 6.5x at 8 GPUs), results compact in the rank's buffer
-    ranges = interleaved_layers(nz, rank, world, depth=8)
-    per_layer = int(dims[0] * dims[1])
-    n_local = per_layer * sum(b - a for a, b in ranges)
-    layers = (rank, world) if world > 1 else None
-    n_total = int(dims[0] * dims[1] * dims[2])
-    out_dev = torch.empty(max(n_local, 1), dtype=torch.uint8, device="cuda")
+    # ---- this rank's share of the queries ---------------------------------------------------------------------------------------
+    lo = 0
+    if grid:
+        origin, spacing, dims = wl["lattice"]
+        # rank r classifies the tile layers r, r+N, r+2N, ... (8 z-planes each) in ONE strided call: same mix of work on every
+        # rank (contiguous z-slabs of a sphere load-imbalance: measured 6.5x at 8 GPUs), results compact in the rank's buffer
+        ranges = interleaved_layers(int(dims[2]), rank, world, depth=8)
+        n_local = int(dims[0] * dims[1]) * sum(b - a for a, b in ranges)
+        layers = (rank, world) if world > 1 else None
+        h2d_bytes = 60
+    else:
+        lo, hi = shard_range(n_total, rank, world)
+        pts_host = torch.from_numpy(wl["points"][lo:hi]).pin_memory()
+        pts_dev = pts_host.cuda()
+        n_local = hi - lo
+        h2d_bytes = 12 * n_total
+    out_dev = torch.empty(max(n_local, 1), dtype=torch.float32 if exact else torch.uint8, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     def step_device():
-        eng.query_grid(origin, spacing, dims, want_inside=True, out_inside=out_dev, layers=layers)
+        if exact:
+            eng.exact_solid_angle(pts_dev, out=out_dev)
+        elif grid:
+            eng.query_grid(origin, spacing, dims, want_inside=True, out_inside=out_dev, layers=layers)
+        else:
+            eng.is_inside(pts_dev, out=out_dev)
 
     def barrier():
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
 
-    for _ in range(args.warmup):
+    # cold first call (fresh engine, fresh query set: the tiling probe and every scratch allocation are inside)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    step_device()
+    torch.cuda.synchronize()
+    cold_ms = 1e3 * (time.perf_counter() - t0)
+    for _ in range(max(0, args.warmup - 1)):
         step_device()
     barrier()
     sampler = ClockSampler(local_rank)
@@ -321,29 +380,46 @@ def main():
     ms_step = float(t.item())
     value = n_total / (ms_step * 1e-3) / 1e9
 
-    # ---- e2e: the public API with a HOST output buffer (pinned), D2H inside the timed region --------------------------------
-    # (bit-packed: 1 bit per query, WN_QUERY_OUT_BITS; the copies of finished batches overlap the next batch)
-    out_host = torch.empty(max((n_local + 7) // 8, 1), dtype=torch.uint8).pin_memory().numpy()
+    # ---- e2e: the public API with HOST buffers (pinned), copies inside the timed region ---------------------------------------------
+    # lattices: 60-byte descriptor in, bit-packed result out (WN_QUERY_OUT_BITS; copies of finished batches overlap the next batch);
+    # point sets: 12 B per query in (H2D), bit-packed result out; exact mode: points in, float32 solid angles out
+    if exact:
+        out_host = torch.empty(max(n_local, 1), dtype=torch.float32).pin_memory().numpy()
+        d2h_bytes = 4 * n_total
+    else:
+        out_host = torch.empty(max((n_local + 7) // 8, 1), dtype=torch.uint8).pin_memory().numpy()
+        d2h_bytes = (n_total + 7) // 8
+    pts_np = None if grid else pts_host.numpy()
+
     def step_host():
-        eng.query_grid(origin, spacing, dims, want_inside=True, out_inside=out_host, layers=layers, bits=True)
+        if exact:
+            eng.exact_solid_angle(pts_np, out=out_host)
+        elif grid:
+            eng.query_grid(origin, spacing, dims, want_inside=True, out_inside=out_host, layers=layers, bits=True)
+        else:
+            eng.is_inside(pts_np, out=out_host, bits=True)
 
     for _ in range(2):
         step_host()
     barrier()
     e2e_times = []
+    checksum = 0
     for _ in range(max(3, min(args.steps, 5))):
         flush.fill_(1)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         step_host()
-        checksum = int(out_host[::509].sum())  # the caller reads the result
+        checksum = float(out_host[::509].sum()) if exact else int(out_host[::509].sum())  # the caller reads the result
         e2e_times.append(time.perf_counter() - t0)
     t = torch.tensor([float(np.mean(e2e_times)) * 1e3], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
     e2e_value = n_total / (e2e_ms * 1e-3) / 1e9
-    inside_local = torch.tensor([int(out_dev[:n_local].sum().item())], dtype=torch.int64, device="cuda")
+    if exact:
+        inside_local = torch.tensor([int((out_dev[:n_local] >= 6.2831854820251465).sum().item())], dtype=torch.int64, device="cuda")
+    else:
+        inside_local = torch.tensor([int(out_dev[:n_local].sum().item())], dtype=torch.int64, device="cuda")
     if dist is not None:
         dist.all_reduce(inside_local)
 
@@ -354,25 +430,41 @@ def main():
         return
 
     # ---- roofline (rank 0): flops EXECUTED by the timed kernels (their own counters), FMA peak measured live -----------------
-    tiled = os.environ.get("WN_TILE", "1") != "0"
-    def summed_stats(tiling):
-        tot = {}
-        for za, zb in ranges:
-            st = eng.query_stats_grid(origin, spacing, dims, z_range=(za, zb), tiling=tiling)
-            for k, v in st.items():
-                tot[k] = tot.get(k, 0) + v
-        return tot
-
-    executed = summed_stats(tiled)
-    per_point = summed_stats(False)
-    nq = max(1, executed["queries"])
-    # SURVEY.md 8(d) units (10 / 83 / 75 flop) + the far-field interpolation of the tiled path: 64 FMA + ~60 for the weights
-    interp_flops = (2 * 64 + 60) if tiled else 0
-    flops_per_query = executed["algorithmic_flops"] / nq + interp_flops
     import ctypes
 
     from lagrange_b200 import _capi
 
+    tiled = os.environ.get("WN_TILE", "1") != "0"
+    nT = len(wl["F"])
+    extra = {}
+    if exact:
+        flops_per_query = 75.0 * nT  # 75 flop per point-triangle pair, exactly
+        extra = {"pairs_per_query": nT, "gpairs_per_s": n_local * nT / (ms_local * 1e-3) / 1e9}
+    else:
+        def stats(tiling):
+            if grid:
+                tot = {}
+                for za, zb in ranges:
+                    st = eng.query_stats_grid(origin, spacing, dims, z_range=(za, zb), tiling=tiling)
+                    for k, v in st.items():
+                        tot[k] = tot.get(k, 0) + v
+                return tot
+            return eng.query_stats(pts_dev, tiling=tiling)
+
+        executed = stats(tiled)
+        per_point = executed if not tiled else stats(False)
+        nq = max(1, executed["queries"])
+        # did the batch actually take the tiled path? (the probe decides per batch; the generic path executes the per-point counts)
+        took_tiles = tiled and executed["node_tests"] != per_point["node_tests"]
+        # SURVEY.md 8(d) units (10 / 83 / 75 flop) + the far-field interpolation of the tiled path: 64 FMA + ~60 for the weights
+        interp_flops = (2 * 64 + 60) if took_tiles else 0
+        flops_per_query = executed["algorithmic_flops"] / nq + interp_flops
+        extra = {"tests_per_query": executed["node_tests"] / nq, "evals_per_query": executed["far_field_evals"] / nq,
+                 "exact_tris_per_query": executed["exact_triangles"] / nq, "lane_utilisation": executed["node_tests"] / max(1, executed["lane_slots"]),
+                 "path": "tiled (k_tile_plan + k_tile_query)" if took_tiles else "generic (k_query)",
+                 "reference_algorithm": {"flops_per_query": per_point["algorithmic_flops"] / nq, "tests_per_query": per_point["node_tests"] / nq,
+                                         "evals_per_query": per_point["far_field_evals"] / nq, "exact_tris_per_query": per_point["exact_triangles"] / nq,
+                                         "equivalent_tflops": per_point["algorithmic_flops"] / nq * n_local / (ms_local * 1e-3) / 1e12}}
     tf, pms = ctypes.c_float(), ctypes.c_float()
     _capi.check(_capi.lib().wn_debug_fma_peak(local_rank, 1 << 14, ctypes.byref(tf), ctypes.byref(pms)))
     fma_peak = float(tf.value)
@@ -384,39 +476,74 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-    ncu_traffic = profile_traffic()
-    algo_bytes = n_local * 1  # implicit lattice in, 1 byte out per query (12 B in only for explicit points)
+    ncu_traffic = profile_traffic() if (args.config == 2 and not exact) else None
+    # 12 B in per explicit point (0 for an implicit lattice) + 1 B (is_inside) or 4 B (solid angle) out per query
+    algo_bytes = n_local * ((0 if grid else 12) + (4 if exact else 1))
     roofline = {
         "bound": "fp32_fma", "achieved": achieved_tflops, "peak": fma_peak, "unit": "TFLOP/s", "frac": achieved_tflops / fma_peak,
         "peak_source": "live FMA microbenchmark k_fma_peak (MEASURED_PEAKS.json has no FP32 CUDA-core figure)",
         "note": "achieved = flops executed by the timed kernels (SURVEY 8(d) units from the kernels' own counters) / event time; "
                 "the per-point counts of the reference algorithm on the same tree are under reference_algorithm",
-        "flops_per_query": flops_per_query, "tests_per_query": executed["node_tests"] / nq, "evals_per_query": executed["far_field_evals"] / nq,
-        "exact_tris_per_query": executed["exact_triangles"] / nq, "lane_utilisation": executed["node_tests"] / max(1, executed["lane_slots"]),
-        "reference_algorithm": {"flops_per_query": per_point["algorithmic_flops"] / nq, "tests_per_query": per_point["node_tests"] / nq,
-                                "evals_per_query": per_point["far_field_evals"] / nq, "exact_tris_per_query": per_point["exact_triangles"] / nq,
-                                "equivalent_tflops": per_point["algorithmic_flops"] / nq * n_local / (ms_local * 1e-3) / 1e12},
+        "flops_per_query": flops_per_query, **extra,
         "traffic": None if ncu_traffic is None else ncu_traffic["bytes_per_launch"], "traffic_detail": ncu_traffic,
         "hbm": {"achieved_gbs": algo_bytes / (ms_local * 1e-3) / 1e9, "peak_gbs": hbm_peak, "peak_source": hbm_src,
                 "frac": algo_bytes / (ms_local * 1e-3) / 1e9 / hbm_peak},
     }
 
+    # ---- parity of the timed configuration against the restatement, strict band, on a bounded sample (rank 0) -----------------------
+    parity = None
+    if not exact and not args.no_cpu_baseline:
+        import oracle
+
+        m = min(n_local, 1 << 18)
+        sel = np.linspace(0, n_local - 1, m).astype(np.int64)
+        if grid:
+            per = int(dims[0] * dims[1])
+            planes = np.asarray([z for a, b in ranges for z in range(a, b)], dtype=np.int64)
+            zz = planes[sel // per]
+            rem = sel % per
+            half = np.float32(0.5)
+            P = np.stack([origin[0] + spacing[0] * ((rem % int(dims[0])).astype(np.float32) + half),
+                          origin[1] + spacing[1] * ((rem // int(dims[0])).astype(np.float32) + half),
+                          origin[2] + spacing[2] * (zz.astype(np.float32) + half)], axis=1).astype(np.float32)
+        else:
+            P = wl["points"][lo:lo + n_local][sel]
+        refe = oracle.RefEngine(wl["V"], wl["F"])
+        w_ref = refe.solid_angle(P, nthreads=HOST_THREADS) / FOUR_PI
+        ins_ref = refe.is_inside(P, nthreads=HOST_THREADS)
+        ins_gpu = out_dev[:n_local].cpu().numpy()[sel]
+        strict = np.abs(w_ref.astype(np.float64) - 0.5) > 1e-3
+        parity = {"sample": int(m), "strict_band_mismatches": int((ins_gpu[strict] != ins_ref[strict]).sum()),
+                  "mismatches_anywhere": int((ins_gpu != ins_ref).sum()), "points_inside_band": int((~strict).sum()),
+                  "against": "oracle restatement of the reference algorithm (parity unpinned: no reference-held vectors exist)"}
+
     cpu = None
     if not args.no_cpu_baseline:
-        _, cpu = cpu_baseline(V, F, (origin, spacing, dims), args.cpu_seconds if world == 1 else min(args.cpu_seconds, 6.0))
-        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cpu = cpu_baseline(wl, args.mode, args.cpu_seconds if world == 1 else min(args.cpu_seconds, 6.0))
 
+    # launches of OUR kernels per step and rank: tiled = (k_tile_plan + k_tile_query) per batch of <= 131072 tiles (the probe that
+    # picks the path runs once, in the cold call, and is remembered per lattice); generic = one k_query; point sets add the Morton
+    # sort of the queries (2 + 4 passes x 5 launches); exact = k_exact + k_exact_reduce
+    tiles = -(-n_local // 512)
+    if exact:
+        launches = 2
+    elif extra.get("path", "").startswith("tiled"):
+        launches = 2 * max(1, -(-tiles // 131072)) + (0 if grid else 22)
+    else:
+        launches = 1 + (0 if grid else 22)
+    api = ("FastWindingNumber.exact_solid_angle(host points) -> wn_exact: pinned HOST points in, float32 solid angles out" if exact else
+           "FastWindingNumber.query_grid(bits=True) -> wn_query_grid[_strided](WN_QUERY_OUT_BITS): implicit lattice (60-byte descriptor in), "
+           "pinned HOST output, 1 bit per query" if grid else
+           "FastWindingNumber.is_inside(host points, bits=True) -> wn_is_inside(WN_QUERY_OUT_BITS): pinned HOST points in, 1 bit per query out")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": config_dict(args, name, n_total),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 60, "d2h_bytes_per_step": (n_total + 7) // 8, "ms_per_step": e2e_ms,
-                "api": "FastWindingNumber.query_grid(bits=True) -> wn_query_grid[_strided](WN_QUERY_OUT_BITS) with a pinned HOST output buffer, 1 bit per "
-                       "query (lattice is implicit: 60-byte descriptor in)"},
-        # per step and rank: tiled = (k_tile_plan + k_tile_query) per batch of <= 131072 tiles (the probe that picks the path runs
-        # once, in the warm-up, and is remembered per lattice); generic = one k_query
-        "gpu_launches": args.steps * (2 * max(1, -(-(-(-n_local // 512)) // 131072)) if tiled else 1),
-        "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+        "config": config_dict(args, wl["name"], n_total),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms, "api": api},
+        "gpu_launches": args.steps * launches,
+        "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "parity": parity,
+        "value_cold": {"ms_first_call": cold_ms, "value": n_local / (cold_ms * 1e-3) / 1e9,
+                       "note": "rank 0's first call on a fresh engine: tiling probe, scratch allocation and lazy kernel loading included"},
         "build": {k: build_info.get(k) for k in ("build_ms", "build_ms_morton", "build_ms_sort", "build_ms_hierarchy", "build_ms_moments",
                                                  "build_ms_pack", "build_wall_ms", "num_entries", "tree_bytes", "max_depth")},
         "tree_broadcast_ms": bcast_ms, "inside_count": int(inside_local.item()), "checksum": checksum,

@@ -28,5 +28,35 @@ def test_roofline_traffic_comes_from_the_committed_profile():
 
     t = bench.profile_traffic()
     assert t is not None and os.path.exists(os.path.join(ROOT, t["source"].split(" ")[0]))
-    assert t["queries_per_launch"] == 131072 * 512
+    assert t["queries_per_launch"] == 131072 * 512 and t["static"] is True  # labelled: read from a committed profile, not measured live
     assert 1e8 < t["bytes_per_launch"] < 1e9  # a few bytes per query: the tree once per launch plus the output
+
+
+def test_reference_arm_uses_every_host_thread_and_shares_the_config_keys():
+    """under torchrun OMP_NUM_THREADS=1 must not make the CPU arm single-threaded, and both arms carry the
+    same `config` keys (the driver compares them)."""
+    import argparse
+
+    sys.path.insert(0, ROOT)
+    import bench
+
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "5", "--points", "20000", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["cpu_baseline"]["cores"] == bench.HOST_THREADS
+    args = argparse.Namespace(gpus=1, mode="tree", hierarchy="reference", leaf_size=4)
+    assert set(line["config"]) == set(bench.config_dict(args, "x", 1))
+    # a non-zero rank of the reference arm exits quietly
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--grid", "16", "--subdiv", "1"], capture_output=True,
+                       text=True, timeout=120, cwd=ROOT, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_exact_mode_reference_arm():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--mode", "exact", "--points", "4000", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["config"]["mode"] == "exact" and "exact mode" in line["config"]["workload"] and line["value"] > 0
