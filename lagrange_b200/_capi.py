@@ -75,6 +75,8 @@ SIGNATURES = {
     "wn_exact": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "wn_exact_grid": (ctypes.c_int, [_vp, _f3, _f3, _l3, _i64, _i64, _vp, _vp, _vp]),
     "wn_sdf_grid": (ctypes.c_int, [_vp, _f3, _f3, _l3, _f, _f, _u32, _vp, ctypes.POINTER(_i64), _vp]),
+    "wn_sdf_grid_sparse": (ctypes.c_int, [_vp, _f3, _f3, _l3, _f, _f, _u32, _i64, _vp, _vp, _vp, ctypes.POINTER(_i64), _vp]),
+    "wn_closest_point": (ctypes.c_int, [_vp, _vp, _i64, _f, _u32, _vp, _vp, _vp, _vp]),
     "wn_tree_packed_size": (ctypes.c_int, [_vp, ctypes.POINTER(_i64)]),
     "wn_tree_pack": (ctypes.c_int, [_vp, _vp, _i64, _vp]),
     "wn_create_from_packed": (ctypes.c_int, [_vp, _i64, ctypes.POINTER(wn_options), ctypes.POINTER(_vp)]),

@@ -160,7 +160,7 @@ struct wn_engine
     mutable cudaEvent_t ev_last = nullptr;
     mutable bool ev_last_valid = false;
     mutable std::mutex sdf_mu; // wn_sdf_grid runs two passes (sign, distance) over shared scratch: one caller at a time
-    mutable DevBuf s_in, s_out_f, s_out_b, s_out_bits, s_sort, s_stats, s_partial, s_plan_hdr, s_plan_items, s_plan_samples, s_plan_order, s_sdf_inside;
+    mutable DevBuf s_in, s_out_f, s_out_b, s_out_bits, s_sort, s_stats, s_partial, s_plan_hdr, s_plan_items, s_plan_samples, s_plan_order, s_plan_lvl, s_sdf_inside, s_sdf_dense;
     mutable PinnedBuf p_small;
     mutable cudaStream_t copy_stream = nullptr; // D2H of finished batches while the next batch computes
     mutable int64_t last_plan_tiles = 0;        // tiles of the last k_tile_plan launch (wn_debug_last_plan)
@@ -1004,7 +1004,11 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
         int64_t default_tiles = 1 << 17;
         if (host_out) default_tiles = std::min<int64_t>(1 << 15, std::max<int64_t>(1 << 13, (units * tiles_per_unit + 1) / 2));
         const int64_t max_tiles = std::max<int64_t>(1, env_int("WN_TILE_BATCH", (int)default_tiles));
-        const int64_t units_per_launch = std::max<int64_t>(1, max_tiles / tiles_per_unit);
+        int64_t units_per_launch = std::max<int64_t>(1, max_tiles / tiles_per_unit);
+        // hierarchical planning (lattices): blocks of 2^k x 2^k x (2^k | 1) tiles above the tiles; a batch must hold whole blocks
+        const int plan_levels = GRID ? std::max(0, std::min(3, env_int("WN_PLAN_LEVELS", 2))) : 0;
+        const bool zgroup = GRID && a.layer_step == 1;
+        if (plan_levels > 0 && zgroup && units_per_launch >= (1 << plan_levels)) units_per_launch &= ~(int64_t)((1 << plan_levels) - 1);
         const int64_t launch_tiles = std::min(units, units_per_launch) * tiles_per_unit;
         if (launch_tiles > INT_MAX / 2)
             return fail(WN_ERR_UNSUPPORTED, "lattice layer too large for the tiled path; pass WN_QUERY_NO_TILING or split it");
@@ -1037,6 +1041,48 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
             }
             a.launch_tiles = blocks;
             WN_CUDA(cudaMemsetAsync(a.plan_cursor, 0, 2 * sizeof(unsigned long long), st)); // arena cursor + the two order counters
+            a.up_hdr = nullptr;
+            a.up_samples = nullptr;
+            if (plan_levels > 0 && (int64_t)a.tiles_x * a.tiles_y * nunits >= 64) {
+                // coarse to fine: every level reads the one above it, the tiles read level 1
+                int64_t nb[4] = {0, 0, 0, 0}, total = 0;
+                int lbx[4], lby[4];
+                for (int k = 1; k <= plan_levels; ++k) {
+                    lbx[k] = (a.tiles_x + (1 << k) - 1) >> k;
+                    lby[k] = (a.tiles_y + (1 << k) - 1) >> k;
+                    const int64_t lbz = zgroup ? (nunits + (1 << k) - 1) >> k : nunits;
+                    nb[k] = (int64_t)lbx[k] * lby[k] * lbz;
+                    total += nb[k];
+                }
+                const size_t hdr_bytes = align_up((size_t)total * sizeof(wn::PlanBlockHeader), 256);
+                WN_CUDA(e->s_plan_lvl.reserve(hdr_bytes + (size_t)total * wn::kTileSampleStride * sizeof(float)));
+                wn::PlanBlockHeader* hdr_base = (wn::PlanBlockHeader*)e->s_plan_lvl.p;
+                float* samp_base = (float*)((char*)e->s_plan_lvl.p + hdr_bytes);
+                int64_t first[4] = {0, 0, 0, 0};
+                for (int k = 2; k <= plan_levels; ++k) first[k] = first[k - 1] + nb[k - 1];
+                for (int k = plan_levels; k >= 1; --k) {
+                    wn::QueryArgs b = a;
+                    b.lvl_shift = k;
+                    b.lvl_zshift = zgroup ? k : 0;
+                    b.lvl_bx = lbx[k];
+                    b.lvl_by = lby[k];
+                    b.lvl_hdr = hdr_base + first[k];
+                    b.lvl_samples = samp_base + first[k] * wn::kTileSampleStride;
+                    if (k < plan_levels) {
+                        b.up_hdr = hdr_base + first[k + 1];
+                        b.up_samples = samp_base + first[k + 1] * wn::kTileSampleStride;
+                        b.up_bx = lbx[k + 1];
+                        b.up_by = lby[k + 1];
+                        b.up_zs = zgroup ? 1 : 0;
+                    }
+                    wn::k_plan_block<<<(int)nb[k], wn::kPlanThreads, 0, st>>>(b);
+                }
+                a.up_hdr = hdr_base + first[1];
+                a.up_samples = samp_base + first[1] * wn::kTileSampleStride;
+                a.up_bx = lbx[1];
+                a.up_by = lby[1];
+                a.up_zs = zgroup ? 1 : 0;
+            }
             wn::k_tile_plan<GRID><<<blocks, wn::kPlanThreads, 0, st>>>(a);
             // a CTA walks a run of consecutive tiles, its warps taking sub-blocks dynamically (see k_tile_query)
             a.launch_tiles = blocks;
@@ -1113,6 +1159,33 @@ struct StreamOrder
     }
 };
 
+// K9: Morton order of a batch of query points (null for small batches), so that a warp's points are spatial neighbours.
+// The permutation lives in the engine's sort scratch until the next call.
+wn_status morton_order(const wn_engine* e, const float* d_q, int64_t n, cudaStream_t st, const unsigned** perm_out)
+{
+    *perm_out = nullptr;
+    const int64_t sort_min = env_int("WN_SORT_MIN", 4096);
+    if (n < sort_min || n > (int64_t)UINT32_MAX) return WN_OK;
+    const size_t kb = align_up((size_t)n * sizeof(uint32_t), 256);
+    const size_t need = 4 * kb + (size_t)wn::sort_scratch_bytes(n) + 256;
+    WN_CUDA(e->s_sort.reserve(need));
+    char* base = (char*)e->s_sort.p;
+    uint32_t* k0 = (uint32_t*)base;
+    uint32_t* k1 = (uint32_t*)(base + kb);
+    unsigned* v0 = (unsigned*)(base + 2 * kb);
+    unsigned* v1 = (unsigned*)(base + 3 * kb);
+    int* bounds = (int*)(base + 4 * kb);
+    void* scratch = base + 4 * kb + 256;
+    const int init[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
+    WN_CUDA(cudaMemcpyAsync(bounds, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    wn::k_point_bounds<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(d_q, n, bounds);
+    wn::k_point_morton<<<(int)((n + 255) / 256), 256, 0, st>>>(d_q, n, bounds, k0, v0);
+    const int which = wn::radix_sort_pairs<uint32_t>(k0, v0, k1, v1, n, 0, 30, scratch, st);
+    WN_CUDA(cudaGetLastError());
+    *perm_out = which ? v1 : v0;
+    return WN_OK;
+}
+
 wn_status points_impl(const wn_engine* e, const float* q_xyz, int64_t n, float beta, uint32_t flags, float* out_omega,
                       uint8_t* out_inside, wn_query_stats* stats, void* stream)
 {
@@ -1162,26 +1235,9 @@ wn_status points_impl(const wn_engine* e, const float* q_xyz, int64_t n, float b
     if (s != WN_OK) return s;
 
     const unsigned* perm = nullptr;
-    const int64_t sort_min = env_int("WN_SORT_MIN", 4096);
-    if (!(flags & WN_QUERY_PRESORTED) && n >= sort_min && n <= (int64_t)UINT32_MAX && e->view.n_entries > 0) {
-        // K9: Morton order of the queries so that a warp's 32*QPL points are spatial neighbours
-        const size_t kb = align_up((size_t)n * sizeof(uint32_t), 256);
-        const size_t need = 4 * kb + (size_t)wn::sort_scratch_bytes(n) + 256;
-        WN_CUDA(e->s_sort.reserve(need));
-        char* base = (char*)e->s_sort.p;
-        uint32_t* k0 = (uint32_t*)base;
-        uint32_t* k1 = (uint32_t*)(base + kb);
-        unsigned* v0 = (unsigned*)(base + 2 * kb);
-        unsigned* v1 = (unsigned*)(base + 3 * kb);
-        int* bounds = (int*)(base + 4 * kb);
-        void* scratch = base + 4 * kb + 256;
-        const int init[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
-        WN_CUDA(cudaMemcpyAsync(bounds, init, sizeof(init), cudaMemcpyHostToDevice, st));
-        wn::k_point_bounds<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(d_q, n, bounds);
-        wn::k_point_morton<<<(int)((n + 255) / 256), 256, 0, st>>>(d_q, n, bounds, k0, v0);
-        const int which = wn::radix_sort_pairs<uint32_t>(k0, v0, k1, v1, n, 0, 30, scratch, st);
-        WN_CUDA(cudaGetLastError());
-        perm = which ? v1 : v0;
+    if (!(flags & WN_QUERY_PRESORTED) && e->view.n_entries > 0) {
+        s = morton_order(e, d_q, n, st, &perm);
+        if (s != WN_OK) return s;
     }
 
     wn::QueryArgs a;
@@ -1431,7 +1487,9 @@ wn_status wn_destroy(wn_engine* e)
         e->s_plan_items.release();
         e->s_plan_samples.release();
         e->s_plan_order.release();
+        e->s_plan_lvl.release();
         e->s_sdf_inside.release();
+        e->s_sdf_dense.release();
         e->p_small.release();
         if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
         if (e->ev_last) cudaEventDestroy(e->ev_last);
@@ -1700,6 +1758,132 @@ wn_status wn_sdf_grid(const wn_engine* e, const float* origin, const float* spac
         *num_active = (int64_t)h;
     }
     return finish_outputs(n, ob, st);
+}
+
+wn_status wn_closest_point(const wn_engine* e, const float* q_xyz, int64_t n, float max_distance, uint32_t flags, float* out_sqdist,
+                           int32_t* out_triangle, float* out_xyz, void* stream)
+{
+    if (!e) return fail(WN_ERR_INVALID_ARGUMENT, "engine is null");
+    if (n < 0 || (n > 0 && !q_xyz)) return fail(WN_ERR_INVALID_ARGUMENT, "null query buffer or negative count");
+    if (!out_sqdist && !out_triangle && !out_xyz) return fail(WN_ERR_INVALID_ARGUMENT, "no output requested");
+    if (n == 0) return WN_OK;
+    if (n > ((int64_t)1 << 36)) return fail(WN_ERR_UNSUPPORTED, "too many points for one call; split it");
+    DeviceGuard guard(e->device);
+    if (!guard.ok) return fail(WN_ERR_CUDA, "cannot select CUDA device %d", e->device);
+    std::lock_guard<std::mutex> lock(e->mu);
+    cudaStream_t st = (cudaStream_t)stream;
+    StreamOrder order(e, st);
+    const float* d_q = nullptr;
+    wn_status s = stage_points(e, q_xyz, n, &d_q, st);
+    if (s != WN_OK) return s;
+    // outputs: device pointers in place, host pointers through one scratch block [sqdist n | tri n | xyz 3n]
+    const bool h_sq = out_sqdist && !is_device_pointer(out_sqdist), h_tri = out_triangle && !is_device_pointer(out_triangle),
+               h_xyz = out_xyz && !is_device_pointer(out_xyz);
+    float* d_sq = out_sqdist;
+    int* d_tri = out_triangle;
+    float* d_xyz = out_xyz;
+    if (h_sq || h_tri || h_xyz) {
+        WN_CUDA(e->s_out_f.reserve((size_t)n * 5 * sizeof(float)));
+        float* base = (float*)e->s_out_f.p;
+        if (h_sq) d_sq = base;
+        if (h_tri) d_tri = (int*)(base + n);
+        if (h_xyz) d_xyz = base + 2 * n;
+    }
+    const unsigned* perm = nullptr;
+    if (!(flags & WN_QUERY_PRESORTED) && e->view.n_entries > 0) {
+        s = morton_order(e, d_q, n, st, &perm);
+        if (s != WN_OK) return s;
+    }
+    wn::ClosestArgs a;
+    memset(&a, 0, sizeof(a));
+    a.tree = e->view;
+    a.tri_order = (const unsigned*)(e->blob + e->hdr.off_tri_order);
+    a.q = d_q;
+    a.perm = perm;
+    a.n = n;
+    a.max_dist = max_distance;
+    a.out_sqdist = d_sq;
+    a.out_tri = d_tri;
+    a.out_xyz = d_xyz;
+    wn::k_closest_point<<<(int)((n + wn::kQueryThreads - 1) / wn::kQueryThreads), wn::kQueryThreads, 0, st>>>(a);
+    WN_CUDA(cudaGetLastError());
+    if (h_sq) WN_CUDA(cudaMemcpyAsync(out_sqdist, d_sq, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (h_tri) WN_CUDA(cudaMemcpyAsync(out_triangle, d_tri, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (h_xyz) WN_CUDA(cudaMemcpyAsync(out_xyz, d_xyz, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (h_sq || h_tri || h_xyz) WN_CUDA(cudaStreamSynchronize(st));
+    return WN_OK;
+}
+
+wn_status wn_sdf_grid_sparse(const wn_engine* e, const float* origin, const float* spacing, const int64_t* dims, float band, float beta,
+                             uint32_t flags, int64_t capacity, int64_t* out_index, float* out_value, uint8_t* out_inside_bits, int64_t* num_active,
+                             void* stream)
+{
+    if (!e) return fail(WN_ERR_INVALID_ARGUMENT, "engine is null");
+    if (!num_active) return fail(WN_ERR_INVALID_ARGUMENT, "num_active is null");
+    if (capacity < 0 || (capacity > 0 && (!out_index || !out_value))) return fail(WN_ERR_INVALID_ARGUMENT, "null output buffers");
+    wn::GridDesc g;
+    int64_t n = 0;
+    wn_status s = check_grid(origin, spacing, dims, 0, dims ? dims[2] : 0, g, n);
+    if (s != WN_OK) return s;
+    *num_active = 0;
+    if (n == 0) return WN_OK;
+    DeviceGuard guard(e->device);
+    if (!guard.ok) return fail(WN_ERR_CUDA, "cannot select CUDA device %d", e->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    // dense block in device scratch (never leaves the GPU), then compaction of the band
+    float* d_sdf = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(e->mu);
+        WN_CUDA(e->s_sdf_dense.reserve((size_t)n * sizeof(float)));
+        d_sdf = (float*)e->s_sdf_dense.p;
+    }
+    s = wn_sdf_grid(e, origin, spacing, dims, band, beta, flags, d_sdf, nullptr, stream);
+    if (s != WN_OK) return s;
+    std::lock_guard<std::mutex> sdf_lock(e->sdf_mu);
+    std::lock_guard<std::mutex> lock(e->mu);
+    StreamOrder order(e, st);
+    const int64_t per_block = (int64_t)wn::kQueryThreads * wn::kCompactItems;
+    const int64_t blocks = (n + per_block - 1) / per_block;
+    if (blocks > INT_MAX) return fail(WN_ERR_UNSUPPORTED, "lattice too large for one launch; split it");
+    WN_CUDA(e->s_sort.reserve((size_t)(blocks + 1) * 4 + (size_t)wn::scan_scratch_elems(blocks + 1) * 4 + 512));
+    uint32_t* d_counts = (uint32_t*)e->s_sort.p;
+    uint32_t* d_scan = (uint32_t*)((char*)e->s_sort.p + align_up((size_t)(blocks + 1) * 4, 256));
+    WN_CUDA(cudaMemsetAsync(d_counts + blocks, 0, 4, st));
+    wn::k_band_count<<<(int)blocks, wn::kQueryThreads, 0, st>>>(d_sdf, n, band, d_counts);
+    wn::exclusive_scan_u32(d_counts, blocks + 1, d_scan, st);
+    uint32_t h_total = 0;
+    WN_CUDA(cudaMemcpyAsync(&h_total, d_counts + blocks, 4, cudaMemcpyDeviceToHost, st));
+    WN_CUDA(cudaStreamSynchronize(st));
+    *num_active = (int64_t)h_total;
+    const int64_t m = std::min<int64_t>(capacity, (int64_t)h_total);
+    if (m > 0) {
+        const bool h_idx = !is_device_pointer(out_index), h_val = !is_device_pointer(out_value);
+        int64_t* d_idx = out_index;
+        float* d_val = out_value;
+        if (h_idx || h_val) {
+            WN_CUDA(e->s_out_f.reserve((size_t)m * 12 + 256));
+            if (h_idx) d_idx = (int64_t*)e->s_out_f.p;
+            if (h_val) d_val = (float*)((char*)e->s_out_f.p + align_up((size_t)m * 8, 256));
+        }
+        wn::k_band_scatter<<<(int)blocks, wn::kQueryThreads, 0, st>>>(d_sdf, n, band, d_counts, m, d_idx, d_val);
+        WN_CUDA(cudaGetLastError());
+        if (h_idx) WN_CUDA(cudaMemcpyAsync(out_index, d_idx, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
+        if (h_val) WN_CUDA(cudaMemcpyAsync(out_value, d_val, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+    }
+    if (out_inside_bits) {
+        // sign of every voxel, 1 bit each (the inactive interior is not in the band list): taken from the dense block
+        const bool h_bits = !is_device_pointer(out_inside_bits);
+        uint8_t* d_bits = out_inside_bits;
+        if (h_bits) {
+            WN_CUDA(e->s_out_bits.reserve((size_t)(n + 7) / 8 + 64));
+            d_bits = (uint8_t*)e->s_out_bits.p;
+        }
+        wn::k_sign_bits<<<(int)(((n + 7) / 8 + 255) / 256), 256, 0, st>>>(d_sdf, n, d_bits);
+        WN_CUDA(cudaGetLastError());
+        if (h_bits) WN_CUDA(cudaMemcpyAsync(out_inside_bits, d_bits, (size_t)(n + 7) / 8, cudaMemcpyDeviceToHost, st));
+    }
+    WN_CUDA(cudaStreamSynchronize(st));
+    return WN_OK;
 }
 
 wn_status wn_debug_last_plan(const wn_engine* e, int32_t* out, int64_t capacity_tiles, int64_t* num_tiles)

@@ -620,8 +620,10 @@ WN_HD float wn_tri_solid_angle(float qx, float qy, float qz, const float4& a, co
     return 2.0f * atan2f(num, den);
 }
 
-// Squared distance from p to triangle (a, b, c): closest-point regions (Ericson, Real-Time Collision Detection, 5.1.5).
-WN_HD float wn_point_tri_dist2(float px, float py, float pz, const float4& a, const float4& b, const float4& c)
+// Closest point of triangle (a, b, c) to p and its squared distance: closest-feature regions (Ericson, Real-Time Collision
+// Detection, 5.1.5). What TriangleAABBTree::get_closest_point evaluates per candidate triangle
+// (modules/bvh/include/lagrange/bvh/TriangleAABBTree.h:84-88).
+WN_HD float wn_point_tri_closest(float px, float py, float pz, const float4& a, const float4& b, const float4& c, float& ox, float& oy, float& oz)
 {
     const float abx = b.x - a.x, aby = b.y - a.y, abz = b.z - a.z;
     const float acx = c.x - a.x, acy = c.y - a.y, acz = c.z - a.z;
@@ -669,7 +671,13 @@ WN_HD float wn_point_tri_dist2(float px, float py, float pz, const float4& a, co
         }
     }
     const float dx = px - cx, dy = py - cy, dz = pz - cz;
+    ox = cx, oy = cy, oz = cz;
     return dx * dx + dy * dy + dz * dz;
+}
+WN_HD float wn_point_tri_dist2(float px, float py, float pz, const float4& a, const float4& b, const float4& c)
+{
+    float x, y, z;
+    return wn_point_tri_closest(px, py, pz, a, b, c, x, y, z);
 }
 
 // FastWindingNumber.cpp:66 computes  omega / (4.f * pi) > 0.5f  with pi a double (constants.h:16), i.e. in double.

@@ -75,6 +75,15 @@ struct TileHeader
     long long pad;
 };
 
+// Entry list of a planning block above the tiles (hierarchical planning, see k_plan_block): the hierarchy nodes its child
+// blocks / tiles have to classify themselves, as ints in the arena.
+struct PlanBlockHeader
+{
+    long long offset; // byte offset of the list in the arena
+    int count;
+    int flags;        // kTileFallback: the block overflowed; its children plan from the root and take no samples from it
+};
+
 struct QueryArgs
 {
     WnTreeView tree;
@@ -105,6 +114,14 @@ struct QueryArgs
     int heavy_cond;           // a tile is 'heavy' from this many conditional records on
     int probe_stride;         // > 0: k_tile_plan only classifies every probe_stride-th tile and adds the class sizes to `probe`
     unsigned long long* probe; // [5] far, conditional, direct, exact records, fallback tiles
+    // hierarchical planning (lattices): a block of level k covers 2^k x 2^k x (2^k | 1) tiles. The level being planned reads its
+    // parent level (up_*), the block kernel writes lvl_*.
+    const PlanBlockHeader* up_hdr; // parent level's entry lists; null: plan from the root
+    const float* up_samples;       // parent level's far-field samples [blocks][kTileSampleStride]
+    int up_bx, up_by, up_zs;       // parent level: blocks per row / column, 1 if the parent halves the layer index too, else 0
+    PlanBlockHeader* lvl_hdr;      // k_plan_block output
+    float* lvl_samples;
+    int lvl_shift, lvl_zshift, lvl_bx, lvl_by;
 };
 
 struct TravCounters
@@ -486,6 +503,204 @@ __device__ __forceinline__ void plan_merge_sort(int* s, int* tmp, int n)
     }
 }
 
+// ---- hierarchical planning: blocks above the tiles -----------------------------------------------------------------------
+// Neighbouring tiles redo the same top of the breadth-first classification and sample largely the same far records. A block of
+// 2^k x 2^k x (2^k | 1) tiles does that part once: it classifies against ITS bounding sphere, starting from its parent block's
+// entry list (the top level: from the root),
+//   far for the whole block and smooth across it -> evaluated at the block's own 4^3 Chebyshev points, added to the parent's
+//                                                   interpolant evaluated there (exact: a tensor cubic is reproduced by 4^3 points)
+//   near for the whole block, internal            -> expanded
+//   anything else                                 -> entry list of the block: its children classify it against their own sphere
+// so a tile starts a few levels above its own scale with most of its far field already in the samples it inherits. Which
+// records a point accepts is untouched (the per-point test stays the reference's); the classification of a record against a
+// tile is the same as from the root, because every ancestor of a listed record is near for the whole block, hence for the tile.
+constexpr int kBlockPassCap = 1024;
+
+__device__ __forceinline__ float plan_parent_interp(const float* __restrict__ up, float px, float py, float pz)
+{
+    // up[0..63] samples, up[64..66] centre, up[67..69] 1 / half-extent of the parent's box
+    float wx[4], wy[4], wz[4];
+    cheb_weights((px - __ldg(up + 64)) * __ldg(up + 67), wx);
+    cheb_weights((py - __ldg(up + 65)) * __ldg(up + 68), wy);
+    cheb_weights((pz - __ldg(up + 66)) * __ldg(up + 69), wz);
+    float acc = 0.0f;
+#pragma unroll
+    for (int kz = 0; kz < 4; ++kz) {
+        float sz = 0.0f;
+#pragma unroll
+        for (int ky = 0; ky < 4; ++ky) {
+            const float4 row = __ldg(reinterpret_cast<const float4*>(up) + kz * 4 + ky);
+            sz += wy[ky] * (wx[0] * row.x + wx[1] * row.y + wx[2] * row.z + wx[3] * row.w);
+        }
+        acc += wz[kz] * sz;
+    }
+    return acc;
+}
+
+__global__ void __launch_bounds__(kPlanThreads) k_plan_block(const QueryArgs a)
+{
+    __shared__ int s_front[2][kTileFrontCap];
+    __shared__ int s_pass[kBlockPassCap];
+    __shared__ int s_far[kTileFarCap];
+    __shared__ float s_samp[kPlanWarps][kTileSamples];
+    __shared__ int s_fcnt[kPlanMaxRounds + 1];
+    __shared__ int s_cnt[4]; // 0 pass, 1 far, 2 overflow / bad, 3 parent usable
+    __shared__ float s_geo[8];
+    __shared__ long long s_off;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const WnTreeView& t = a.tree;
+    const int X = (int)blockIdx.x % a.lvl_bx, Y = ((int)blockIdx.x / a.lvl_bx) % a.lvl_by, Z = (int)blockIdx.x / (a.lvl_bx * a.lvl_by);
+    const int pidx = a.up_hdr ? ((Z >> a.up_zs) * a.up_by + (Y >> 1)) * a.up_bx + (X >> 1) : 0;
+    bool my_ovf = false;
+    if (tid < 4) s_cnt[tid] = 0;
+    for (int r = tid; r <= kPlanMaxRounds; r += kPlanThreads) s_fcnt[r] = 0;
+    if (tid == 0) s_off = 0;
+    __syncthreads();
+    if (tid == 0) {
+        const int span = 8 << a.lvl_shift;
+        const int zt = a.tile_z0 + (Z << a.lvl_zshift) * a.layer_step;
+        const int zp = a.g.z0 + zt * 8;
+        const float lx = wn_lattice_coord(a.g.ox, a.g.sx, X * span), hx = wn_lattice_coord(a.g.ox, a.g.sx, X * span + span - 1);
+        const float ly = wn_lattice_coord(a.g.oy, a.g.sy, Y * span), hy = wn_lattice_coord(a.g.oy, a.g.sy, Y * span + span - 1);
+        const float lz = wn_lattice_coord(a.g.oz, a.g.sz, zp), hz = wn_lattice_coord(a.g.oz, a.g.sz, zp + (8 << a.lvl_zshift) - 1);
+        const float lo[3] = {fminf(lx, hx), fminf(ly, hy), fminf(lz, hz)}, hi[3] = {fmaxf(lx, hx), fmaxf(ly, hy), fmaxf(lz, hz)};
+        float r2 = 0.0f;
+        bool finite = true;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const float c = 0.5f * (lo[d] + hi[d]), h = 0.5f * (hi[d] - lo[d]);
+            s_geo[d] = c;
+            s_geo[3 + d] = h > 0.0f ? 1.0f / h : 0.0f;
+            r2 += h * h;
+            finite = finite && (fabsf(c) <= 3.0e38f) && (h >= 0.0f) && (h <= 3.0e38f);
+        }
+        s_geo[6] = sqrtf(r2) * 1.0001f + 1e-30f;
+        s_geo[7] = 0.0f;
+        if (!finite) s_cnt[2] = 1;
+        bool from_parent = false;
+        if (a.up_hdr) {
+            const PlanBlockHeader ph = a.up_hdr[pidx];
+            from_parent = !(ph.flags & kTileFallback) && ph.count <= kTileFrontCap;
+            if (from_parent) {
+                s_fcnt[0] = ph.count;
+                s_off = ph.offset; // read below by everybody
+            }
+        }
+        s_cnt[3] = from_parent ? 1 : 0;
+        if (!from_parent && t.n_entries > 1) plan_push_kids(__ldg(t.kids), 0, s_front[0], &s_fcnt[0], &s_cnt[2], my_ovf);
+        if (t.n_entries <= 1) s_cnt[2] = 1; // a single leaf: nothing to share, the tiles plan by themselves
+    }
+    __syncthreads();
+    const bool from_parent = s_cnt[3] != 0;
+    if (from_parent) {
+        const int* src = reinterpret_cast<const int*>(a.plan_arena + s_off);
+        const int n0 = s_fcnt[0];
+        for (int j = tid; j < n0; j += kPlanThreads) s_front[0][j] = __ldg(src + j);
+    }
+    __syncthreads();
+    const float cx = s_geo[0], cy = s_geo[1], cz = s_geo[2], ra = s_geo[6];
+    const float hx = s_geo[3] > 0.0f ? 1.0f / s_geo[3] : 0.0f, hy = s_geo[4] > 0.0f ? 1.0f / s_geo[4] : 0.0f,
+                hz = s_geo[5] > 0.0f ? 1.0f / s_geo[5] : 0.0f;
+    int round = 0;
+    bool stop = s_cnt[2] != 0;
+    while (!stop) {
+        const int F = min(s_fcnt[round], kTileFrontCap);
+        if (F == 0) break;
+        const int* cur = s_front[round & 1];
+        int* nxt = s_front[(round + 1) & 1];
+        int* ncnt = &s_fcnt[round + 1];
+        for (int idx = tid; idx < F; idx += kPlanThreads) {
+            const int e = cur[idx] & 0x3fffffff;
+            const float4 f0 = rec_hot(t, e, 0);
+            const bool leaf = __float_as_int(f0.w) < 0;
+            const float thr = fabsf(f0.w) * a.beta2;
+            const float dx = cx - f0.x, dy = cy - f0.y, dz = cz - f0.z;
+            const float D = sqrtf(dx * dx + dy * dy + dz * dz);
+            const float dm = D - ra, dp = D + ra;
+            const bool allfar = dm > 0.0f && dm * dm > thr * 1.0001f;
+            const bool allnear = dp * dp <= thr * 0.9999f;
+            if (allfar && D >= a.kappa * ra && D - sqrtf(fabsf(f0.w)) >= 0.5f * a.kappa * ra)
+                plan_append(s_far, &s_cnt[1], kTileFarCap, e, &s_cnt[2], my_ovf);
+            else if (allnear && !leaf)
+                plan_push_kids(__ldg(t.kids + e), 0, nxt, ncnt, &s_cnt[2], my_ovf);
+            else
+                plan_append(s_pass, &s_cnt[0], kBlockPassCap, e, &s_cnt[2], my_ovf);
+        }
+        ++round;
+        if (round >= kPlanMaxRounds) {
+            my_ovf = true;
+            if (tid == 0) s_cnt[2] = 1;
+        }
+        stop = __syncthreads_or((int)my_ovf) != 0;
+    }
+    __syncthreads();
+    bool fallback = s_cnt[2] != 0;
+    const int n_pass = fallback ? 0 : s_cnt[0], n_far = fallback ? 0 : s_cnt[1];
+    if (tid == 0 && !fallback && n_pass > 0) {
+        const long long bytes = ((long long)n_pass * 4 + 15) & ~15ll;
+        const long long off = (long long)atomicAdd(a.plan_cursor, (unsigned long long)bytes);
+        if (off + bytes > a.plan_arena_bytes) s_cnt[2] = 1;
+        s_off = off;
+    }
+    __syncthreads();
+    fallback = s_cnt[2] != 0;
+    if (!fallback) {
+        int* dst = reinterpret_cast<int*>(a.plan_arena + s_off);
+        for (int j = tid; j < n_pass; j += kPlanThreads) dst[j] = s_pass[j];
+    }
+    // far set at the block's Chebyshev points, on top of what the parent already holds
+    float sacc[2] = {0.0f, 0.0f};
+    bool bad = false;
+    if (!fallback) {
+        float px[2], py[2], pz[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int sidx = lane + 32 * k;
+            px[k] = cx + hx * cheb_node(sidx & 3);
+            py[k] = cy + hy * cheb_node((sidx >> 2) & 3);
+            pz[k] = cz + hz * cheb_node(sidx >> 4);
+        }
+        if (wid == 0 && from_parent) {
+            const float* up = a.up_samples + (int64_t)pidx * kTileSampleStride;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) sacc[k] = plan_parent_interp(up, px[k], py[k], pz[k]);
+        }
+        for (int m = wid; m < n_far; m += kPlanWarps) {
+            const int e = s_far[m];
+            const float4 f0 = rec_hot(t, e, 0), f1 = rec_hot(t, e, 1), f2 = rec_cold(t, e, 0), f3 = rec_cold(t, e, 1),
+                         f4 = rec_cold(t, e, 2), f5 = rec_cold(t, e, 3);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const float rx = px[k] - f0.x, ry = py[k] - f0.y, rz = pz[k] - f0.z;
+                const float l2 = rx * rx + ry * ry + rz * rz;
+                const float om = eval_record(rx, ry, rz, l2, f1, f2, f3, f4, f5);
+                bad = bad || !(fabsf(om) <= 3.402823466e38f);
+                sacc[k] += om;
+            }
+        }
+        bad = bad || !(fabsf(sacc[0]) <= 3.402823466e38f) || !(fabsf(sacc[1]) <= 3.402823466e38f);
+        s_samp[wid][lane] = sacc[0];
+        s_samp[wid][lane + 32] = sacc[1];
+    }
+    fallback = __syncthreads_or((int)(bad || fallback)) != 0;
+    float* sout = a.lvl_samples + (int64_t)blockIdx.x * kTileSampleStride;
+    for (int j = tid; !fallback && j < kTileSamples; j += kPlanThreads) {
+        float v = 0.0f;
+#pragma unroll
+        for (int w = 0; w < kPlanWarps; ++w) v += s_samp[w][j];
+        sout[j] = v;
+    }
+    if (tid < 8) sout[kTileSamples + tid] = s_geo[tid];
+    if (tid == 0) {
+        PlanBlockHeader h;
+        h.offset = s_off;
+        h.count = fallback ? 0 : n_pass;
+        h.flags = fallback ? kTileFallback : 0;
+        a.lvl_hdr[blockIdx.x] = h;
+        if (a.stats) atomicAdd(a.stats + 1, (unsigned long long)(fallback ? 0 : n_far) * kTileSamples);
+    }
+}
+
 template <bool GRID>
 __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
 {
@@ -505,6 +720,11 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
     // probe mode (probe_stride > 0): classify every probe_stride-th tile only and add up the class sizes, so that the host
     // can decide whether the tiled path pays off for this batch (it does when the far set is a large share of the work)
     const int tile = a.probe_stride > 0 ? (int)blockIdx.x * a.probe_stride : (int)blockIdx.x;
+    int pidx = 0; // parent block of this tile (hierarchical planning, lattices only)
+    if (GRID && a.up_hdr) {
+        const int tbx = tile % a.tiles_x, tby = (tile / a.tiles_x) % a.tiles_y, tl = tile / (a.tiles_x * a.tiles_y);
+        pidx = ((tl >> a.up_zs) * a.up_by + (tby >> 1)) * a.up_bx + (tbx >> 1);
+    }
 
     // ---- tile bounding sphere ------------------------------------------------------------------------------------
     if (GRID) {
@@ -586,7 +806,19 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
         s_geo[7] = 0.0f;
         if (!finite) s_cnt[4] = 1; // non-finite coordinates (or an empty tile): generic path
         const int n_entries = t.n_entries;
-        if (n_entries > 1) {
+        // hierarchical planning: start from the parent block's entry list (k_plan_block) instead of the root
+        bool from_parent = false;
+        if (GRID && a.up_hdr && a.probe_stride == 0 && n_entries > 1) {
+            const PlanBlockHeader ph = a.up_hdr[pidx];
+            from_parent = !(ph.flags & kTileFallback) && ph.count <= kTileFrontCap;
+            if (from_parent) {
+                s_fcnt[0] = ph.count;
+                s_off = ph.offset;
+            }
+        }
+        s_cnt[0] = from_parent ? 1 : 0;
+        if (from_parent) {
+        } else if (n_entries > 1) {
             plan_push_kids(__ldg(t.kids), 0, s_front[0], &s_fcnt[0], &s_cnt[4], my_ovf);
         } else if (n_entries == 1) {
             s_exact[0] = 0; // the root is a leaf: exact for everybody
@@ -594,6 +826,14 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
         }
     }
     __syncthreads();
+    const bool from_parent = GRID && s_cnt[0] != 0;
+    if (from_parent) {
+        const int* src = reinterpret_cast<const int*>(a.plan_arena + s_off);
+        const int n0 = s_fcnt[0];
+        for (int j = tid; j < n0; j += kPlanThreads) s_front[0][j] = __ldg(src + j);
+        __syncthreads();
+        if (tid == 0) s_off = 0;
+    }
     const float cx = s_geo[0], cy = s_geo[1], cz = s_geo[2], ra = s_geo[6];
     const float hx = s_geo[3] > 0.0f ? 1.0f / s_geo[3] : 0.0f, hy = s_geo[4] > 0.0f ? 1.0f / s_geo[4] : 0.0f,
                 hz = s_geo[5] > 0.0f ? 1.0f / s_geo[5] : 0.0f;
@@ -751,6 +991,12 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
             px[k] = cx + hx * cheb_node(s & 3);
             py[k] = cy + hy * cheb_node((s >> 2) & 3);
             pz[k] = cz + hz * cheb_node(s >> 4);
+        }
+        if (GRID && from_parent && wid == 0) {
+            // what the blocks above already sampled (their far sets), interpolated to this tile's Chebyshev points
+            const float* up = a.up_samples + (int64_t)pidx * kTileSampleStride;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) sacc[k] = plan_parent_interp(up, px[k], py[k], pz[k]);
         }
         for (int m = wid; m < n_far; m += kPlanWarps) {
             const int e = s_far[m];

@@ -292,6 +292,45 @@ class FastWindingNumber:
                                           _Buf(out, np.float32, writable=True).ptr, ctypes.byref(active), _current_stream_ptr()))
         return out.reshape(int(dims[2]), int(dims[1]), int(dims[0])), int(active.value)
 
+    def sdf_grid_sparse(self, origin, spacing, dims, band, accuracy_scale=None, signed=True, tiling=True, want_inside_bits=False):
+        """Narrow band only: (linear indices int64 [m], signed distances float32 [m], inside bits or None). The cells with
+        |distance| < band, ordered by linear index (z*ny + y)*nx + x: what an OpenVDB grid keeps active. wn_sdf_grid_sparse."""
+        o, s, d, _, _, n = self._grid_args(origin, spacing, dims, None)
+        flags = self._flags(False, tiling) | (0 if signed else 4)
+        active = ctypes.c_int64()
+        self._check(self._lib.wn_sdf_grid_sparse(self._handle(), o, s, d, float(band), float(accuracy_scale or 0.0), flags, 0, None, None, None,
+                                                 ctypes.byref(active), _current_stream_ptr()))
+        m = int(active.value)
+        idx = np.empty(m, dtype=np.int64)
+        val = np.empty(m, dtype=np.float32)
+        bits = np.empty((n + 7) // 8, dtype=np.uint8) if want_inside_bits else None
+        self._check(self._lib.wn_sdf_grid_sparse(self._handle(), o, s, d, float(band), float(accuracy_scale or 0.0), flags, m,
+                                                 ctypes.c_void_p(idx.ctypes.data) if m else None, ctypes.c_void_p(val.ctypes.data) if m else None,
+                                                 ctypes.c_void_p(bits.ctypes.data) if bits is not None else None, ctypes.byref(active),
+                                                 _current_stream_ptr()))
+        return idx, val, bits
+
+    def closest_point(self, pos, max_distance=None, presorted=False):
+        """Closest point on the mesh: (squared distance, triangle id, closest point) per query, like
+        TriangleAABBTree::get_closest_point (modules/bvh/include/lagrange/bvh/TriangleAABBTree.h:84-88). ``pos``: (3,) or (n,3),
+        numpy or torch CUDA. ``max_distance`` bounds the search (farther points report it, triangle -1)."""
+        buf, n, single = self._points(pos)
+        if buf.is_torch and buf.device.type == "cuda":
+            import torch
+
+            sq = torch.empty(n, dtype=torch.float32, device=buf.device)
+            tri = torch.empty(n, dtype=torch.int32, device=buf.device)
+            xyz = torch.empty((n, 3), dtype=torch.float32, device=buf.device)
+            ptrs = [ctypes.c_void_p(t.data_ptr()) for t in (sq, tri, xyz)]
+        else:
+            sq, tri, xyz = np.empty(n, dtype=np.float32), np.empty(n, dtype=np.int32), np.empty((n, 3), dtype=np.float32)
+            ptrs = [ctypes.c_void_p(t.ctypes.data) for t in (sq, tri, xyz)]
+        self._check(self._lib.wn_closest_point(self._handle(), buf.ptr, n, float(max_distance or 0.0), self._flags(presorted, True) & 1, ptrs[0], ptrs[1],
+                                               ptrs[2], _current_stream_ptr()))
+        if single:
+            return float(sq[0]), int(tri[0]), xyz[0]
+        return sq, tri, xyz
+
     def is_inside_grid(self, origin, spacing, dims, **kw):
         return self.query_grid(origin, spacing, dims, want_inside=True, want_omega=False, **kw)[1]
 

@@ -156,3 +156,89 @@ def test_oversized_lattices_are_rejected_not_wrapped(lb, prim):
     st = L.wn_query_grid(eng._handle(), o, s, d, 0, 1 << 24, 0.0, 0, None, ctypes.c_void_p(out.ctypes.data), None)
     assert st == 4  # WN_ERR_UNSUPPORTED
     assert b"too large" in L.wn_last_error()
+
+
+# ---- closest point on the mesh (TriangleAABBTree::get_closest_point) ---------------------------------------
+def _tri_closest64(p, a, b, c):
+    """Closest point of triangle (a, b, c) to p in float64 (Ericson 5.1.5), vectorised over rows."""
+    ab, ac, ap = b - a, c - a, p - a
+    d1, d2 = (ab * ap).sum(1), (ac * ap).sum(1)
+    bp = p - b
+    d3, d4 = (ab * bp).sum(1), (ac * bp).sum(1)
+    cp = p - c
+    d5, d6 = (ab * cp).sum(1), (ac * cp).sum(1)
+    vc, vb, va = d1 * d4 - d3 * d2, d5 * d2 - d1 * d6, d3 * d6 - d5 * d4
+    out = np.empty_like(p)
+    done = np.zeros(len(p), bool)
+
+    def put(mask, val):
+        m = mask & ~done
+        out[m] = val[m]
+        done[m] = True
+
+    put((d1 <= 0) & (d2 <= 0), a)
+    put((d3 >= 0) & (d4 <= d3), b)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        put((vc <= 0) & (d1 >= 0) & (d3 <= 0), a + (d1 / (d1 - d3))[:, None] * ab)
+        put((d6 >= 0) & (d5 <= d6), c)
+        put((vb <= 0) & (d2 >= 0) & (d6 <= 0), a + (d2 / (d2 - d6))[:, None] * ac)
+        put((va <= 0) & (d4 - d3 >= 0) & (d5 - d6 >= 0), b + ((d4 - d3) / ((d4 - d3) + (d5 - d6)))[:, None] * (c - b))
+        den = 1.0 / (va + vb + vc)
+        put(np.ones(len(p), bool), a + ab * (vb * den)[:, None] + ac * (vc * den)[:, None])
+    return out
+
+
+@pytest.mark.parametrize("hierarchy,leaf", [("reference", 1), ("kd_sah", 4), ("lbvh", 1)])
+def test_closest_point_matches_brute_force(lb, oracle_mod, prim, hierarchy, leaf):
+    """wn_closest_point vs the double-precision brute force (oracle.distance64): the squared distance agrees, the returned
+    triangle attains it, and the returned point is that triangle's closest point (ties between triangles sharing the closest
+    edge or vertex are legitimate, so the id is checked through the distance, like the reference's own contract)."""
+    import torch
+
+    V, F = prim.config_mesh(3, small=True)  # open soup with duplicates and flips
+    eng = lb.FastWindingNumber(V, F, hierarchy=hierarchy, leaf_size=leaf)
+    lo, hi = prim.mesh_bbox(V)
+    rng = np.random.Generator(np.random.PCG64(11))
+    P = np.concatenate([prim.uniform_points_in_bbox(lo, hi, 20000, seed=5), prim.near_surface_points(V, F, 20000, sigma_rel=5e-3, seed=6),
+                        V[rng.integers(0, len(V), 500)],  # on the mesh: distance 0
+                        (rng.random((200, 3)) * 200 - 100).astype(np.float32)]).astype(np.float32)  # far away
+    sq, tri, xyz = eng.closest_point(P)
+    d_ref = oracle_mod.distance64(V, F, P)
+    scale = float(np.linalg.norm(hi - lo))
+    assert np.abs(np.sqrt(sq.astype(np.float64)) - d_ref).max() < 2e-6 * max(scale, float(d_ref.max()))
+    assert tri.min() >= 0 and tri.max() < len(F)
+    Vd = V.astype(np.float64)
+    a, b, c = Vd[F[tri, 0]], Vd[F[tri, 1]], Vd[F[tri, 2]]
+    cp = _tri_closest64(P.astype(np.float64), a, b, c)
+    d_tri = np.linalg.norm(P - cp, axis=1)
+    assert np.abs(d_tri - d_ref).max() < 2e-6 * max(scale, float(d_ref.max()))  # the triangle attains the minimum
+    assert np.abs(xyz - cp).max() < 1e-5 * scale  # and the point is the closest point of that triangle
+    # device pointers, same answers; single point overload
+    sq_d, tri_d, xyz_d = eng.closest_point(torch.from_numpy(P).cuda())
+    assert np.array_equal(sq_d.cpu().numpy(), sq) and np.array_equal(tri_d.cpu().numpy(), tri) and np.array_equal(xyz_d.cpu().numpy(), xyz)
+    s1, t1, x1 = eng.closest_point(P[7])
+    assert s1 == sq[7] and np.array_equal(x1, xyz[7])
+    # bounded search: points farther than the bound report it
+    bound = float(np.median(d_ref))
+    sq_b, tri_b, _ = eng.closest_point(P, max_distance=bound)
+    near = d_ref < bound * (1 - 1e-5)
+    far = d_ref > bound * (1 + 1e-5)
+    assert np.array_equal(sq_b[near], sq[near]) and np.all(tri_b[far] == -1) and np.allclose(sq_b[far], bound * bound, rtol=1e-6)
+
+
+def test_sparse_narrow_band_equals_the_dense_block(lb, prim):
+    V, F = prim.generate_subdivided_sphere("icosahedron", 4)
+    eng = lb.FastWindingNumber(V, F)
+    for dims in ((48, 48, 48), (37, 21, 19)):
+        d = np.array(dims, dtype=np.int64)
+        o = np.full(3, -1.2, np.float32)
+        s = (2.4 / d).astype(np.float32)
+        band = 3.0 * float(s.max())
+        dense, n_active = eng.sdf_grid(o, s, d, band)
+        idx, val, bits = eng.sdf_grid_sparse(o, s, d, band, want_inside_bits=True)
+        flat = dense.reshape(-1)
+        want = np.nonzero(np.abs(flat) < band)[0]
+        assert len(idx) == n_active == len(want)
+        assert np.array_equal(idx, want) and np.array_equal(val, flat[want])
+        assert np.array_equal(np.unpackbits(bits, bitorder="little")[: flat.size].astype(bool), flat < 0)
+        assert 0 < len(idx) < flat.size // 2
