@@ -1014,7 +1014,7 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
             return fail(WN_ERR_UNSUPPORTED, "lattice layer too large for the tiled path; pass WN_QUERY_NO_TILING or split it");
         // Variable-size packets (conditional list + gathered direct records + gathered exact triangles) are bump-allocated
         // from an arena sized for the average tile; a tile that does not fit falls back to the generic traversal.
-        const int64_t arena_bytes = std::min<int64_t>(std::max<int64_t>(launch_tiles * env_int("WN_TILE_ARENA_PER_TILE", 8192), (int64_t)64 << 20),
+        const int64_t arena_bytes = std::min<int64_t>(std::max<int64_t>(launch_tiles * env_int("WN_TILE_ARENA_PER_TILE", 12288), (int64_t)64 << 20),
                                                       (int64_t)4 << 30);
         WN_CUDA(e->s_plan_hdr.reserve((size_t)launch_tiles * sizeof(wn::TileHeader) + 256));
         WN_CUDA(e->s_plan_items.reserve((size_t)arena_bytes));

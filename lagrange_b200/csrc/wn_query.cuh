@@ -71,7 +71,7 @@ constexpr int kClsExact = 3;      // leaf, near for every point, unconditional
 struct TileHeader
 {
     int n_cond, n_dir, n_tri, flags;
-    long long offset; // byte offset of the tile's packet in the arena: [cond int2 x n_cond | pad16 | dir 96 B x n_dir | tri 48 B x n_tri]
+    long long offset; // byte offset of the tile's packet in the arena: [cond 32 B x n_cond | dir 96 B x n_dir | tri 48 B x n_tri]
     long long pad;
 };
 
@@ -273,6 +273,92 @@ __device__ __forceinline__ bool warp_traverse(const WnTreeView& t, const float b
         anynear = __any_sync(kFull, anynear);
         if (leaf) {
             if (anynear) {
+                const int first = lk >> WN_LEAF_COUNT_BITS, count = (lk & (WN_MAX_LEAF_SIZE - 1)) + 1;
+                for (int tt = 0; tt < count; ++tt) {
+                    const float4 ta = __ldg(tris + 3 * (int64_t)(first + tt));
+                    const float4 tb = __ldg(tris + 3 * (int64_t)(first + tt) + 1);
+                    const float4 tc = __ldg(tris + 3 * (int64_t)(first + tt) + 2);
+#pragma unroll
+                    for (int k = 0; k < QPL; ++k) {
+                        if (nearq[k]) {
+                            acc[k] += wn_tri_solid_angle(qx[k], qy[k], qz[k], ta, tb, tc);
+                            if (STATS) ++cnt.E;
+                        }
+                    }
+                }
+            }
+            i = i + 1;
+        } else {
+            i = anynear ? i + 1 : after;
+        }
+    }
+    return bad;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// The per-point traversal over a tile's conditional list (k_tile_query). Same decisions as warp_traverse, but the list is
+// self-contained for the test: an item is 32 bytes, (Px, Py, Pz, beta^2 R^2) + (key, skip position, leaf link, -), written by the
+// plan, so a step is two consecutive 128-bit loads instead of list -> record (a dependent pair) and the tree is touched only
+// when some lane actually evaluates. A non-finite far-field value makes the warp redo its sub-block with the generic traversal
+// (the reference descends in that case; that path handles it point by point).
+// ----------------------------------------------------------------------------------------------------------------
+template <int QPL, bool STATS>
+__device__ __forceinline__ bool tile_cond_walk(const WnTreeView& t, const float (&qx)[QPL], const float (&qy)[QPL], const float (&qz)[QPL],
+                                               const bool (&valid)[QPL], float (&acc)[QPL], const float4* __restrict__ items, const int n_items,
+                                               TravCounters& cnt)
+{
+    const int lane = threadIdx.x & 31;
+    const float4* __restrict__ hot = t.hot;
+    const float4* __restrict__ cold = t.cold;
+    const float4* __restrict__ tris = t.tri;
+    int skip[QPL];
+#pragma unroll
+    for (int k = 0; k < QPL; ++k) skip[k] = valid[k] ? 0 : n_items;
+    bool bad = false;
+    int i = 0;
+    while (i < n_items) {
+        const float4 c0 = __ldg(items + 2 * i);
+        const int4 c1 = __ldg(reinterpret_cast<const int4*>(items + 2 * i + 1));
+        const int e = c1.x >> 3, after = c1.y;
+        const bool leaf = (c1.x & 4) != 0, notest = (c1.x & 3) == kClsCondFar;
+        float rx[QPL], ry[QPL], rz[QPL], l2[QPL];
+        bool nearq[QPL], farq[QPL];
+        bool anyfar = false, anynear = false;
+#pragma unroll
+        for (int k = 0; k < QPL; ++k) {
+            const bool active = i >= skip[k];
+            rx[k] = qx[k] - c0.x;
+            ry[k] = qy[k] - c0.y;
+            rz[k] = qz[k] - c0.z;
+            // unfused, like the reference (see warp_traverse)
+            l2[k] = __fadd_rn(__fadd_rn(__fmul_rn(rx[k], rx[k]), __fmul_rn(ry[k], ry[k])), __fmul_rn(rz[k], rz[k]));
+            const bool nr = !notest && l2[k] <= c0.w;
+            nearq[k] = active && nr;
+            farq[k] = active && !nr;
+            anyfar |= farq[k];
+            anynear |= nearq[k];
+            if (STATS) cnt.T += (active && !notest) ? 1 : 0;
+        }
+        if (STATS) cnt.V += (lane == 0) ? 32 * QPL : 0;
+        if (__any_sync(kFull, anyfar)) {
+            const float4* __restrict__ cp = cold + 4 * (int64_t)e;
+            const float4 f1 = __ldg(hot + 2 * (int64_t)e + 1);
+            const float4 f2 = __ldg(cp), f3 = __ldg(cp + 1), f4 = __ldg(cp + 2), f5 = __ldg(cp + 3);
+#pragma unroll
+            for (int k = 0; k < QPL; ++k) {
+                if (farq[k]) {
+                    const float om = eval_record(rx[k], ry[k], rz[k], l2[k], f1, f2, f3, f4, f5);
+                    bad = bad || !(fabsf(om) <= 3.402823466e38f);
+                    acc[k] += om;
+                    skip[k] = after;
+                    if (STATS) ++cnt.A;
+                }
+            }
+        }
+        anynear = __any_sync(kFull, anynear);
+        if (leaf) {
+            if (anynear) {
+                const int lk = c1.z;
                 const int first = lk >> WN_LEAF_COUNT_BITS, count = (lk & (WN_MAX_LEAF_SIZE - 1)) + 1;
                 for (int tt = 0; tt < count; ++tt) {
                     const float4 ta = __ldg(tris + 3 * (int64_t)(first + tt));
@@ -939,7 +1025,7 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
     const int n_tri = s_cnt[7];
 
     // ---- packet allocation and contents ---------------------------------------------------------------------------------
-    const long long cond_bytes = ((long long)n_cond * 8 + 15) & ~15ll;
+    const long long cond_bytes = (long long)n_cond * 32;
     const long long bytes = cond_bytes + (long long)n_dir * 96 + (long long)n_tri * 48;
     if (tid == 0 && !fallback && bytes > 0) {
         const long long off = (long long)atomicAdd(a.plan_cursor, (unsigned long long)bytes);
@@ -950,13 +1036,15 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
     fallback = s_cnt[4] != 0;
     if (!fallback) {
         char* pk = a.plan_arena + s_off;
-        int2* out_cond = reinterpret_cast<int2*>(pk);
+        float4* out_cond = reinterpret_cast<float4*>(pk);
         float4* out_dir = reinterpret_cast<float4*>(pk + cond_bytes);
         float4* out_tri = out_dir + (long long)n_dir * 6;
         for (int j = tid; j < n_cond; j += kPlanThreads) {
             // skip link in list coordinates: first conditional record at or after the end of this record's subtree
             const int key = s_cond[j], e = key >> 3;
-            const int end = (key & 4) ? e + 1 : rec_link(t, e);
+            const float4 f0 = rec_hot(t, e, 0);
+            const int lk = rec_link(t, e);
+            const int end = (key & 4) ? e + 1 : lk;
             const int target = end << 3;
             int lo = j + 1, hi = n_cond;
             while (lo < hi) {
@@ -966,7 +1054,10 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
                 else
                     hi = mid;
             }
-            out_cond[j] = make_int2(key, lo);
+            // self-contained item: centre + the acceptance threshold beta^2 R^2 exactly as the traversal forms it, key, skip
+            // position, leaf link
+            out_cond[2 * j] = make_float4(f0.x, f0.y, f0.z, __fmul_rn(fabsf(f0.w), a.beta2));
+            out_cond[2 * j + 1] = make_float4(__int_as_float(key), __int_as_float(lo), __int_as_float(lk), 0.0f);
         }
         for (int j = tid; j < n_dir * 6; j += kPlanThreads) {
             const int e = s_dir[j / 6], r = j % 6;
@@ -1085,7 +1176,7 @@ __global__ void __launch_bounds__(kQueryThreads, WN_TQ_MIN_CTAS) k_tile_query(co
         for (int k = 0; k < QPL; ++k) acc[k] = 0.0f;
         if (!fallback) {
             // ---- direct records: far for every point of the tile; gathered contiguously by the plan -----------------
-            const float4* __restrict__ dr = reinterpret_cast<const float4*>(pk + (((long long)n_cond * 8 + 15) & ~15ll));
+            const float4* __restrict__ dr = reinterpret_cast<const float4*>(pk + (long long)n_cond * 32);
             for (int j = 0; j < n_dir; ++j) {
                 const float4 f0 = __ldg(dr + 0), f1 = __ldg(dr + 1), f2 = __ldg(dr + 2), f3 = __ldg(dr + 3), f4 = __ldg(dr + 4), f5 = __ldg(dr + 5);
                 dr += 6;
@@ -1116,7 +1207,7 @@ __global__ void __launch_bounds__(kQueryThreads, WN_TQ_MIN_CTAS) k_tile_query(co
                 }
             }
             // ---- conditional records --------------------------------------------------------------------------------
-            bad = warp_traverse<QPL, STATS, true>(a.tree, a.beta2, qx, qy, qz, valid, acc, reinterpret_cast<const int2*>(pk), n_cond, cnt) || bad;
+            bad = tile_cond_walk<QPL, STATS>(a.tree, qx, qy, qz, valid, acc, reinterpret_cast<const float4*>(pk), n_cond, cnt) || bad;
         }
         // The fallback is a per-warp matter: a point's result never depends on its neighbours.
         if (fallback || __any_sync(kFull, bad)) {

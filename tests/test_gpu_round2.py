@@ -241,4 +241,4 @@ def test_sparse_narrow_band_equals_the_dense_block(lb, prim):
         assert len(idx) == n_active == len(want)
         assert np.array_equal(idx, want) and np.array_equal(val, flat[want])
         assert np.array_equal(np.unpackbits(bits, bitorder="little")[: flat.size].astype(bool), flat < 0)
-        assert 0 < len(idx) < flat.size // 2
+        assert 0 < len(idx) < flat.size
