@@ -19,6 +19,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "liboracle_wn.so")
 _lib = None
+loaded_path = None
 
 _f32p = ctypes.POINTER(ctypes.c_float)
 _f64p = ctypes.POINTER(ctypes.c_double)
@@ -41,12 +42,35 @@ def build(force: bool = False) -> str:
     return _LIB_PATH
 
 
+def build_native() -> str | None:
+    """-march=native build of the same source into oracle/_native/ (git-ignored), for the CPU arm of bench.py on the box it runs
+    on (the CPU baseline is built for the host it is timed on). Same flags otherwise (-ffp-contract=off), so
+    results are unchanged. Returns None if the compiler is unavailable."""
+    src = os.path.join(_HERE, "wn_oracle.cpp")
+    out_dir = os.path.join(_HERE, "_native")
+    out = os.path.join(out_dir, "liboracle_wn_native.so")
+    try:
+        os.makedirs(out_dir, exist_ok=True)
+        if (not os.path.exists(out)) or os.path.getmtime(out) < os.path.getmtime(src):
+            subprocess.run(["/usr/bin/g++", "-O3", "-march=native", "-ffp-contract=off", "-fopenmp", "-fPIC", "-std=c++17", "-shared", "-o", out, src],
+                           check=True, capture_output=True, timeout=300)
+        return out
+    except Exception:
+        return None
+
+
 def lib() -> ctypes.CDLL:
     global _lib
     if _lib is None:
         build()
-        L = ctypes.CDLL(_LIB_PATH)
+        path = _LIB_PATH
+        if os.environ.get("WN_ORACLE_NATIVE", "0") == "1":
+            path = build_native() or _LIB_PATH
+        global loaded_path
+        loaded_path = path
+        L = ctypes.CDLL(path)
         L.wno_num_threads.restype = ctypes.c_int
+        L.wno_set_simd_lanes.argtypes = [ctypes.c_int]
         L.wno_exact64.argtypes = [_f32p, ctypes.c_int64, _i32p, ctypes.c_int64, _f32p, ctypes.c_int64, _f64p, ctypes.c_int]
         L.wno_distance64.argtypes = [_f32p, ctypes.c_int64, _i32p, ctypes.c_int64, _f32p, ctypes.c_int64, _f64p, ctypes.c_int]
         L.wno_exact32.argtypes = [_f32p, ctypes.c_int64, _i32p, ctypes.c_int64, _f32p, ctypes.c_int64, _f32p, ctypes.c_int]
@@ -79,6 +103,11 @@ def _i32(a):
 
 def _p(a, t):
     return a.ctypes.data_as(t)
+
+
+def set_simd_lanes(on: bool) -> None:
+    """Evaluate a node's 4 child lanes 4-wide with SSE (default, like upstream's v4uf path) or in a scalar loop (bit-identical)."""
+    lib().wno_set_simd_lanes(1 if on else 0)
 
 
 def num_threads() -> int:

@@ -35,6 +35,9 @@
 #ifdef _OPENMP
 #include <omp.h>
 #endif
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 namespace {
 
@@ -93,6 +96,10 @@ inline bool is_tri(int32_t c) { return c <= -2; }
 inline int32_t dec_tri(int32_t c) { return -(c + 2); }
 
 constexpr int BVH_N = 4;
+
+// The 4 child lanes of a node are evaluated 4-wide (SSE), like upstream's v4uf code path; 0 selects the scalar lane loop
+// (same operations in the same order: the two are bit-identical, tests/test_oracle.py checks it).
+int g_simd_lanes = 1;
 
 struct Node
 {
@@ -671,6 +678,67 @@ struct RefEngine
         float omega_lane[BVH_N];
         unsigned descend = 0;
         int nlanes = 0;
+#if defined(__SSE2__)
+        if (g_simd_lanes) {
+            // all four lanes at once; empty lanes carry zeros and an infinite radius (=> "descend", ignored below)
+            typedef float v4f __attribute__((vector_size(16)));
+            auto LD = [&](int k) {
+                v4f v;
+                std::memcpy(&v, d.f[k], sizeof(v));
+                return v;
+            };
+            const v4f qx = {q.x, q.x, q.x, q.x}, qy = {q.y, q.y, q.y, q.y}, qz = {q.z, q.z, q.z, q.z};
+            v4f rx = qx - LD(F_PX), ry = qy - LD(F_PY), rz = qz - LD(F_PZ);
+            const v4f ql2 = rx * rx + ry * ry + rz * rz;
+            const v4f thr = LD(F_R2) * beta2;
+            const v4f one = {1.0f, 1.0f, 1.0f, 1.0f};
+            const v4f m2 = one / ql2;
+            const v4f m1 = (v4f)_mm_sqrt_ps((__m128)m2);
+            rx = rx * m1;
+            ry = ry * m1;
+            rz = rz * m1;
+            v4f om = -m2 * (rx * LD(F_NX) + ry * LD(F_NY) + rz * LD(F_NZ));
+            if (order >= 1) {
+                const v4f q2x = rx * rx, q2y = ry * ry, q2z = rz * rz;
+                const v4f m3 = m2 * m1;
+                const v4f nxx = LD(F_NXX), nyy = LD(F_NYY), nzz = LD(F_NZZ);
+                const v4f o1 = m3 * (nxx + nyy + nzz -
+                                     3.0f * ((q2x * nxx + q2y * nyy + q2z * nzz) + rx * ry * LD(F_NXY_YX) + rx * rz * LD(F_NZX_XZ) +
+                                             ry * rz * LD(F_NYZ_ZY)));
+                om += o1;
+                if (order >= 2) {
+                    const v4f q3x = q2x * rx, q3y = q2y * ry, q3z = q2z * rz;
+                    const v4f m4 = m2 * m2;
+                    const v4f bxxy = LD(F_2XXY_YXX), bxxz = LD(F_2XXZ_ZXX), byyz = LD(F_2YYZ_ZYY), byyx = LD(F_2YYX_XYY), bzzx = LD(F_2ZZX_XZZ),
+                              bzzy = LD(F_2ZZY_YZZ);
+                    const v4f t0x = byyx + bzzx, t0y = bzzy + bxxy, t0z = bxxz + byyz;
+                    const v4f t1x = ry * bxxy + rz * bxxz, t1y = rz * byyz + rx * byyx, t1z = rx * bzzx + ry * bzzy;
+                    const v4f dgx = LD(F_NXXX), dgy = LD(F_NYYY), dgz = LD(F_NZZZ);
+                    const v4f o2 = m4 * (1.5f * (rx * (3.0f * dgx + t0x) + ry * (3.0f * dgy + t0y) + rz * (3.0f * dgz + t0z)) -
+                                         7.5f * ((q3x * dgx + q3y * dgy + q3z * dgz) + rx * ry * rz * LD(F_SUMPERM) +
+                                                 (q2x * t1x + q2y * t1y + q2z * t1z)));
+                    om += o2;
+                }
+            }
+            for (int s = 0; s < BVH_N; ++s) {
+                if (nd.child[s] == kEmpty) {
+                    omega_lane[s] = 0;
+                    continue;
+                }
+                ++nlanes;
+                const bool desc = ql2[s] <= thr[s];
+                if (cnt) ++cnt->tests;
+                if (!desc && std::isfinite(om[s])) {
+                    omega_lane[s] = om[s];
+                    if (cnt) ++cnt->approx;
+                } else {
+                    omega_lane[s] = 0;
+                    descend |= 1u << s;
+                }
+            }
+        } else
+#endif
+        {
         for (int s = 0; s < BVH_N; ++s) {
             if (nd.child[s] == kEmpty) {
                 omega_lane[s] = 0;
@@ -718,6 +786,7 @@ struct RefEngine
                 omega_lane[s] = 0;
                 descend |= 1u << s;
             }
+        }
         }
         float sum = omega_lane[0];
         for (int s = 1; s < BVH_N; ++s) sum += omega_lane[s];
@@ -768,6 +837,11 @@ int resolve_threads(int nthreads)
 } // namespace
 
 extern "C" {
+
+void wno_set_simd_lanes(int on)
+{
+    g_simd_lanes = on ? 1 : 0;
+}
 
 int wno_num_threads()
 {

@@ -151,3 +151,20 @@ def test_grid_entry_point_matches_points(oracle_mod, prim):
     assert np.array_equal(om, ref.solid_angle(P)) and np.array_equal(ins, ref.is_inside(P))
     ins2 = ref.grid(o, s, d, first=5, stride=7)
     assert np.array_equal(ins2, ins[5::7])
+
+
+def test_simd_lane_evaluation_is_bit_identical_to_the_scalar_loop(oracle_mod, prim):
+    """The 4 child lanes of a node are evaluated 4-wide (SSE) like upstream's v4uf path; same operations, same order."""
+    V, F = prim.config_mesh(3, small=True)
+    o, s, d = prim.lattice_for_bbox(*prim.mesh_bbox(V), 24)
+    P = prim.lattice_points(o, s, d)
+    try:
+        for order in (0, 1, 2):
+            ref = oracle_mod.RefEngine(V, F, order=order)
+            oracle_mod.set_simd_lanes(True)
+            a, ca = ref.solid_angle(P, counters=True)
+            oracle_mod.set_simd_lanes(False)
+            b, cb = ref.solid_angle(P, counters=True)
+            assert np.array_equal(a, b) and np.array_equal(ca, cb)
+    finally:
+        oracle_mod.set_simd_lanes(True)
