@@ -21,6 +21,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <memory>
+#include <vector>
 
 struct wn_engine;
 
@@ -47,6 +48,9 @@ struct FastWindingNumberOptions
     bool vertex_radius = false; ///< exact cluster radius instead of the reference's box-corner bound (changes results)
     bool balanced_hierarchy = false; ///< deprecated spelling of hierarchy = Hierarchy::Kd
     int device = -1; ///< CUDA device, -1 = current
+    /// More than one entry: the tree is built on devices[0] and replicated to the others (wn_replicate), and the whole-lattice
+    /// overloads shard their tile layers over all of them from one host thread per GPU (wn_query_grid_multi). Overrides `device`.
+    std::vector<int> devices;
     /// The reference-surface single-point overloads is_inside(pos) / solid_angle(pos) are called once per voxel from many
     /// host threads (modules/volume/src/mesh_to_volume.cpp:175-183). true (default): they walk a HOST copy of the packed
     /// tree (made on first use, lock-free afterwards, ~1-3 us per call and thread). false: every call is a kernel launch

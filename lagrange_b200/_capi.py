@@ -80,6 +80,8 @@ SIGNATURES = {
     "wn_tree_packed_size": (ctypes.c_int, [_vp, ctypes.POINTER(_i64)]),
     "wn_tree_pack": (ctypes.c_int, [_vp, _vp, _i64, _vp]),
     "wn_create_from_packed": (ctypes.c_int, [_vp, _i64, ctypes.POINTER(wn_options), ctypes.POINTER(_vp)]),
+    "wn_replicate": (ctypes.c_int, [_vp, ctypes.POINTER(_i32), _i32, ctypes.POINTER(_vp)]),
+    "wn_query_grid_multi": (ctypes.c_int, [ctypes.POINTER(_vp), _i32, _f3, _f3, _l3, _f, _u32, _vp, _vp]),
     "wn_debug_node_moments": (ctypes.c_int, [_vp, _i64, _i64, _vp]),
     "wn_debug_topology": (ctypes.c_int, [_vp, _vp, _i64, ctypes.POINTER(_i64)]),
     "wn_debug_last_plan": (ctypes.c_int, [_vp, _vp, _i64, ctypes.POINTER(_i64)]),

@@ -16,6 +16,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/wn_b200.h"
@@ -1883,6 +1884,136 @@ wn_status wn_sdf_grid_sparse(const wn_engine* e, const float* origin, const floa
         if (h_bits) WN_CUDA(cudaMemcpyAsync(out_inside_bits, d_bits, (size_t)(n + 7) / 8, cudaMemcpyDeviceToHost, st));
     }
     WN_CUDA(cudaStreamSynchronize(st));
+    return WN_OK;
+}
+
+wn_status wn_replicate(const wn_engine* src, const int32_t* devices, int32_t n_devices, wn_engine** out)
+{
+    if (!src || !devices || !out || n_devices < 0) return fail(WN_ERR_INVALID_ARGUMENT, "null argument");
+    for (int i = 0; i < n_devices; ++i) out[i] = nullptr;
+    int count = 0;
+    WN_CUDA(cudaGetDeviceCount(&count));
+    for (int i = 0; i < n_devices; ++i)
+        if (devices[i] < 0 || devices[i] >= count) return fail(WN_ERR_INVALID_ARGUMENT, "device %d out of range (%d devices)", devices[i], count);
+    // One packed blob, copied device to device (NVLink peer copies where the topology allows, staged by the driver otherwise);
+    // all copies are in flight together, then every replica validates and adopts its copy.
+    std::vector<void*> staging((size_t)n_devices, nullptr);
+    std::vector<cudaStream_t> streams((size_t)n_devices, nullptr);
+    wn_status st = WN_OK;
+    const size_t bytes = (size_t)src->hdr.total_bytes;
+    for (int i = 0; i < n_devices && st == WN_OK; ++i) {
+        DeviceGuard g(devices[i]);
+        if (!g.ok) {
+            st = fail(WN_ERR_CUDA, "cannot select CUDA device %d", devices[i]);
+            break;
+        }
+        if (devices[i] != src->device) {
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, devices[i], src->device) == cudaSuccess && can) {
+                const cudaError_t pe = cudaDeviceEnablePeerAccess(src->device, 0);
+                if (pe != cudaSuccess) cudaGetLastError(); // already enabled, or not permitted: the copy still works
+            }
+        }
+        cudaError_t ce = cudaMalloc(&staging[i], bytes);
+        if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking);
+        if (ce == cudaSuccess) ce = cudaMemcpyPeerAsync(staging[i], devices[i], src->blob, src->device, bytes, streams[i]);
+        if (ce != cudaSuccess) {
+            cudaGetLastError();
+            st = fail(ce == cudaErrorMemoryAllocation ? WN_ERR_OUT_OF_MEMORY : WN_ERR_CUDA, "replicating to device %d failed: %s", devices[i],
+                      cudaGetErrorString(ce));
+        }
+    }
+    for (int i = 0; i < n_devices; ++i) {
+        if (!streams[i]) continue;
+        DeviceGuard g(devices[i]);
+        const cudaError_t ce = cudaStreamSynchronize(streams[i]);
+        if (ce != cudaSuccess && st == WN_OK) st = fail(WN_ERR_CUDA, "replicating to device %d failed: %s", devices[i], cudaGetErrorString(ce));
+        cudaStreamDestroy(streams[i]);
+    }
+    for (int i = 0; i < n_devices && st == WN_OK; ++i) {
+        wn_options opt;
+        wn_options_init(&opt);
+        opt.device = devices[i];
+        opt.accuracy_scale = 0.0f; // keep the source engine's
+        DeviceGuard g(devices[i]);
+        st = wn_create_from_packed(staging[i], (int64_t)bytes, &opt, &out[i]);
+        if (st == WN_OK) out[i]->opt.accuracy_scale = out[i]->info.accuracy_scale = src->opt.accuracy_scale;
+    }
+    for (int i = 0; i < n_devices; ++i) {
+        if (staging[i]) {
+            DeviceGuard g(devices[i]);
+            cudaFree(staging[i]);
+        }
+        if (st != WN_OK && out[i]) {
+            wn_destroy(out[i]);
+            out[i] = nullptr;
+        }
+    }
+    return st;
+}
+
+wn_status wn_query_grid_multi(wn_engine* const* engines, int32_t n_engines, const float* origin, const float* spacing, const int64_t* dims,
+                              float beta, uint32_t flags, float* out_omega, uint8_t* out_inside)
+{
+    if (!engines || n_engines < 1) return fail(WN_ERR_INVALID_ARGUMENT, "no engines");
+    for (int i = 0; i < n_engines; ++i)
+        if (!engines[i]) return fail(WN_ERR_INVALID_ARGUMENT, "engine %d is null", i);
+    if (!out_omega && !out_inside) return fail(WN_ERR_INVALID_ARGUMENT, "no output requested");
+    if (is_device_pointer(out_omega) || is_device_pointer(out_inside))
+        return fail(WN_ERR_INVALID_ARGUMENT, "wn_query_grid_multi gathers into HOST buffers (each device holds only its own layers)");
+    wn::GridDesc g;
+    int64_t n = 0;
+    wn_status s = check_grid(origin, spacing, dims, 0, dims ? dims[2] : 0, g, n);
+    if (s != WN_OK) return s;
+    if (n == 0) return WN_OK;
+    if (n_engines == 1) return wn_query_grid(engines[0], origin, spacing, dims, 0, dims[2], beta, flags, out_omega, out_inside, nullptr);
+    // Engine i classifies the tile layers i, i + N, i + 2N, ... (8 z-planes each: the same mix of work on every device, no
+    // exchange step), one host thread per device; the compact per-device results are then laid out in lattice order.
+    const bool bits = (flags & WN_QUERY_OUT_BITS) != 0 && out_inside;
+    const int64_t per_layer = dims[0] * dims[1] * 8, n_layers = (dims[2] + 7) / 8;
+    std::vector<std::vector<float>> om((size_t)n_engines);
+    std::vector<std::vector<uint8_t>> in((size_t)n_engines);
+    std::vector<wn_status> status((size_t)n_engines, WN_OK);
+    std::vector<std::string> errors((size_t)n_engines);
+    std::vector<std::thread> pool;
+    for (int i = 0; i < n_engines; ++i) {
+        int64_t planes = 0;
+        for (int64_t L = i; L < n_layers; L += n_engines) planes += std::min<int64_t>(8, dims[2] - L * 8);
+        const int64_t ni = dims[0] * dims[1] * planes;
+        if (out_omega) om[i].resize((size_t)ni);
+        if (out_inside) in[i].resize((size_t)(bits ? (ni + 7) / 8 : ni));
+        pool.emplace_back([&, i, ni]() {
+            if (ni == 0) return;
+            status[i] = wn_query_grid_strided(engines[i], origin, spacing, dims, i, n_engines, beta, flags, out_omega ? om[i].data() : nullptr,
+                                              out_inside ? in[i].data() : nullptr, nullptr);
+            if (status[i] != WN_OK) errors[i] = wn_last_error();
+        });
+    }
+    for (auto& t : pool) t.join();
+    for (int i = 0; i < n_engines; ++i)
+        if (status[i] != WN_OK) return fail(status[i], "device %d: %s", engines[i]->device, errors[i].c_str());
+    for (int i = 0; i < n_engines; ++i) {
+        int64_t local = 0; // points of engine i consumed so far
+        for (int64_t L = i; L < n_layers; L += n_engines) {
+            const int64_t cnt = dims[0] * dims[1] * std::min<int64_t>(8, dims[2] - L * 8);
+            const int64_t first = L * per_layer;
+            if (out_omega) memcpy(out_omega + first, om[i].data() + local, (size_t)cnt * sizeof(float));
+            if (out_inside && bits) {
+                if ((first & 7) == 0 && (local & 7) == 0) {
+                    memcpy(out_inside + first / 8, in[i].data() + local / 8, (size_t)(cnt + 7) / 8);
+                } else { // layers of nx*ny*8 points are byte aligned; only a ragged lattice tail can land here
+                    for (int64_t k = 0; k < cnt; ++k) {
+                        const int bit = (in[i][(size_t)((local + k) >> 3)] >> ((local + k) & 7)) & 1;
+                        uint8_t& dst = out_inside[(first + k) >> 3];
+                        dst = (uint8_t)((dst & ~(1u << ((first + k) & 7))) | (bit << ((first + k) & 7)));
+                    }
+                }
+            } else if (out_inside) {
+                memcpy(out_inside + first, in[i].data() + local, (size_t)cnt);
+            }
+            local += cnt;
+        }
+    }
     return WN_OK;
 }
 

@@ -314,7 +314,6 @@ __device__ __forceinline__ bool tile_cond_walk(const WnTreeView& t, const float 
     int skip[QPL];
 #pragma unroll
     for (int k = 0; k < QPL; ++k) skip[k] = valid[k] ? 0 : n_items;
-    bool bad = false;
     int i = 0;
     while (i < n_items) {
         const float4 c0 = __ldg(items + 2 * i);
@@ -347,9 +346,8 @@ __device__ __forceinline__ bool tile_cond_walk(const WnTreeView& t, const float 
 #pragma unroll
             for (int k = 0; k < QPL; ++k) {
                 if (farq[k]) {
-                    const float om = eval_record(rx[k], ry[k], rz[k], l2[k], f1, f2, f3, f4, f5);
-                    bad = bad || !(fabsf(om) <= 3.402823466e38f);
-                    acc[k] += om;
+                    // a non-finite value poisons acc for good (inf stays inf or turns NaN): checked once, after the walk
+                    acc[k] += eval_record(rx[k], ry[k], rz[k], l2[k], f1, f2, f3, f4, f5);
                     skip[k] = after;
                     if (STATS) ++cnt.A;
                 }
@@ -378,6 +376,9 @@ __device__ __forceinline__ bool tile_cond_walk(const WnTreeView& t, const float 
             i = anynear ? i + 1 : after;
         }
     }
+    bool bad = false;
+#pragma unroll
+    for (int k = 0; k < QPL; ++k) bad = bad || (valid[k] && !(fabsf(acc[k]) <= 3.402823466e38f));
     return bad;
 }
 
@@ -1184,9 +1185,7 @@ __global__ void __launch_bounds__(kQueryThreads, WN_TQ_MIN_CTAS) k_tile_query(co
                 for (int k = 0; k < QPL; ++k) {
                     const float rx = qx[k] - f0.x, ry = qy[k] - f0.y, rz = qz[k] - f0.z;
                     const float l2 = __fadd_rn(__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)), __fmul_rn(rz, rz)); // as in warp_traverse
-                    const float om = eval_record(rx, ry, rz, l2, f1, f2, f3, f4, f5);
-                    bad = bad || (valid[k] && !(fabsf(om) <= 3.402823466e38f));
-                    acc[k] += om;
+                    acc[k] += eval_record(rx, ry, rz, l2, f1, f2, f3, f4, f5); // non-finite values are caught after the walk
                 }
             }
             // ---- exact triangles: leaves that are near for every point of the tile --------------------------------------

@@ -422,6 +422,31 @@ class FastWindingNumber:
             raise Error(lib.wn_last_error().decode())
         return cls(_handle=h)
 
+    def replicate(self, devices):
+        """Copies of this engine on other GPUs of the same process (wn_replicate: device-to-device copies of the packed tree)."""
+        devices = [int(d) for d in devices]
+        arr = (ctypes.c_int32 * len(devices))(*devices)
+        out = (ctypes.c_void_p * len(devices))()
+        self._check(self._lib.wn_replicate(self._handle(), arr, len(devices), out))
+        return [FastWindingNumber(_handle=ctypes.c_void_p(h)) for h in out]
+
+    @staticmethod
+    def query_grid_multi(engines, origin, spacing, dims, accuracy_scale=None, want_omega=False, want_inside=True, tiling=True, bits=False):
+        """One lattice over several engines holding the same tree (one per GPU, single process): engine i evaluates the tile layers
+        i, i+N, ... from its own host thread; results are gathered in lattice order on the host (wn_query_grid_multi)."""
+        lib = _capi.lib()
+        o, s, d, _, _, n = FastWindingNumber._grid_args(origin, spacing, dims, None)
+        om = np.empty(n, dtype=np.float32) if want_omega else None
+        ins = np.empty((n + 7) // 8 if bits else n, dtype=np.uint8) if want_inside else None
+        hs = (ctypes.c_void_p * len(engines))(*[e._handle() for e in engines])
+        flags = FastWindingNumber._flags(False, tiling) | (_capi.WN_QUERY_OUT_BITS if (bits and ins is not None) else 0)
+        st = lib.wn_query_grid_multi(hs, len(engines), o, s, d, float(accuracy_scale or 0.0), flags,
+                                     ctypes.c_void_p(om.ctypes.data) if om is not None else None,
+                                     ctypes.c_void_p(ins.ctypes.data) if ins is not None else None)
+        if st != _capi.WN_OK:
+            raise Error(lib.wn_last_error().decode())
+        return om, ins
+
     # -- parity hooks ------------------------------------------------------------------------------------------------------
     def debug_node_moments(self, first=0, count=None) -> np.ndarray:
         if count is None:

@@ -38,7 +38,12 @@ struct FastWindingNumber::Impl
     mutable std::vector<char> host_blob;
     mutable WnTreeView host_view{};
     mutable std::string host_error;
-    ~Impl() { wn_destroy(engine); }
+    std::vector<wn_engine*> all; // engine + its replicas on other GPUs (options.devices); empty when single-GPU
+    ~Impl()
+    {
+        for (size_t i = 1; i < all.size(); ++i) wn_destroy(all[i]);
+        wn_destroy(engine);
+    }
 
     const WnTreeView* host_tree() const
     {
@@ -90,11 +95,18 @@ void FastWindingNumber::initialize(const float* vertices, int64_t num_vertices, 
     opt.morton_bits = options.morton_bits;
     opt.hierarchy = options.balanced_hierarchy ? WN_HIERARCHY_KD : static_cast<int>(options.hierarchy);
     opt.radius_mode = options.vertex_radius ? WN_RADIUS_VERTEX : WN_RADIUS_BOX_CORNER;
-    opt.device = options.device;
+    opt.device = options.devices.empty() ? options.device : options.devices[0];
     m_impl = std::make_unique<Impl>();
     m_impl->beta = options.accuracy_scale;
     m_impl->host_single_point = options.host_single_point;
     check(wn_create(vertices, num_vertices, triangles, num_triangles, &opt, &m_impl->engine));
+    if (options.devices.size() > 1) {
+        std::vector<int32_t> others(options.devices.begin() + 1, options.devices.end());
+        std::vector<wn_engine*> reps(others.size(), nullptr);
+        check(wn_replicate(m_impl->engine, others.data(), static_cast<int32_t>(others.size()), reps.data()));
+        m_impl->all.push_back(m_impl->engine);
+        m_impl->all.insert(m_impl->all.end(), reps.begin(), reps.end());
+    }
 }
 
 template <typename Scalar, typename Index>
@@ -165,6 +177,11 @@ void FastWindingNumber::solid_angle(const float* xyz, size_t n, float* out) cons
 void FastWindingNumber::is_inside(const Lattice& l, uint8_t* out, int64_t z_begin, int64_t z_end) const
 {
     const wn_engine* e = engine();
+    if (m_impl->all.size() > 1 && z_begin == 0 && (z_end < 0 || z_end == l.dims[2])) {
+        check(wn_query_grid_multi(m_impl->all.data(), static_cast<int32_t>(m_impl->all.size()), l.origin.data(), l.spacing.data(), l.dims.data(),
+                                  m_impl->beta, WN_QUERY_DEFAULT, nullptr, out));
+        return;
+    }
     check(wn_query_grid(e, l.origin.data(), l.spacing.data(), l.dims.data(), z_begin, z_end < 0 ? l.dims[2] : z_end, m_impl->beta, WN_QUERY_DEFAULT, nullptr,
                         out, nullptr));
 }
@@ -172,6 +189,11 @@ void FastWindingNumber::is_inside(const Lattice& l, uint8_t* out, int64_t z_begi
 void FastWindingNumber::is_inside_bits(const Lattice& l, uint8_t* out, int64_t z_begin, int64_t z_end) const
 {
     const wn_engine* e = engine();
+    if (m_impl->all.size() > 1 && z_begin == 0 && (z_end < 0 || z_end == l.dims[2])) {
+        check(wn_query_grid_multi(m_impl->all.data(), static_cast<int32_t>(m_impl->all.size()), l.origin.data(), l.spacing.data(), l.dims.data(),
+                                  m_impl->beta, WN_QUERY_OUT_BITS, nullptr, out));
+        return;
+    }
     check(wn_query_grid(e, l.origin.data(), l.spacing.data(), l.dims.data(), z_begin, z_end < 0 ? l.dims[2] : z_end, m_impl->beta, WN_QUERY_OUT_BITS,
                         nullptr, out, nullptr));
 }
@@ -179,6 +201,11 @@ void FastWindingNumber::is_inside_bits(const Lattice& l, uint8_t* out, int64_t z
 void FastWindingNumber::solid_angle(const Lattice& l, float* out, int64_t z_begin, int64_t z_end) const
 {
     const wn_engine* e = engine();
+    if (m_impl->all.size() > 1 && z_begin == 0 && (z_end < 0 || z_end == l.dims[2])) {
+        check(wn_query_grid_multi(m_impl->all.data(), static_cast<int32_t>(m_impl->all.size()), l.origin.data(), l.spacing.data(), l.dims.data(),
+                                  m_impl->beta, WN_QUERY_DEFAULT, out, nullptr));
+        return;
+    }
     check(wn_query_grid(e, l.origin.data(), l.spacing.data(), l.dims.data(), z_begin, z_end < 0 ? l.dims[2] : z_end, m_impl->beta, WN_QUERY_DEFAULT, out,
                         nullptr, nullptr));
 }

@@ -11,6 +11,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <memory>
 #include <random>
 #include <thread>
 #include <vector>
@@ -294,6 +295,38 @@ int main()
         size_t bitdiff = 0;
         for (size_t i = 0; i < n; ++i) bitdiff += ((bits[i >> 3] >> (i & 7)) & 1) != bytes[i];
         CHECK(bitdiff == 0);
+    }
+
+    // --- single-process multi-GPU through the drop-in class (options.devices); skipped on a one-GPU box -----------------------
+    {
+        lagrange::winding::FastWindingNumberOptions mo;
+        mo.devices = {0, 1};
+        bool have_two = true;
+        std::unique_ptr<lagrange::winding::FastWindingNumber> multi;
+        try {
+            multi = std::make_unique<lagrange::winding::FastWindingNumber>(mesh, mo);
+        } catch (const lagrange::Error& err) {
+            have_two = false;
+            std::printf("multi-GPU section skipped: %s\n", err.what());
+        }
+        if (have_two) {
+            lagrange::winding::Lattice lat;
+            lat.origin = {-6.5f, -1.5f, -6.5f};
+            lat.spacing = {13.f / 96, 3.f / 40, 13.f / 96};
+            lat.dims = {96, 40, 96};
+            const size_t n = 96 * 40 * 96;
+            std::vector<uint8_t> one(n), two(n), bits((n + 7) / 8);
+            engine.is_inside(lat, one.data());
+            multi->is_inside(lat, two.data());
+            multi->is_inside_bits(lat, bits.data());
+            size_t diff = 0, bitdiff = 0;
+            for (size_t i = 0; i < n; ++i) {
+                diff += one[i] != two[i];
+                bitdiff += ((bits[i >> 3] >> (i & 7)) & 1) != one[i];
+            }
+            std::printf("two GPUs, one process: %zu lattice points, %zu differ from the single-GPU answer\n", n, diff);
+            CHECK(diff == 0 && bitdiff == 0);
+        }
     }
 
     std::printf(g_failures ? "FAILED (%d)\n" : "ALL PASSED\n", g_failures);
