@@ -1002,8 +1002,7 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
             units = (n + wn::kTileQueries - 1) / wn::kTileQueries;
             tiles_per_unit = 1;
         }
-        int64_t default_tiles = 1 << 17;
-        if (host_out) default_tiles = std::min<int64_t>(1 << 15, std::max<int64_t>(1 << 13, (units * tiles_per_unit + 1) / 2));
+        const int64_t default_tiles = 1 << 17;
         const int64_t max_tiles = std::max<int64_t>(1, env_int("WN_TILE_BATCH", (int)default_tiles));
         int64_t units_per_launch = std::max<int64_t>(1, max_tiles / tiles_per_unit);
         // hierarchical planning (lattices): blocks of 2^k x 2^k x (2^k | 1) tiles above the tiles; a batch must hold whole blocks
@@ -1029,10 +1028,28 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
         a.tile_order = (int*)e->s_plan_order.p;
         a.heavy_cond = env_int("WN_TILE_HEAVY", 192);
         a.kappa = tile_kappa();
-        const bool overlap = GRID && ob && (ob->h_omega || ob->h_inside) && units > units_per_launch;
+        // Batches. Device outputs: as few as the scratch allows (every batch boundary costs a launch tail). Host outputs: the same,
+        // plus a SHORT last batch (an eighth of the work): the copy of everything before it overlaps its computation and only its own
+        // small copy is exposed (measured: 8 equal batches lost 4 % end to end to tails; one batch leaves the whole copy exposed).
+        std::vector<int64_t> batch_units;
+        {
+            int64_t tail = 0;
+            if (GRID && host_out && units >= 4) {
+                tail = std::max<int64_t>(1, units / 8);
+                if (plan_levels > 0 && zgroup) {
+                    // planning blocks span 2^levels tile layers: the last batch has to start on a block boundary
+                    const int64_t g = (int64_t)1 << plan_levels, start = (units - tail) / g * g;
+                    tail = start > 0 ? units - start : 0;
+                }
+            }
+            for (int64_t left = units - tail; left > 0; left -= std::min(left, units_per_launch)) batch_units.push_back(std::min(left, units_per_launch));
+            if (tail > 0) batch_units.push_back(tail);
+        }
+        const bool overlap = GRID && ob && (ob->h_omega || ob->h_inside) && batch_units.size() > 1;
         if (overlap && !e->copy_stream) WN_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
-        for (int64_t u0 = 0; u0 < units; u0 += units_per_launch) {
-            const int64_t nunits = std::min(units_per_launch, units - u0);
+        int64_t u0 = 0;
+        for (size_t bi = 0; bi < batch_units.size(); u0 += batch_units[bi], ++bi) {
+            const int64_t nunits = batch_units[bi];
             const int blocks = (int)(nunits * tiles_per_unit);
             if (GRID) {
                 a.tile_z0 = layer_first + (int)u0 * a.layer_step;
