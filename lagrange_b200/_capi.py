@@ -5,7 +5,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libwn_b200.so")
+LIB_PATH = os.environ.get("WN_B200_LIB") or os.path.join(_HERE, "lib", "libwn_b200.so")  # the override is for A/B experiments
 
 WN_OK = 0
 WN_QUERY_DEFAULT = 0

@@ -314,6 +314,7 @@ __device__ __forceinline__ bool tile_cond_walk(const WnTreeView& t, const float 
     int skip[QPL];
 #pragma unroll
     for (int k = 0; k < QPL; ++k) skip[k] = valid[k] ? 0 : n_items;
+    bool bad = false;
     int i = 0;
     while (i < n_items) {
         const float4 c0 = __ldg(items + 2 * i);
@@ -346,8 +347,14 @@ __device__ __forceinline__ bool tile_cond_walk(const WnTreeView& t, const float 
 #pragma unroll
             for (int k = 0; k < QPL; ++k) {
                 if (farq[k]) {
+#ifdef WN_BAD_PER_EVAL
+                    const float om = eval_record(rx[k], ry[k], rz[k], l2[k], f1, f2, f3, f4, f5);
+                    bad = bad || !(fabsf(om) <= 3.402823466e38f);
+                    acc[k] += om;
+#else
                     // a non-finite value poisons acc for good (inf stays inf or turns NaN): checked once, after the walk
                     acc[k] += eval_record(rx[k], ry[k], rz[k], l2[k], f1, f2, f3, f4, f5);
+#endif
                     skip[k] = after;
                     if (STATS) ++cnt.A;
                 }
@@ -376,10 +383,7 @@ __device__ __forceinline__ bool tile_cond_walk(const WnTreeView& t, const float 
             i = anynear ? i + 1 : after;
         }
     }
-    bool bad = false;
-#pragma unroll
-    for (int k = 0; k < QPL; ++k) bad = bad || (valid[k] && !(fabsf(acc[k]) <= 3.402823466e38f));
-    return bad;
+    return bad; // (non-finite sums are also detected by the caller from acc itself)
 }
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -1207,6 +1211,9 @@ __global__ void __launch_bounds__(kQueryThreads, WN_TQ_MIN_CTAS) k_tile_query(co
             }
             // ---- conditional records --------------------------------------------------------------------------------
             bad = tile_cond_walk<QPL, STATS>(a.tree, qx, qy, qz, valid, acc, reinterpret_cast<const float4*>(pk), n_cond, cnt) || bad;
+            // a non-finite far-field value poisons the sum for good (inf stays inf or turns NaN): one check per point, here
+#pragma unroll
+            for (int k = 0; k < QPL; ++k) bad = bad || (oidx[k] >= 0 && !(fabsf(acc[k]) <= 3.402823466e38f));
         }
         // The fallback is a per-warp matter: a point's result never depends on its neighbours.
         if (fallback || __any_sync(kFull, bad)) {
