@@ -353,103 +353,6 @@ __device__ __forceinline__ bool tile_cond_walk(const WnTreeView& t, const float 
                     bad = bad || !(fabsf(om) <= 3.402823466e38f);
                     acc[k] += om;
                     skip[k] = after;
-                        if (STATS) ++cnt.A;
-                    } else {
-                        nearq[k] = true; // non-finite expansion: descend instead (A.5)
-                        if (LISTED && notest) bad = true; // its children are not in the list
-                    }
-                }
-            }
-        }
-        bool anynear = false;
-#pragma unroll
-        for (int k = 0; k < QPL; ++k) anynear |= nearq[k];
-        anynear = __any_sync(kFull, anynear);
-        if (leaf) {
-            if (anynear) {
-                const int first = lk >> WN_LEAF_COUNT_BITS, count = (lk & (WN_MAX_LEAF_SIZE - 1)) + 1;
-                for (int tt = 0; tt < count; ++tt) {
-                    const float4 ta = __ldg(tris + 3 * (int64_t)(first + tt));
-                    const float4 tb = __ldg(tris + 3 * (int64_t)(first + tt) + 1);
-                    const float4 tc = __ldg(tris + 3 * (int64_t)(first + tt) + 2);
-#pragma unroll
-                    for (int k = 0; k < QPL; ++k) {
-                        if (nearq[k]) {
-                            acc[k] += wn_tri_solid_angle(qx[k], qy[k], qz[k], ta, tb, tc);
-                            if (STATS) ++cnt.E;
-                        }
-                    }
-                }
-            }
-            i = i + 1;
-        } else {
-            i = anynear ? i + 1 : after;
-        }
-    }
-    return bad;
-}
-
-// ----------------------------------------------------------------------------------------------------------------
-// The per-point traversal over a tile's conditional list (k_tile_query). Same decisions as warp_traverse, but the list is
-// self-contained for the test: an item is 32 bytes, (Px, Py, Pz, beta^2 R^2) + (key, skip position, leaf link, -), written by the
-// plan, so a step is two consecutive 128-bit loads instead of list -> record (a dependent pair) and the tree is touched only
-// when some lane actually evaluates. A non-finite far-field value makes the warp redo its sub-block with the generic traversal
-// (the reference descends in that case; that path handles it point by point).
-// ----------------------------------------------------------------------------------------------------------------
-template <int QPL, bool STATS>
-__device__ __forceinline__ bool tile_cond_walk(const WnTreeView& t, const float (&qx)[QPL], const float (&qy)[QPL], const float (&qz)[QPL],
-                                               const bool (&valid)[QPL], float (&acc)[QPL], const float4* __restrict__ items, const int n_items,
-                                               TravCounters& cnt)
-{
-    const int lane = threadIdx.x & 31;
-    const float4* __restrict__ hot = t.hot;
-    const float4* __restrict__ cold = t.cold;
-    const float4* __restrict__ tris = t.tri;
-    int skip[QPL];
-#pragma unroll
-    for (int k = 0; k < QPL; ++k) skip[k] = valid[k] ? 0 : n_items;
-    bool bad = false;
-    int i = 0;
-    while (i < n_items) {
-        const float4 c0 = __ldg(items + 2 * i);
-        const int4 c1 = __ldg(reinterpret_cast<const int4*>(items + 2 * i + 1));
-        const int e = c1.x >> 3, after = c1.y;
-        const bool leaf = (c1.x & 4) != 0, notest = (c1.x & 3) == kClsCondFar;
-        float rx[QPL], ry[QPL], rz[QPL], l2[QPL];
-        bool nearq[QPL], farq[QPL];
-        bool anyfar = false, anynear = false;
-#pragma unroll
-        for (int k = 0; k < QPL; ++k) {
-            const bool active = i >= skip[k];
-            rx[k] = qx[k] - c0.x;
-            ry[k] = qy[k] - c0.y;
-            rz[k] = qz[k] - c0.z;
-            // unfused, like the reference (see warp_traverse)
-            l2[k] = __fadd_rn(__fadd_rn(__fmul_rn(rx[k], rx[k]), __fmul_rn(ry[k], ry[k])), __fmul_rn(rz[k], rz[k]));
-            const bool nr = !notest && l2[k] <= c0.w;
-            nearq[k] = active && nr;
-            farq[k] = active && !nr;
-            anyfar |= farq[k];
-            anynear |= nearq[k];
-            if (STATS) cnt.T += (active && !notest) ? 1 : 0;
-        }
-        if (STATS) cnt.V += (lane == 0) ? 32 * QPL : 0;
-        if (__any_sync(kFull, anyfar)) {
-            const float4* __restrict__ cp = cold + 4 * (int64_t)e;
-            const float4 f1 = __ldg(hot + 2 * (int64_t)e + 1);
-            const float4 f2 = __ldg(cp), f3 = __ldg(cp + 1), f4 = __ldg(cp + 2), f5 = __ldg(cp + 3);
-#pragma unroll
-            for (int k = 0; k < QPL; ++k) {
-                if (farq[k]) {
-#ifdef WN_BAD_PER_EVAL
-                    const float om = eval_record(rx[k], ry[k], rz[k], l2[k], f1, f2, f3, f4, f5);
-                    bad = bad || !(fabsf(om) <= 3.402823466e38f);
-                    acc[k] += om;
-#else
-                    // a non-finite value poisons acc for good (inf stays inf or turns NaN): checked once, after the walk
-                    acc[k] += eval_record(rx[k], ry[k], rz[k], l2[k], f1, f2, f3, f4, f5);
-#endif
-                    skip[k] = after;
                     if (STATS) ++cnt.A;
                 }
             }
