@@ -159,6 +159,7 @@ struct wn_engine
     // the per-engine scratch is reused by every call: work submitted on a different stream than the previous call's waits for it
     mutable cudaStream_t last_stream = nullptr;
     mutable cudaEvent_t ev_last = nullptr;
+    mutable cudaEvent_t ev_batch = nullptr; // orders a finished batch before its copy on copy_stream
     mutable bool ev_last_valid = false;
     mutable std::mutex sdf_mu; // wn_sdf_grid runs two passes (sign, distance) over shared scratch: one caller at a time
     mutable DevBuf s_in, s_out_f, s_out_b, s_out_bits, s_sort, s_stats, s_partial, s_plan_hdr, s_plan_items, s_plan_samples, s_plan_order, s_plan_lvl, s_sdf_inside, s_sdf_dense;
@@ -1036,7 +1037,8 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
         std::vector<int64_t> batch_units;
         {
             int64_t tail = 0;
-            if (GRID && host_out && units >= 4) {
+            // (small batches, e.g. one rank's share of a lattice on 8 GPUs: a second batch boundary costs more than the ~2 MB copy)
+            if (GRID && host_out && units >= 4 && units * tiles_per_unit > env_int("WN_TILE_SPLIT_MIN", 1 << 16)) {
                 tail = std::max<int64_t>(1, units / 8);
                 if (plan_levels > 0 && zgroup) {
                     // planning blocks span 2^levels tile layers: the last batch has to start on a block boundary
@@ -1119,11 +1121,9 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
                 const int64_t first = 8 * u0 * per_layer;
                 const int64_t count = std::min<int64_t>(8 * nunits, grid_layers - 8 * u0) * per_layer;
                 if (ob->bits) pack_bits(*ob, first, count, st); // first = 8 * u0 * per_layer: byte aligned
-                cudaEvent_t ev;
-                WN_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-                WN_CUDA(cudaEventRecord(ev, st));
-                WN_CUDA(cudaStreamWaitEvent(e->copy_stream, ev, 0));
-                WN_CUDA(cudaEventDestroy(ev)); // released by the runtime once it has completed
+                if (!e->ev_batch) WN_CUDA(cudaEventCreateWithFlags(&e->ev_batch, cudaEventDisableTiming));
+                WN_CUDA(cudaEventRecord(e->ev_batch, st)); // re-recording is fine: the wait below captures this record
+                WN_CUDA(cudaStreamWaitEvent(e->copy_stream, e->ev_batch, 0));
                 if (ob->h_omega)
                     WN_CUDA(cudaMemcpyAsync(ob->h_omega + first, ob->d_omega + first, (size_t)count * sizeof(float), cudaMemcpyDeviceToHost,
                                             e->copy_stream));
@@ -1513,6 +1513,7 @@ wn_status wn_destroy(wn_engine* e)
         e->p_small.release();
         if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
         if (e->ev_last) cudaEventDestroy(e->ev_last);
+        if (e->ev_batch) cudaEventDestroy(e->ev_batch);
     }
     delete e;
     return WN_OK;
