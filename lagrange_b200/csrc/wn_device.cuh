@@ -620,6 +620,40 @@ WN_HD float wn_tri_solid_angle(float qx, float qy, float qz, const float4& a, co
     return 2.0f * atan2f(num, den);
 }
 
+// Exact mode, fast path. The half solid angle of a triangle is the argument of the complex number (den, num) of
+// wn_tri_solid_angle, and arguments add under multiplication: a group of triangles that each subtend a small angle contributes
+// arg(prod (den_k + i num_k)) — one atan2 per group instead of one per triangle. This folds one triangle into the running product
+// z and reports whether it qualifies: |half angle| < pi/8 (so that eight of them cannot wrap) and den >= 1/2 (so that the product
+// of eight cannot underflow). Anything else (a triangle the query is close to, a vertex on the query, NaN) makes the caller
+// redo the group term by term with wn_tri_solid_angle, which carries the reference's zero rules. Same normalised formulation
+// (one MUFU.RSQ each, denormal squared lengths flush to +inf -> NaN -> the careful path).
+#define WN_EXACT_GROUP 8
+WN_HD bool wn_tri_fold(float qx, float qy, float qz, const float4& a, const float4& b, const float4& c, float& zr, float& zi)
+{
+    float ax = a.x - qx, ay = a.y - qy, az = a.z - qz;
+    float bx = b.x - qx, by = b.y - qy, bz = b.z - qz;
+    float cx = c.x - qx, cy = c.y - qy, cz = c.z - qz;
+    const float ia = wn_rsqrt_ftz(ax * ax + ay * ay + az * az), ib = wn_rsqrt_ftz(bx * bx + by * by + bz * bz), ic = wn_rsqrt_ftz(cx * cx + cy * cy + cz * cz);
+    ax *= ia;
+    ay *= ia;
+    az *= ia;
+    bx *= ib;
+    by *= ib;
+    bz *= ib;
+    cx *= ic;
+    cy *= ic;
+    cz *= ic;
+    const float ux = bx - ax, uy = by - ay, uz = bz - az;
+    const float vx = cx - ax, vy = cy - ay, vz = cz - az;
+    const float num = ax * (uy * vz - uz * vy) + ay * (uz * vx - ux * vz) + az * (ux * vy - uy * vx);
+    const float den = 1.0f + (ax * bx + ay * by + az * bz) + (ax * cx + ay * cy + az * cz) + (bx * cx + by * cy + bz * cz);
+    const float nr = zr * den - zi * num, ni = zr * num + zi * den;
+    zr = nr;
+    zi = ni;
+    // tan(pi/8) = 0.41421356; a hair less, so that eight half angles stay strictly inside (-pi, pi). False for NaN.
+    return fabsf(num) <= 0.4142f * den && den >= 0.5f;
+}
+
 // Closest point of triangle (a, b, c) to p and its squared distance: closest-feature regions (Ericson, Real-Time Collision
 // Detection, 5.1.5). What TriangleAABBTree::get_closest_point evaluates per candidate triangle
 // (modules/bvh/include/lagrange/bvh/TriangleAABBTree.h:84-88).

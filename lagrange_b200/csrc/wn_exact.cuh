@@ -58,6 +58,28 @@ __device__ __forceinline__ void exact_query_point(const ExactArgs& a, int64_t i,
     }
 }
 
+// Sum of the solid angles of `cnt` triangles (3 float4 each, shared memory) seen from (x, y, z). Groups of WN_EXACT_GROUP
+// triangles go through one complex product and one atan2 (wn_tri_fold); a group with a triangle that subtends a large angle from
+// this point (or touches it) is redone term by term with the reference formulation and its zero rules.
+__device__ __forceinline__ float exact_tile_sum(float x, float y, float z, const float4* __restrict__ sh, int cnt)
+{
+    float tile = 0.0f;
+    int t = 0;
+    for (; t + WN_EXACT_GROUP <= cnt; t += WN_EXACT_GROUP) {
+        float zr = 1.0f, zi = 0.0f;
+        bool ok = true;
+#pragma unroll
+        for (int j = 0; j < WN_EXACT_GROUP; ++j) ok = wn_tri_fold(x, y, z, sh[3 * (t + j)], sh[3 * (t + j) + 1], sh[3 * (t + j) + 2], zr, zi) && ok;
+        if (ok) {
+            tile += 2.0f * atan2f(zi, zr);
+        } else {
+            for (int j = 0; j < WN_EXACT_GROUP; ++j) tile += wn_tri_solid_angle(x, y, z, sh[3 * (t + j)], sh[3 * (t + j) + 1], sh[3 * (t + j) + 2]);
+        }
+    }
+    for (; t < cnt; ++t) tile += wn_tri_solid_angle(x, y, z, sh[3 * t], sh[3 * t + 1], sh[3 * t + 2]);
+    return tile;
+}
+
 template <bool GRID>
 __global__ void __launch_bounds__(256) k_exact(const ExactArgs a)
 {
@@ -74,9 +96,7 @@ __global__ void __launch_bounds__(256) k_exact(const ExactArgs a)
         __syncthreads();
         for (int j = threadIdx.x; j < cnt * 3; j += blockDim.x) sh[j] = __ldg(a.tris + 3 * (int64_t)t0 + j);
         __syncthreads();
-        float tile = 0.0f;
-#pragma unroll 4
-        for (int t = 0; t < cnt; ++t) tile += wn_tri_solid_angle(x, y, z, sh[3 * t], sh[3 * t + 1], sh[3 * t + 2]);
+        float tile = exact_tile_sum(x, y, z, sh, cnt);
         const float yk = tile - comp;
         const float tk = sum + yk;
         comp = (tk - sum) - yk;

@@ -242,3 +242,34 @@ def test_sparse_narrow_band_equals_the_dense_block(lb, prim):
         assert np.array_equal(idx, want) and np.array_equal(val, flat[want])
         assert np.array_equal(np.unpackbits(bits, bitorder="little")[: flat.size].astype(bool), flat < 0)
         assert 0 < len(idx) < flat.size
+
+
+def test_exact_mode_grouped_fast_path_keeps_the_zero_rules_and_accuracy(lb, oracle_mod, prim):
+    """K7 folds groups of 8 small-angle triangles into one complex product + one atan2; a group with a triangle the query is
+    close to (or on) is redone term by term with the reference formulation (A.1: a vertex on the query or a zero numerator
+    contribute 0). Queries ON vertices, IN triangle planes (inside and outside the triangle), very close to the surface and
+    far away all have to agree with the double-precision brute force."""
+    V, F = prim.generate_torus(5.0, 1.0, 64, 32)  # 4096 triangles: 16 shared-memory tiles of 256
+    rng = np.random.Generator(np.random.PCG64(3))
+    on_vertex = V[rng.integers(0, len(V), 300)]
+    tri = F[rng.integers(0, len(F), 600)]
+    w = rng.dirichlet(np.ones(3), size=600).astype(np.float32)
+    in_plane_inside = (V[tri[:, 0]] * w[:, :1] + V[tri[:, 1]] * w[:, 1:2] + V[tri[:, 2]] * w[:, 2:3]).astype(np.float32)
+    e1, e2 = V[tri[:, 1]] - V[tri[:, 0]], V[tri[:, 2]] - V[tri[:, 0]]
+    in_plane_outside = (V[tri[:, 0]] + 3.0 * e1 + 2.0 * e2).astype(np.float32)
+    near = prim.near_surface_points(V, F, 5000, sigma_rel=1e-4, seed=9)
+    far = prim.uniform_points_in_bbox(*prim.mesh_bbox(V), 5000, inflate=2.0, seed=10)
+    P = np.concatenate([on_vertex, in_plane_outside, near, far, in_plane_inside]).astype(np.float32)
+    eng = lb.FastWindingNumber(V, F)
+    got = eng.exact_solid_angle(P)
+    want = oracle_mod.exact64(V, F, P)
+    assert np.all(np.isfinite(got))
+    # (a point INSIDE a triangle, in its plane, sits on the 4 pi jump of that triangle's solid angle: which side float rounding puts
+    # it on is arbitrary in any implementation, so those are only required to be finite and within 4 pi of the reference)
+    n_ok = len(P) - len(in_plane_inside)
+    assert np.abs(got[:n_ok] - want[:n_ok]).max() < 2e-5 * 4 * np.pi
+    d = np.abs(got[n_ok:] - want[n_ok:])
+    assert np.all((d < 1e-4 * 4 * np.pi) | (np.abs(d - 4 * np.pi) < 1e-4 * 4 * np.pi) | (np.abs(d - 2 * np.pi) < 1e-4 * 4 * np.pi))
+    # small batches take the warp-per-query kernel: same function, same answers
+    small = eng.exact_solid_angle(P[:100])
+    assert np.abs(small - got[:100]).max() < 1e-5 * 4 * np.pi
