@@ -689,6 +689,8 @@ __global__ void __launch_bounds__(kPlanThreads) k_plan_block(const QueryArgs a)
     const float cx = s_geo[0], cy = s_geo[1], cz = s_geo[2], ra = s_geo[6];
     const float hx = s_geo[3] > 0.0f ? 1.0f / s_geo[3] : 0.0f, hy = s_geo[4] > 0.0f ? 1.0f / s_geo[4] : 0.0f,
                 hz = s_geo[5] > 0.0f ? 1.0f / s_geo[5] : 0.0f;
+    // half extents of the box, inflated like the radius (relative 1e-4 of the radius on every axis)
+    const float bhx = hx + 1e-4f * ra, bhy = hy + 1e-4f * ra, bhz = hz + 1e-4f * ra;
     int round = 0;
     bool stop = s_cnt[2] != 0;
     while (!stop) {
@@ -704,9 +706,14 @@ __global__ void __launch_bounds__(kPlanThreads) k_plan_block(const QueryArgs a)
             const float thr = fabsf(f0.w) * a.beta2;
             const float dx = cx - f0.x, dy = cy - f0.y, dz = cz - f0.z;
             const float D = sqrtf(dx * dx + dy * dy + dz * dz);
-            const float dm = D - ra, dp = D + ra;
-            const bool allfar = dm > 0.0f && dm * dm > thr * 1.0001f;
-            const bool allnear = dp * dp <= thr * 0.9999f;
+            // nearest / farthest point of the block's BOX from the record's centre (the points lie inside the box; the bounding
+            // sphere of a cube has 2.7x its volume and called many records "mixed" that no point of the box disagrees on);
+            // 1e-4 relative slack on the threshold + an absolute one on the box for the rounding of the per-point test
+            const float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
+            const float nx = fmaxf(ax - bhx, 0.0f), ny = fmaxf(ay - bhy, 0.0f), nz = fmaxf(az - bhz, 0.0f);
+            const float fx = ax + bhx, fy = ay + bhy, fz = az + bhz;
+            const bool allfar = nx * nx + ny * ny + nz * nz > thr * 1.0001f;
+            const bool allnear = fx * fx + fy * fy + fz * fz <= thr * 0.9999f;
             if (allfar && D >= a.kappa * ra && D - sqrtf(fabsf(f0.w)) >= 0.5f * a.kappa * ra)
                 plan_append(s_far, &s_cnt[1], kTileFarCap, e, &s_cnt[2], my_ovf);
             else if (allnear && !leaf)
@@ -925,6 +932,8 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
     const float cx = s_geo[0], cy = s_geo[1], cz = s_geo[2], ra = s_geo[6];
     const float hx = s_geo[3] > 0.0f ? 1.0f / s_geo[3] : 0.0f, hy = s_geo[4] > 0.0f ? 1.0f / s_geo[4] : 0.0f,
                 hz = s_geo[5] > 0.0f ? 1.0f / s_geo[5] : 0.0f;
+    // half extents of the box, inflated like the radius (relative 1e-4 of the radius on every axis)
+    const float bhx = hx + 1e-4f * ra, bhy = hy + 1e-4f * ra, bhz = hz + 1e-4f * ra;
 
     // ---- breadth-first classification ----------------------------------------------------------------------------
     // One barrier per round: every round has its own frontier counter (no reset between rounds), and the decision to stop
@@ -947,9 +956,14 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
             const float thr = fabsf(f0.w) * a.beta2;
             const float dx = cx - f0.x, dy = cy - f0.y, dz = cz - f0.z;
             const float D = sqrtf(dx * dx + dy * dy + dz * dz);
-            const float dm = D - ra, dp = D + ra;
-            const bool allfar = dm > 0.0f && dm * dm > thr * 1.0001f;
-            const bool allnear = dp * dp <= thr * 0.9999f;
+            // nearest / farthest point of the block's BOX from the record's centre (the points lie inside the box; the bounding
+            // sphere of a cube has 2.7x its volume and called many records "mixed" that no point of the box disagrees on);
+            // 1e-4 relative slack on the threshold + an absolute one on the box for the rounding of the per-point test
+            const float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
+            const float nx = fmaxf(ax - bhx, 0.0f), ny = fmaxf(ay - bhy, 0.0f), nz = fmaxf(az - bhz, 0.0f);
+            const float fx = ax + bhx, fy = ay + bhy, fz = az + bhz;
+            const bool allfar = nx * nx + ny * ny + nz * nz > thr * 1.0001f;
+            const bool allnear = fx * fx + fy * fy + fz * fz <= thr * 0.9999f;
             if (allfar) {
                 // far set: the record's field must be smooth across the tile, i.e. the tile is small against its distance
                 // both to the expansion centre and to the nearest possible source point (bounding sphere of radius R)
