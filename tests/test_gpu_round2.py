@@ -267,7 +267,14 @@ def test_exact_mode_grouped_fast_path_keeps_the_zero_rules_and_accuracy(lb, orac
     # (a point INSIDE a triangle, in its plane, sits on the 4 pi jump of that triangle's solid angle: which side float rounding puts
     # it on is arbitrary in any implementation, so those are only required to be finite and within 4 pi of the reference)
     n_ok = len(P) - len(in_plane_inside)
-    assert np.abs(got[:n_ok] - want[:n_ok]).max() < 2e-5 * 4 * np.pi
+    err = np.abs(got[:n_ok] - want[:n_ok])
+    n_a, n_b = len(on_vertex) + len(in_plane_outside), len(on_vertex) + len(in_plane_outside) + len(near)
+    assert err[:n_a].max() < 2e-5 * 4 * np.pi and err[n_b:].max() < 2e-5 * 4 * np.pi
+    # 1e-4 of the bbox diagonal from the surface the float32 formulation itself is ill-conditioned (a triangle fills almost a half
+    # space): the bar there is the float32 twin of the reference formulation on the CPU, and BASELINE's 1e-4 * 4 pi against double
+    twin = oracle_mod.exact32(V, F, P[n_a:n_b])
+    assert err[n_a:n_b].max() < 1e-4 * 4 * np.pi
+    assert np.abs(got[n_a:n_b] - twin).max() < 1e-4 * 4 * np.pi
     d = np.abs(got[n_ok:] - want[n_ok:])
     assert np.all((d < 1e-4 * 4 * np.pi) | (np.abs(d - 4 * np.pi) < 1e-4 * 4 * np.pi) | (np.abs(d - 2 * np.pi) < 1e-4 * 4 * np.pi))
     # small batches take the warp-per-query kernel: same function, same answers
