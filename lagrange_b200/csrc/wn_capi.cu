@@ -283,6 +283,14 @@ wn_status finish_build(wn_engine* e, WnBuild& b, BuildArena& arena, size_t blob_
         WN_CUDA(cudaMalloc((void**)&e->blob, (size_t)e->hdr.total_bytes));
     }
     set_view(e);
+    {
+        // the alignment gaps between the sections travel with the blob (wn_tree_pack, broadcasts): keep them defined
+        const int64_t ends[6] = {(int64_t)sizeof(PackedHeader), e->hdr.off_hot + (int64_t)h_size * 32, e->hdr.off_cold + (int64_t)h_size * 64,
+                                 e->hdr.off_kids + (int64_t)h_size * 16, e->hdr.off_tris + (int64_t)b.nL * 48, e->hdr.off_tri_order + (int64_t)b.nL * 4};
+        const int64_t starts[6] = {e->hdr.off_hot, e->hdr.off_cold, e->hdr.off_kids, e->hdr.off_tris, e->hdr.off_tri_order, e->hdr.total_bytes};
+        for (int k = 0; k < 6; ++k)
+            if (starts[k] > ends[k]) WN_CUDA(cudaMemsetAsync(e->blob + ends[k], 0, (size_t)(starts[k] - ends[k]), st));
+    }
     b.hot = (float4*)(e->blob + e->hdr.off_hot);
     b.cold = (float4*)(e->blob + e->hdr.off_cold);
     b.kids = (int4*)(e->blob + e->hdr.off_kids);
@@ -417,6 +425,7 @@ wn_status create_impl(const float* v_xyz, int64_t nV, const int32_t* tri, int64_
         e->hdr.accuracy_scale = opt.accuracy_scale;
         e->hdr.num_vertices = nV;
         WN_CUDA_C(cudaMalloc((void**)&e->blob, (size_t)e->hdr.total_bytes));
+        WN_CUDA_C(cudaMemset(e->blob, 0, (size_t)e->hdr.total_bytes));
         WN_CUDA_C(cudaMemcpy(e->blob, &e->hdr, sizeof(PackedHeader), cudaMemcpyHostToDevice));
         set_view(e);
         fill_info(e);
