@@ -52,11 +52,14 @@ constexpr int kTileQueries = kQueryThreads * kTileQPL;
 #endif
 constexpr int kPlanThreads = WN_PLAN_THREADS;                 // k_tile_plan: latency bound, small CTAs so that many are resident
 constexpr int kPlanWarps = kPlanThreads / 32;
-constexpr int kTileAllCap = 2048;                 // classified records per tile (conditional + direct + exact)
-constexpr int kTileFrontCap = 1024;               // breadth-first frontier
+#ifndef WN_TILE_CAP_SCALE
+#define WN_TILE_CAP_SCALE 1
+#endif
+constexpr int kTileAllCap = 2048 * WN_TILE_CAP_SCALE;   // classified records per tile (conditional + direct + exact)
+constexpr int kTileFrontCap = 1024 * WN_TILE_CAP_SCALE; // breadth-first frontier
 constexpr int kTileFarCap = 512;                  // far set
 constexpr int kTileDirCap = 512;                  // direct records
-constexpr int kTileExactCap = 1024;               // exact leaves (also bounded by the frontier buffer reused for offsets)
+constexpr int kTileExactCap = 1024 * WN_TILE_CAP_SCALE; // exact leaves (also bounded by the frontier buffer reused for offsets)
 constexpr int kPlanMaxRounds = 96;                // breadth-first rounds = hierarchy depth bound (deeper: generic path)
 constexpr int kTileSamples = 64;                  // 4^3 Chebyshev points
 constexpr int kTileSampleStride = 72;             // 64 samples + centre(3) + 1/half-extent(3) + radius + pad
