@@ -101,6 +101,13 @@ public:
     /// holds; what volume::mesh_to_volume asks of OpenVDB with Sign::WindingNumber (mesh_to_volume.cpp:160-183, band = 3 voxels).
     /// Returns the number of cells with distance < band. signed_distance = false skips the predicate.
     int64_t signed_distance(const Lattice& lattice, float band, float* out, bool signed_distance = true) const;
+    /// Sparse variant: only the cells of the band (|d| < band), ordered by linear index (z*ny + y)*nx + x -- what an OpenVDB grid keeps
+    /// active. Returns the size of the band; fills at most `capacity` cells (call with capacity 0 to size the buffers).
+    int64_t signed_distance_sparse(const Lattice& lattice, float band, int64_t capacity, int64_t* index, float* value,
+                                   bool signed_distance = true) const;
+    /// Closest point of the mesh for n query points (bvh::TriangleAABBTree::get_closest_point, modules/bvh/include/lagrange/bvh/
+    /// TriangleAABBTree.h:84-88): squared distance, triangle id, closest point; any output may be null (not all).
+    void closest_point(const float* xyz, size_t n, float* sq_dist, int32_t* triangle, float* point, float max_distance = 0.f) const;
     /// Exact mode: brute-force sum over all triangles (no hierarchy, no approximation).
     void exact_solid_angle(const float* xyz, size_t n, float* out) const;
 

@@ -77,3 +77,40 @@ def sample_points_in_mesh(engine: FastWindingNumber, bbox_min, bbox_max, num_sam
     pts = (raw * (hi - lo)[None, :] + lo[None, :]).astype(np.float32)
     keep = engine.is_inside(pts).astype(bool)
     return pts[keep]
+
+
+# ---- consumers of the closest-point query -------------------------------------------------
+#     compute_mesh_distances / compute_hausdorff / compute_chamfer   modules/bvh/src/compute_mesh_distances.cpp:45-166
+# The reference builds a TriangleAABBTree over the target and calls get_closest_point once per source vertex from a TBB
+# parallel_for (:60-73); here the source's vertices go through wn_closest_point in one batch on the target's engine.
+def _target_engine(target_vertices, target_facets, engine):
+    return engine if engine is not None else FastWindingNumber(target_vertices, target_facets)
+
+
+def compute_mesh_distances(source_vertices, target_vertices, target_facets, engine=None) -> np.ndarray:
+    """Distance from every source vertex to the closest point of the target mesh (float32 [nV]); an empty target gives zeros,
+    like the reference (compute_mesh_distances.cpp:53-56)."""
+    sv = np.ascontiguousarray(source_vertices, dtype=np.float32).reshape(-1, 3)
+    if len(np.asarray(target_facets).reshape(-1, 3)) == 0 or len(sv) == 0:
+        return np.zeros(len(sv), dtype=np.float32)
+    sq, _, _ = _target_engine(target_vertices, target_facets, engine).closest_point(sv)
+    return np.sqrt(sq)
+
+
+def compute_hausdorff(source_vertices, source_facets, target_vertices, target_facets) -> float:
+    """max(directed source->target, directed target->source) over the vertices (compute_mesh_distances.cpp:100-126)."""
+    fwd = compute_mesh_distances(source_vertices, target_vertices, target_facets)
+    bwd = compute_mesh_distances(target_vertices, source_vertices, source_facets)
+    return float(max(fwd.max() if len(fwd) else 0.0, bwd.max() if len(bwd) else 0.0))
+
+
+def compute_chamfer(source_vertices, source_facets, target_vertices, target_facets) -> float:
+    """mean squared source->target distance + mean squared target->source distance (compute_mesh_distances.cpp:128-166)."""
+    fwd = compute_mesh_distances(source_vertices, target_vertices, target_facets).astype(np.float64)
+    bwd = compute_mesh_distances(target_vertices, source_vertices, source_facets).astype(np.float64)
+    out = 0.0
+    if len(fwd):
+        out += float((fwd * fwd).sum() / len(fwd))
+    if len(bwd):
+        out += float((bwd * bwd).sum() / len(bwd))
+    return out

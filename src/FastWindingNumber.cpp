@@ -219,6 +219,20 @@ int64_t FastWindingNumber::signed_distance(const Lattice& l, float band, float* 
     return active;
 }
 
+int64_t FastWindingNumber::signed_distance_sparse(const Lattice& l, float band, int64_t capacity, int64_t* index, float* value, bool signed_distance) const
+{
+    const wn_engine* e = engine();
+    int64_t active = 0;
+    check(wn_sdf_grid_sparse(e, l.origin.data(), l.spacing.data(), l.dims.data(), band, m_impl->beta, signed_distance ? 0u : WN_SDF_UNSIGNED, capacity, index,
+                             value, nullptr, &active, nullptr));
+    return active;
+}
+
+void FastWindingNumber::closest_point(const float* xyz, size_t n, float* sq_dist, int32_t* triangle, float* point, float max_distance) const
+{
+    check(wn_closest_point(engine(), xyz, static_cast<int64_t>(n), max_distance, WN_QUERY_DEFAULT, sq_dist, triangle, point, nullptr));
+}
+
 void FastWindingNumber::exact_solid_angle(const float* xyz, size_t n, float* out) const
 {
     check(wn_exact(engine(), xyz, static_cast<int64_t>(n), out, nullptr, nullptr));

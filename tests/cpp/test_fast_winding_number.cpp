@@ -7,6 +7,7 @@
 // Needs a GPU: run by tests/test_cpp_host_layer.py under the `gpu` marker.
 #include <lagrange/winding/FastWindingNumber.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cmath>
@@ -200,6 +201,36 @@ int main()
         CHECK(sign_mismatch == 0);
         CHECK(size_t(active) == in_band);
         CHECK(worst < 3e-2);
+
+        // sparse narrow band == the dense block's active cells; closest point of the lattice's cell centres agrees with the band
+        {
+            const int64_t m = engine.signed_distance_sparse(lat, band, 0, nullptr, nullptr);
+            CHECK(m == active);
+            std::vector<int64_t> idx(m);
+            std::vector<float> val(m);
+            engine.signed_distance_sparse(lat, band, m, idx.data(), val.data());
+            size_t bad = 0;
+            for (int64_t k = 0; k < m; ++k) bad += val[k] != sdf[idx[k]] || (k > 0 && idx[k] <= idx[k - 1]);
+            CHECK(bad == 0);
+            std::vector<float> pts;
+            for (int64_t k = 0; k < std::min<int64_t>(m, 2000); ++k) {
+                const int64_t i = idx[k] % 40, j = (idx[k] / 40) % 16, kk = idx[k] / (40 * 16);
+                pts.push_back(lat.origin[0] + lat.spacing[0] * (float(i) + 0.5f));
+                pts.push_back(lat.origin[1] + lat.spacing[1] * (float(j) + 0.5f));
+                pts.push_back(lat.origin[2] + lat.spacing[2] * (float(kk) + 0.5f));
+            }
+            const size_t np = pts.size() / 3;
+            std::vector<float> sq(np), cp(3 * np);
+            std::vector<int32_t> tri(np);
+            engine.closest_point(pts.data(), np, sq.data(), tri.data(), cp.data());
+            double worst_cp = 0;
+            for (size_t k = 0; k < np; ++k) {
+                worst_cp = std::max(worst_cp, std::fabs(std::sqrt(double(sq[k])) - std::fabs(double(val[k]))));
+                CHECK(tri[k] >= 0 && tri[k] < 200 * 100 * 2);
+            }
+            std::printf("sparse band: %lld cells; closest point vs band distance: max deviation %.2e\n", (long long)m, worst_cp);
+            CHECK(worst_cp < 1e-5);
+        }
 
         // the balanced k-d hierarchy classifies the lattice like the LBVH does (different trees: allow the surface shell)
         lagrange::winding::FastWindingNumberOptions kd_opt;

@@ -124,3 +124,23 @@ def test_sample_points_in_mesh_gpu(prim, oracle_mod):
     assert len(a ^ b) <= 0.003 * 10000
     w = oracle_mod.exact64(V, F, pts[:500]) / (4 * np.pi)
     assert np.all(w > 0.45)
+
+
+@pytest.mark.gpu
+def test_mesh_distances_hausdorff_chamfer_against_the_brute_force(prim, oracle_mod):
+    """compute_mesh_distances / compute_hausdorff / compute_chamfer (modules/bvh/src/compute_mesh_distances.cpp:45-166) over
+    wn_closest_point, against the double-precision brute-force distance."""
+    from lagrange_b200 import callers
+
+    Va, Fa = prim.generate_torus(5.0, 1.0, 40, 20)
+    Vb, Fb = prim.generate_torus(5.2, 0.8, 36, 18)
+    Vb = (Vb + np.array([0.1, -0.05, 0.2], np.float32)).astype(np.float32)
+    d = callers.compute_mesh_distances(Va, Vb, Fb)
+    ref_ab = oracle_mod.distance64(Vb, Fb, Va)
+    ref_ba = oracle_mod.distance64(Va, Fa, Vb)
+    assert np.abs(d - ref_ab).max() < 1e-5
+    assert callers.compute_hausdorff(Va, Fa, Vb, Fb) == pytest.approx(max(ref_ab.max(), ref_ba.max()), abs=1e-5)
+    assert callers.compute_chamfer(Va, Fa, Vb, Fb) == pytest.approx((ref_ab ** 2).mean() + (ref_ba ** 2).mean(), rel=1e-5)
+    assert np.array_equal(callers.compute_mesh_distances(Va, Vb, np.zeros((0, 3), np.int32)), np.zeros(len(Va), np.float32))
+    # a mesh against itself: every vertex is on the target
+    assert callers.compute_mesh_distances(Va, Va, Fa).max() < 1e-6
