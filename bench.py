@@ -477,7 +477,9 @@ def main():
                  "path": "tiled (k_tile_plan + k_tile_query)" if took_tiles else "generic (k_query)",
                  "reference_algorithm": {"flops_per_query": per_point["algorithmic_flops"] / nq, "tests_per_query": per_point["node_tests"] / nq,
                                          "evals_per_query": per_point["far_field_evals"] / nq, "exact_tris_per_query": per_point["exact_triangles"] / nq,
-                                         "equivalent_tflops": per_point["algorithmic_flops"] / nq * n_local / (ms_local * 1e-3) / 1e12}}
+                                         "equivalent_tflops": per_point["algorithmic_flops"] / nq * n_local / (ms_local * 1e-3) / 1e12,
+                                         "note": "SURVEY 8(d) counts T, A, E of the reference algorithm on the same tree (what the CPU executes per "
+                                                 "query); `achieved` / `frac` above use the smaller number of operations this engine executes"}}
     tf, pms = ctypes.c_float(), ctypes.c_float()
     _capi.check(_capi.lib().wn_debug_fma_peak(local_rank, 1 << 14, ctypes.byref(tf), ctypes.byref(pms)))
     fma_peak = float(tf.value)

@@ -48,7 +48,15 @@ def build_native() -> str | None:
     results are unchanged. Returns None if the compiler is unavailable."""
     src = os.path.join(_HERE, "wn_oracle.cpp")
     out_dir = os.path.join(_HERE, "_native")
-    out = os.path.join(out_dir, "liboracle_wn_native.so")
+    # one file per CPU feature set: a library built -march=native on one host must never be loaded on another (the directory
+    # travels with the repo snapshot to the GPU box, whose CPU may differ)
+    try:
+        flags = next(ln for ln in open("/proc/cpuinfo") if ln.startswith("flags"))
+    except Exception:
+        flags = "unknown"
+    import hashlib
+
+    out = os.path.join(out_dir, "liboracle_wn_native_%s.so" % hashlib.sha1(flags.encode()).hexdigest()[:12])
     try:
         os.makedirs(out_dir, exist_ok=True)
         if (not os.path.exists(out)) or os.path.getmtime(out) < os.path.getmtime(src):
