@@ -1118,7 +1118,13 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
             // a CTA walks a run of consecutive tiles, its warps taking sub-blocks dynamically (see k_tile_query)
             a.launch_tiles = blocks;
             e->last_plan_tiles = blocks;
-            a.tiles_per_cta = std::max(1, env_int("WN_TILE_RUN", 1));
+            // A CTA takes a run of consecutive tiles of the heavy-first order and its 8 warps pull the 8 x run sub-block tasks from a
+            // CTA-local counter: with one tile per CTA every warp gets exactly one task and the CTA lives as long as its slowest
+            // warp. Measured on cfg2 (131072 tiles per launch): run 1 / 2 / 4 / 6 / 8 / 12 -> 7.56 / 7.81 / 7.94 / 7.96 / 7.95 / 7.92
+            // G q/s; with 32768 tiles (one rank of eight): 1 / 2 / 4 / 8 -> 3.87 / 4.01 / 4.04 / 3.83 (long runs lengthen the tail).
+            const int run_auto = (int)std::min<int64_t>(6, std::max<int64_t>(1, (int64_t)blocks / 8192));
+            const int run_env = env_int("WN_TILE_RUN", 0);
+            a.tiles_per_cta = run_env > 0 ? run_env : run_auto;
             const int qblocks = (blocks + a.tiles_per_cta - 1) / a.tiles_per_cta;
             if (stats)
                 wn::k_tile_query<GRID, true><<<qblocks, wn::kQueryThreads, 0, st>>>(a);

@@ -45,8 +45,12 @@ namespace wn {
 #endif
 constexpr int kQueryThreads = 256;
 constexpr int kQueryWarps = kQueryThreads / 32;
-constexpr int kTileQPL = 2;                       // queries per lane in k_tile_query: 8 warps * 32 * 2 = 512 = 8^3
-constexpr int kTileQueries = kQueryThreads * kTileQPL;
+#ifndef WN_TILE_QPL
+#define WN_TILE_QPL 2
+#endif
+constexpr int kTileQPL = WN_TILE_QPL;             // queries per lane in k_tile_query: 2 (8 warp tasks of 4x4x4 points per tile) or 4 (4 tasks of 4x4x8)
+constexpr int kTileQueries = 512;                 // a tile is 8^3 lattice points / 512 consecutive sorted points whatever the split
+constexpr int kTileTasks = kTileQueries / (32 * kTileQPL);
 #ifndef WN_PLAN_THREADS
 #define WN_PLAN_THREADS 128
 #endif
@@ -415,13 +419,40 @@ __device__ __forceinline__ void grid_points(const QueryArgs& a, const int block,
     }
 }
 
+// k_tile_query with 4 queries per lane: task `sub` (0..3) of an 8x8x8 tile = the 4x4x8 column (sub & 1, sub >> 1); lane -> (x, y,
+// z parity), query k -> z pair k
+template <int QPL>
+__device__ __forceinline__ void tile_column_points(const QueryArgs& a, const int block, const int sub, float (&qx)[QPL], float (&qy)[QPL],
+                                                   float (&qz)[QPL], bool (&valid)[QPL], int64_t (&oidx)[QPL])
+{
+    const int lane = threadIdx.x & 31;
+    const int bx = block % a.tiles_x;
+    const int by = (block / a.tiles_x) % a.tiles_y;
+    const int l = block / (a.tiles_x * a.tiles_y);
+    const int bz = a.tile_z0 + l * a.layer_step;
+    const int x = bx * 8 + (sub & 1) * 4 + (lane & 3);
+    const int y = by * 8 + (sub >> 1) * 4 + ((lane >> 2) & 3);
+#pragma unroll
+    for (int k = 0; k < QPL; ++k) {
+        const int dz = 2 * k + (lane >> 4);
+        const int z = a.g.z0 + bz * 8 + dz;
+        const int zl = (a.out_layer0 + l) * 8 + dz;
+        valid[k] = x < a.g.nx && y < a.g.ny && z < a.g.z1;
+        qx[k] = wn_lattice_coord(a.g.ox, a.g.sx, x);
+        qy[k] = wn_lattice_coord(a.g.oy, a.g.sy, y);
+        qz[k] = wn_lattice_coord(a.g.oz, a.g.sz, z);
+        oidx[k] = valid[k] ? ((int64_t)zl * a.g.ny + y) * a.g.nx + x : -1;
+    }
+}
+
 // Points: warp w of block b owns slots [(b*8 + w) * 32*QPL, +32*QPL); `stage` = 24*QPL float4 of shared memory per warp.
 template <int QPL>
 __device__ __forceinline__ void list_points(const QueryArgs& a, int64_t block, const int wid, float4* stage, float (&qx)[QPL],
-                                            float (&qy)[QPL], float (&qz)[QPL], bool (&valid)[QPL], int64_t (&oidx)[QPL])
+                                            float (&qy)[QPL], float (&qz)[QPL], bool (&valid)[QPL], int64_t (&oidx)[QPL],
+                                            const int tasks_per_block = kQueryWarps)
 {
     const int lane = threadIdx.x & 31;
-    const int64_t wbase = (block * kQueryWarps + wid) * (32 * QPL);
+    const int64_t wbase = (block * tasks_per_block + wid) * (32 * QPL);
     const bool staged = a.perm == nullptr && a.q_aligned16 && wbase + 32 * QPL <= a.n;
     if (staged) {
         // 32*QPL points = 96*QPL floats = 24*QPL float4, contiguous and 16-byte aligned: vectorised, coalesced
@@ -1170,21 +1201,23 @@ __global__ void __launch_bounds__(kQueryThreads, WN_TQ_MIN_CTAS) k_tile_query(co
     if (threadIdx.x == 0) s_next = 0;
     __syncthreads();
     const int tile0 = (int)blockIdx.x * a.tiles_per_cta;
-    const int n_task = min(a.tiles_per_cta, a.launch_tiles - tile0) * kQueryWarps;
+    const int n_task = min(a.tiles_per_cta, a.launch_tiles - tile0) * kTileTasks;
     TravCounters cnt;
     while (true) {
         int task = 0;
         if (lane == 0) task = atomicAdd(&s_next, 1);
         task = __shfl_sync(kFull, task, 0);
         if (task >= n_task) break;
-        const int tile = __ldg(a.tile_order + tile0 + task / kQueryWarps), sub = task % kQueryWarps;
+        const int tile = __ldg(a.tile_order + tile0 + task / kTileTasks), sub = task % kTileTasks;
         float qx[QPL], qy[QPL], qz[QPL], acc[QPL];
         bool valid[QPL];
         int64_t oidx[QPL];
-        if (GRID)
+        if (GRID && QPL == 2)
             grid_points<QPL>(a, tile, sub, qx, qy, qz, valid, oidx);
+        else if (GRID)
+            tile_column_points<QPL>(a, tile, sub, qx, qy, qz, valid, oidx);
         else
-            list_points<QPL>(a, (int64_t)tile + a.tile_base, sub, stage + (threadIdx.x >> 5) * 24 * QPL, qx, qy, qz, valid, oidx);
+            list_points<QPL>(a, (int64_t)tile + a.tile_base, sub, stage + (threadIdx.x >> 5) * 24 * QPL, qx, qy, qz, valid, oidx, kTileTasks);
         const int4 h4 = __ldg(reinterpret_cast<const int4*>(a.plan_hdr + tile));
         const long long offset = __ldg(&a.plan_hdr[tile].offset);
         const int n_cond = h4.x, n_dir = h4.y, n_tri = h4.z;
