@@ -887,13 +887,19 @@ wn_status stage_points(const wn_engine* e, const float* q_xyz, int64_t n, const 
     return WN_OK;
 }
 
+// `blocks` = groups of 8 warp tasks (a lattice tile of 8 x 8 x 4*QPL points, or 256*QPL consecutive points); a CTA takes a run of them
 template <bool GRID, bool STATS>
-void launch_query(int qpl, int blocks, const wn::QueryArgs& a, cudaStream_t st)
+void launch_query(int qpl, int blocks, const wn::QueryArgs& a_in, cudaStream_t st)
 {
+    wn::QueryArgs a = a_in;
+    const int run_env = env_int("WN_QUERY_RUN", 0);
+    a.tiles_per_cta = run_env > 0 ? run_env : (int)std::min<int64_t>(4, std::max<int64_t>(1, (int64_t)blocks / 8192));
+    a.launch_tiles = blocks;
+    const int ctas = (blocks + a.tiles_per_cta - 1) / a.tiles_per_cta;
     if (qpl == 2)
-        wn::k_query<2, GRID, STATS><<<blocks, wn::kQueryThreads, 0, st>>>(a);
+        wn::k_query<2, GRID, STATS><<<ctas, wn::kQueryThreads, 0, st>>>(a);
     else
-        wn::k_query<1, GRID, STATS><<<blocks, wn::kQueryThreads, 0, st>>>(a);
+        wn::k_query<1, GRID, STATS><<<ctas, wn::kQueryThreads, 0, st>>>(a);
 }
 
 int pick_qpl(int64_t n)
