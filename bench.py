@@ -8,8 +8,8 @@ Default workload (BASELINE.json configs[1]): is_inside classif
 [-1.1, 1.1]^3 (134 217 728 queries) against an icosahedron midpoint-subdivided 8x (1 310 720 triangles), beta = 2, order 2,
 on the reference builder's own hierarchy built on the GPU (WN_HIERARCHY_REFERENCE: results match the reference algorithm).
 One "step" = one pass of the query path over the whole query set (the tree is built once, before the timed region; its build
-time is reported beside the throughput). With N GPUs the queries are sharded (lattices: tile layers round-robin; point sets:
-index ranges), the tree is built on rank 0 and broadcast once with NCCL; there is no collective on the query path.
+time is reported beside the throughput). With N GPUs the queries are sharded (lattices: diagonally, one y-part of every c-th
+tile layer per rank; point sets: index ranges), the tree is built on rank 0 and broadcast once with NCCL; there is no collective on the query path.
 --config 1/3/4/5 run the other BASELINE configs through the same flow (cfg4/cfg5 are point sets: device-resident points for
 `value`, pinned host points + H2D inside the timed region for `e2e`); --mode exact times the brute-force all-pairs mode (cfg5's
 mesh, a bounded number of queries per step).
@@ -107,8 +107,8 @@ def workload(args):
 def config_dict(args, name, n_total):
     """The same `config` for both arms (the driver compares them key by key)."""
     return {"workload": name, "queries_per_step": n_total, "mode": args.mode,
-            "sharding": f"lattices: tile layers (8 z-planes) round-robin over {args.gpus} rank(s); point sets: index ranges; tree built on rank 0 "
-                        "and broadcast; CPU arm: rank 0 only",
+            "sharding": f"lattices: diagonal over {args.gpus} rank(s) (one y-part of every c-th 8-plane tile layer per rank, wn_query_grid_sharded); "
+                        "point sets: index ranges; tree built on rank 0 and broadcast; CPU arm: rank 0 only",
             "l2": "GPU arm: flushed between timed steps (256 MiB fill); CPU arm: not applicable",
             "gpu_arm": {"hierarchy": args.hierarchy, "leaf_size": 1 if args.hierarchy == "reference" else args.leaf_size,
                         "tiled": os.environ.get("WN_TILE", "1") != "0"},
@@ -278,7 +278,7 @@ def main():
     import torch
 
     import lagrange_b200 as lb
-    from lagrange_b200.distributed import interleaved_layers, replicate_engine, shard_range
+    from lagrange_b200.distributed import replicate_engine, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -336,11 +336,12 @@ def main():
     lo = 0
     if grid:
         origin, spacing, dims = wl["lattice"]
-        # rank r classifies the tile layers r, r+N, r+2N, ... (8 z-planes each) in ONE strided call: same mix of work on every
-        # rank (contiguous z-slabs of a sphere load-imbalance: measured 6.5x at 8 GPUs), results compact in the rank's buffer
-        ranges = interleaved_layers(int(dims[2]), rank, world, depth=8)
-        n_local = int(dims[0] * dims[1]) * sum(b - a for a, b in ranges)
-        layers = (rank, world) if world > 1 else None
+        # diagonal sharding (wn_query_grid_sharded): rank r takes, of every c-th tile layer, one of Q y-parts, so that every rank sees
+        # every part and every height equally often; ONE call per rank, results compact in the rank's buffer. (Whole layers dealt
+        # round-robin cap the efficiency at 0.906 on 8 GPUs: 58 of the 64 layers carry work, 8 + 7 + ...; contiguous z-slabs: 0.81.)
+        shard = (rank, world) if world > 1 else None
+        layout = lb.FastWindingNumber.shard_layout(dims, rank, world)
+        n_local = layout["n_points"]
         h2d_bytes = 60
     else:
         lo, hi = shard_range(n_total, rank, world)
@@ -355,7 +356,7 @@ def main():
         if exact:
             eng.exact_solid_angle(pts_dev, out=out_dev)
         elif grid:
-            eng.query_grid(origin, spacing, dims, want_inside=True, out_inside=out_dev, layers=layers)
+            eng.query_grid(origin, spacing, dims, want_inside=True, out_inside=out_dev, shard=shard)
         else:
             eng.is_inside(pts_dev, out=out_dev)
 
@@ -408,7 +409,7 @@ def main():
         if exact:
             eng.exact_solid_angle(pts_np, out=out_host)
         elif grid:
-            eng.query_grid(origin, spacing, dims, want_inside=True, out_inside=out_host, layers=layers, bits=True)
+            eng.query_grid(origin, spacing, dims, want_inside=True, out_inside=out_host, shard=shard, bits=True)
         else:
             eng.is_inside(pts_np, out=out_host, bits=True)
 
@@ -456,12 +457,7 @@ def main():
     else:
         def stats(tiling):
             if grid:
-                tot = {}
-                for za, zb in ranges:
-                    st = eng.query_stats_grid(origin, spacing, dims, z_range=(za, zb), tiling=tiling)
-                    for k, v in st.items():
-                        tot[k] = tot.get(k, 0) + v
-                return tot
+                return eng.query_stats_grid(origin, spacing, dims, tiling=tiling)  # whole lattice: per-query averages are what is used
             return eng.query_stats(pts_dev, tiling=tiling)
 
         executed = stats(tiled)
@@ -513,14 +509,19 @@ def main():
         m = min(n_local, 1 << 18)
         sel = np.linspace(0, n_local - 1, m).astype(np.int64)
         if grid:
-            per = int(dims[0] * dims[1])
-            planes = np.asarray([z for a, b in ranges for z in range(a, b)], dtype=np.int64)
-            zz = planes[sel // per]
-            rem = sel % per
+            # lattice indices of the sampled output positions, from the rank's unit layout (z0, z1, y0, y1 per unit, x fastest)
+            nx = int(dims[0])
+            starts = np.cumsum([0] + [(z1 - z0) * (y1 - y0) * nx for z0, z1, y0, y1 in layout["units"]])
+            u = np.searchsorted(starts, sel, side="right") - 1
+            units = np.asarray(layout["units"], dtype=np.int64)
+            rem = sel - starts[u]
+            rows = units[u, 3] - units[u, 2]
+            ix = rem % nx
+            iy = units[u, 2] + (rem // nx) % rows
+            iz = units[u, 0] + rem // (nx * rows)
             half = np.float32(0.5)
-            P = np.stack([origin[0] + spacing[0] * ((rem % int(dims[0])).astype(np.float32) + half),
-                          origin[1] + spacing[1] * ((rem // int(dims[0])).astype(np.float32) + half),
-                          origin[2] + spacing[2] * (zz.astype(np.float32) + half)], axis=1).astype(np.float32)
+            P = np.stack([origin[0] + spacing[0] * (ix.astype(np.float32) + half), origin[1] + spacing[1] * (iy.astype(np.float32) + half),
+                          origin[2] + spacing[2] * (iz.astype(np.float32) + half)], axis=1).astype(np.float32)
         else:
             P = wl["points"][lo:lo + n_local][sel]
         refe = oracle.RefEngine(wl["V"], wl["F"])

@@ -178,6 +178,19 @@ WN_API wn_status wn_query_grid_strided(const wn_engine* e, const float origin[3]
                                        int64_t layer_first, int64_t layer_step, float beta, uint32_t flags, float* out_omega,
                                        uint8_t* out_inside, void* stream);
 
+/* Diagonal sharding of a lattice across `world` GPUs (what bench.py uses): the lattice is cut in Q parts along y (Q = 4, 2 or 1: the
+ * largest that divides both `world` and the tile rows, ny % (8 Q) == 0) and rank r evaluates, of every c-th tile layer (c = world / Q,
+ * starting at layer r mod c), the one part ((r - layer) / c) mod Q. Every rank sees every part and every height equally often and the
+ * unit of balance is a Q-th of a layer (whole layers dealt to 8 ranks cap the efficiency at 0.906 on a 64-layer lattice whose end
+ * layers are empty). Output: the rank's units in layer order, each planes x part_rows x nx values (planes = 8, fewer for the last
+ * layer); wn_grid_shard_layout describes it. Q == 1 is exactly wn_query_grid_strided(rank, world). Honours WN_QUERY_OUT_BITS. */
+WN_API wn_status wn_query_grid_sharded(const wn_engine* e, const float origin[3], const float spacing[3], const int64_t dims[3], int32_t rank,
+                                       int32_t world, float beta, uint32_t flags, float* out_omega, uint8_t* out_inside, void* stream);
+/* Layout of rank's output: unit k (k = 0 .. n_units-1) = tile layer lz = rank % layer_step + k * layer_step, rows
+ * [q * part_rows, (q + 1) * part_rows) with q = ((rank - lz) / layer_step) mod parts_y (non-negative), planes [8 lz, min(nz, 8 lz + 8)). */
+WN_API wn_status wn_grid_shard_layout(const int64_t dims[3], int32_t rank, int32_t world, int32_t* parts_y, int32_t* layer_step,
+                                      int64_t* part_rows, int64_t* n_units, int64_t* n_points);
+
 /* Counters of the traversal for a batch of points (same traversal as wn_solid_angle, results discarded). */
 WN_API wn_status wn_query_stats_points(const wn_engine* e, const float* q_xyz, int64_t n, float beta, uint32_t flags,
                                        wn_query_stats* stats, void* stream);

@@ -70,6 +70,9 @@ SIGNATURES = {
     "wn_is_inside": (ctypes.c_int, [_vp, _vp, _i64, _f, _u32, _vp, _vp]),
     "wn_query_grid": (ctypes.c_int, [_vp, _f3, _f3, _l3, _i64, _i64, _f, _u32, _vp, _vp, _vp]),
     "wn_query_grid_strided": (ctypes.c_int, [_vp, _f3, _f3, _l3, _i64, _i64, _f, _u32, _vp, _vp, _vp]),
+    "wn_query_grid_sharded": (ctypes.c_int, [_vp, _f3, _f3, _l3, _i32, _i32, _f, _u32, _vp, _vp, _vp]),
+    "wn_grid_shard_layout": (ctypes.c_int, [_l3, _i32, _i32, ctypes.POINTER(_i32), ctypes.POINTER(_i32), ctypes.POINTER(_i64), ctypes.POINTER(_i64),
+                                            ctypes.POINTER(_i64)]),
     "wn_query_stats_points": (ctypes.c_int, [_vp, _vp, _i64, _f, _u32, ctypes.POINTER(wn_query_stats), _vp]),
     "wn_query_stats_grid": (ctypes.c_int, [_vp, _f3, _f3, _l3, _i64, _i64, _f, _u32, ctypes.POINTER(wn_query_stats), _vp]),
     "wn_exact": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),

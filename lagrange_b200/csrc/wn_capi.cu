@@ -993,7 +993,7 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
     }
     const int layer_first = a.tile_z0; // lattices: first tile layer (8 z-planes) of this call; 0 unless strided
     if (!tiled) {
-        const int qpl = (GRID && a.layer_step > 1) ? 2 : pick_qpl(n);
+        const int qpl = (GRID && (a.layer_step > 1 || a.shard_q > 1)) ? 2 : pick_qpl(n);
         int64_t blocks64;
         if (GRID) {
             const int tz = (int)((grid_layers + 4 * qpl - 1) / (4 * qpl));
@@ -1025,7 +1025,7 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
         int64_t units_per_launch = std::max<int64_t>(1, max_tiles / tiles_per_unit);
         // hierarchical planning (lattices): blocks of 2^k x 2^k x (2^k | 1) tiles above the tiles; a batch must hold whole blocks
         const int plan_levels = GRID ? std::max(0, std::min(3, env_int("WN_PLAN_LEVELS", 2))) : 0;
-        const bool zgroup = GRID && a.layer_step == 1;
+        const bool zgroup = GRID && a.layer_step == 1 && a.shard_q <= 1;
         if (plan_levels > 0 && zgroup && units_per_launch >= (1 << plan_levels)) units_per_launch &= ~(int64_t)((1 << plan_levels) - 1);
         const int64_t launch_tiles = std::min(units, units_per_launch) * tiles_per_unit;
         if (launch_tiles > INT_MAX / 2)
@@ -1138,7 +1138,7 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
                 wn::k_tile_query<GRID, false><<<qblocks, wn::kQueryThreads, 0, st>>>(a);
             if (overlap) {
                 // results of z layers [8*u0, 8*(u0+nunits)) of the slab are final: ship them while the next batch runs
-                const int64_t per_layer = (int64_t)a.g.nx * a.g.ny;
+                const int64_t per_layer = (int64_t)a.g.nx * a.part_ny;
                 const int64_t first = 8 * u0 * per_layer;
                 const int64_t count = std::min<int64_t>(8 * nunits, grid_layers - 8 * u0) * per_layer;
                 if (ob->bits) pack_bits(*ob, first, count, st); // first = 8 * u0 * per_layer: byte aligned
@@ -1323,22 +1323,59 @@ wn_status check_grid(const float* origin, const float* spacing, const int64_t* d
 
 // layer_step == 1: the z-slab [z0, z1). layer_step > 1: the tile layers (8 z-planes each, counted from z = 0) layer_first,
 // layer_first + layer_step, ... of the whole lattice, results stored compactly in that order (z0/z1 ignored).
+// Diagonal sharding of a lattice over `world` ranks (wn_query_grid_sharded): the lattice is cut in Q parts along y and rank r takes,
+// of every c-th tile layer (c = world / Q, starting at r mod c), the ONE part ((r - layer) / c) mod Q. Every rank sees every part and
+// every height equally often, and the unit of balance is a Q-th of a layer: dealing whole layers to 8 ranks leaves 64 layers of which
+// 58 carry work as 8 + 7 + ... (efficiency bound 0.906 on cfg2, measured 0.908). Q = 4 or 2 when world and the tile rows allow it,
+// else 1 (whole layers, the same as wn_query_grid_strided).
+struct ShardLayout
+{
+    int Q = 1, c = 1;
+    int64_t part_rows = 0, n_units = 0, planes = 0;
+};
+ShardLayout shard_layout(const int64_t* dims, int rank, int world)
+{
+    ShardLayout L;
+    const int64_t ny = dims[1], nz = dims[2];
+    for (int q : {4, 2}) {
+        if (world % q == 0 && ny % (8 * q) == 0 && ny > 0) {
+            L.Q = q;
+            break;
+        }
+    }
+    L.c = world / L.Q;
+    L.part_rows = L.Q > 1 ? ny / L.Q : ny;
+    const int64_t n_layers = (nz + 7) / 8;
+    for (int64_t lz = rank % L.c; lz < n_layers; lz += L.c) {
+        ++L.n_units;
+        L.planes += std::min<int64_t>(8, nz - lz * 8);
+    }
+    return L;
+}
+
 wn_status grid_impl(const wn_engine* e, const float* origin, const float* spacing, const int64_t* dims, int64_t z0, int64_t z1, float beta,
                     uint32_t flags, float* out_omega, uint8_t* out_inside, wn_query_stats* stats, void* stream, int64_t layer_first = 0,
-                    int64_t layer_step = 1)
+                    int64_t layer_step = 1, int shard_rank = 0, int shard_world = 0)
 {
     if (!e) return fail(WN_ERR_INVALID_ARGUMENT, "engine is null");
     if (!out_omega && !out_inside && !stats) return fail(WN_ERR_INVALID_ARGUMENT, "no output requested");
     wn::GridDesc g;
     int64_t n = 0;
-    if (layer_step > 1 && dims) {
+    if ((layer_step > 1 || shard_world > 1) && dims) {
         z0 = 0;
         z1 = dims[2];
     }
     wn_status s = check_grid(origin, spacing, dims, z0, z1, g, n);
     if (s != WN_OK) return s;
     int64_t local_planes = z1 - z0;
-    if (layer_step > 1) {
+    ShardLayout sh;
+    if (shard_world > 1) {
+        sh = shard_layout(dims, shard_rank, shard_world);
+        layer_first = shard_rank % sh.c;
+        layer_step = sh.c;
+        local_planes = sh.planes;
+        n = dims[0] * sh.part_rows * local_planes;
+    } else if (layer_step > 1) {
         if (layer_first < 0 || layer_step > (1 << 20)) return fail(WN_ERR_INVALID_ARGUMENT, "bad layer_first / layer_step");
         local_planes = 0;
         for (int64_t L = layer_first; L * 8 < dims[2]; L += layer_step) local_planes += std::min<int64_t>(8, dims[2] - L * 8);
@@ -1364,9 +1401,17 @@ wn_status grid_impl(const wn_engine* e, const float* origin, const float* spacin
     a.out_inside = ob.d_inside;
     a.tiles_x = (g.nx + 7) / 8;
     a.tiles_y = (g.ny + 7) / 8;
+    a.part_ny = g.ny;
     a.layer_step = (int)std::max<int64_t>(1, layer_step);
-    a.tile_z0 = layer_step > 1 ? (int)layer_first : 0;
+    a.tile_z0 = (layer_step > 1 || shard_world > 1) ? (int)layer_first : 0;
     a.out_layer0 = 0;
+    if (shard_world > 1 && sh.Q > 1) {
+        a.shard_q = sh.Q;
+        a.shard_c = sh.c;
+        a.shard_r = shard_rank;
+        a.part_ny = (int)sh.part_rows;
+        a.tiles_y = (int)(sh.part_rows / 8);
+    }
     bool copied = false;
     s = dispatch_query<true>(e, a, n, local_planes, want_tiling(e, n, flags, true), stats, st, &ob, &copied);
     if (s != WN_OK) return s;
@@ -1571,6 +1616,28 @@ wn_status wn_query_grid_strided(const wn_engine* e, const float origin[3], const
     if (layer_step < 1) return fail(WN_ERR_INVALID_ARGUMENT, "layer_step must be >= 1");
     if (layer_step == 1) return grid_impl(e, origin, spacing, dims, layer_first * 8, dims ? dims[2] : 0, beta, flags, out_omega, out_inside, nullptr, stream);
     return grid_impl(e, origin, spacing, dims, 0, 0, beta, flags, out_omega, out_inside, nullptr, stream, layer_first, layer_step);
+}
+
+wn_status wn_query_grid_sharded(const wn_engine* e, const float origin[3], const float spacing[3], const int64_t dims[3], int32_t rank, int32_t world,
+                                float beta, uint32_t flags, float* out_omega, uint8_t* out_inside, void* stream)
+{
+    if (world < 1 || rank < 0 || rank >= world || world > (1 << 16)) return fail(WN_ERR_INVALID_ARGUMENT, "rank / world out of range");
+    if (world == 1) return grid_impl(e, origin, spacing, dims, 0, dims ? dims[2] : 0, beta, flags, out_omega, out_inside, nullptr, stream);
+    return grid_impl(e, origin, spacing, dims, 0, 0, beta, flags, out_omega, out_inside, nullptr, stream, 0, 1, rank, world);
+}
+
+wn_status wn_grid_shard_layout(const int64_t dims[3], int32_t rank, int32_t world, int32_t* parts_y, int32_t* layer_step, int64_t* part_rows,
+                               int64_t* n_units, int64_t* n_points)
+{
+    if (!dims || world < 1 || rank < 0 || rank >= world || dims[0] < 0 || dims[1] < 0 || dims[2] < 0)
+        return fail(WN_ERR_INVALID_ARGUMENT, "bad lattice or rank / world");
+    const ShardLayout L = shard_layout(dims, rank, world);
+    if (parts_y) *parts_y = L.Q;
+    if (layer_step) *layer_step = L.c;
+    if (part_rows) *part_rows = L.part_rows;
+    if (n_units) *n_units = L.n_units;
+    if (n_points) *n_points = dims[0] * L.part_rows * L.planes;
+    return WN_OK;
 }
 
 wn_status wn_query_stats_points(const wn_engine* e, const float* q_xyz, int64_t n, float beta, uint32_t flags, wn_query_stats* stats, void* stream)

@@ -104,6 +104,10 @@ struct QueryArgs
     GridDesc g;
     int tiles_x, tiles_y, tile_z0;
     int layer_step, out_layer0; // strided layers: CTA layer l -> lattice layer tile_z0 + l*layer_step, output layer out_layer0 + l
+    // diagonal sharding (wn_query_grid_sharded): the lattice is cut in shard_q parts along y (part_ny rows each, a multiple of 8;
+    // tiles_y counts the tile rows of ONE part) and a layer of this call covers one part only: layer lz -> part
+    // ((shard_r - lz) / shard_c) mod shard_q. shard_q <= 1: whole rows (part_ny = ny).
+    int shard_q, shard_c, shard_r, part_ny;
     // outputs (either may be null)
     float* out_omega;
     uint8_t* out_inside;
@@ -393,6 +397,18 @@ __device__ __forceinline__ bool tile_cond_walk(const WnTreeView& t, const float 
 // ----------------------------------------------------------------------------------------------------------------
 // Query point set-up shared by the kernels. Grid: CTA tile = 8 x 8 x (4*QPL) lattice points, warp tile 4 x 4 x (2*QPL).
 // ----------------------------------------------------------------------------------------------------------------
+// Lattice tile layer and first row of CTA layer l of this launch (see QueryArgs: strided layers, diagonal sharding).
+__device__ __forceinline__ void layer_geom(const QueryArgs& a, const int l, int& bz, int& y0)
+{
+    bz = a.tile_z0 + l * a.layer_step;
+    y0 = 0;
+    if (a.shard_q > 1) {
+        int q = ((a.shard_r - bz) / a.shard_c) % a.shard_q; // shard_r - bz is a multiple of shard_c by construction
+        if (q < 0) q += a.shard_q;
+        y0 = q * a.part_ny;
+    }
+}
+
 template <int QPL>
 __device__ __forceinline__ void grid_points(const QueryArgs& a, const int block, const int wid, float (&qx)[QPL], float (&qy)[QPL],
                                             float (&qz)[QPL], bool (&valid)[QPL], int64_t (&oidx)[QPL])
@@ -403,9 +419,11 @@ __device__ __forceinline__ void grid_points(const QueryArgs& a, const int block,
     // CTA layer l of this launch covers the lattice layer tile_z0 + l * layer_step (strided sharding across GPUs: every
     // layer_step-th layer, results stored compactly: local layer out_layer0 + l)
     const int l = block / (a.tiles_x * a.tiles_y);
-    const int bz = a.tile_z0 + l * a.layer_step;
+    int bz, y0;
+    layer_geom(a, l, bz, y0);
     const int x = bx * 8 + (wid & 1) * 4 + (lane & 3);
-    const int y = by * 8 + ((wid >> 1) & 1) * 4 + ((lane >> 2) & 3);
+    const int yl = by * 8 + ((wid >> 1) & 1) * 4 + ((lane >> 2) & 3); // row inside the part (= the lattice row when not sharded in y)
+    const int y = y0 + yl;
 #pragma unroll
     for (int k = 0; k < QPL; ++k) {
         const int dz = (wid >> 2) * (2 * QPL) + 2 * k + (lane >> 4);
@@ -415,7 +433,7 @@ __device__ __forceinline__ void grid_points(const QueryArgs& a, const int block,
         qx[k] = wn_lattice_coord(a.g.ox, a.g.sx, x);
         qy[k] = wn_lattice_coord(a.g.oy, a.g.sy, y);
         qz[k] = wn_lattice_coord(a.g.oz, a.g.sz, z);
-        oidx[k] = valid[k] ? ((int64_t)zl * a.g.ny + y) * a.g.nx + x : -1;
+        oidx[k] = valid[k] ? ((int64_t)zl * a.part_ny + yl) * a.g.nx + x : -1;
     }
 }
 
@@ -429,9 +447,11 @@ __device__ __forceinline__ void tile_column_points(const QueryArgs& a, const int
     const int bx = block % a.tiles_x;
     const int by = (block / a.tiles_x) % a.tiles_y;
     const int l = block / (a.tiles_x * a.tiles_y);
-    const int bz = a.tile_z0 + l * a.layer_step;
+    int bz, y0;
+    layer_geom(a, l, bz, y0);
     const int x = bx * 8 + (sub & 1) * 4 + (lane & 3);
-    const int y = by * 8 + (sub >> 1) * 4 + ((lane >> 2) & 3);
+    const int yl = by * 8 + (sub >> 1) * 4 + ((lane >> 2) & 3);
+    const int y = y0 + yl;
 #pragma unroll
     for (int k = 0; k < QPL; ++k) {
         const int dz = 2 * k + (lane >> 4);
@@ -441,7 +461,7 @@ __device__ __forceinline__ void tile_column_points(const QueryArgs& a, const int
         qx[k] = wn_lattice_coord(a.g.ox, a.g.sx, x);
         qy[k] = wn_lattice_coord(a.g.oy, a.g.sy, y);
         qz[k] = wn_lattice_coord(a.g.oz, a.g.sz, z);
-        oidx[k] = valid[k] ? ((int64_t)zl * a.g.ny + y) * a.g.nx + x : -1;
+        oidx[k] = valid[k] ? ((int64_t)zl * a.part_ny + yl) * a.g.nx + x : -1;
     }
 }
 
@@ -696,10 +716,11 @@ __global__ void __launch_bounds__(kPlanThreads) k_plan_block(const QueryArgs a)
     __syncthreads();
     if (tid == 0) {
         const int span = 8 << a.lvl_shift;
-        const int zt = a.tile_z0 + (Z << a.lvl_zshift) * a.layer_step;
+        int zt, y0;
+        layer_geom(a, Z << a.lvl_zshift, zt, y0);
         const int zp = a.g.z0 + zt * 8;
         const float lx = wn_lattice_coord(a.g.ox, a.g.sx, X * span), hx = wn_lattice_coord(a.g.ox, a.g.sx, X * span + span - 1);
-        const float ly = wn_lattice_coord(a.g.oy, a.g.sy, Y * span), hy = wn_lattice_coord(a.g.oy, a.g.sy, Y * span + span - 1);
+        const float ly = wn_lattice_coord(a.g.oy, a.g.sy, y0 + Y * span), hy = wn_lattice_coord(a.g.oy, a.g.sy, y0 + Y * span + span - 1);
         const float lz = wn_lattice_coord(a.g.oz, a.g.sz, zp), hz = wn_lattice_coord(a.g.oz, a.g.sz, zp + (8 << a.lvl_zshift) - 1);
         const float lo[3] = {fminf(lx, hx), fminf(ly, hy), fminf(lz, hz)}, hi[3] = {fmaxf(lx, hx), fmaxf(ly, hy), fmaxf(lz, hz)};
         float r2 = 0.0f;
@@ -876,9 +897,10 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
         if (tid == 0) {
             const int bx = tile % a.tiles_x;
             const int by = (tile / a.tiles_x) % a.tiles_y;
-            const int bz = a.tile_z0 + (tile / (a.tiles_x * a.tiles_y)) * a.layer_step;
+            int bz, y0;
+            layer_geom(a, tile / (a.tiles_x * a.tiles_y), bz, y0);
             const float lx = wn_lattice_coord(a.g.ox, a.g.sx, bx * 8), hx = wn_lattice_coord(a.g.ox, a.g.sx, bx * 8 + 7);
-            const float ly = wn_lattice_coord(a.g.oy, a.g.sy, by * 8), hy = wn_lattice_coord(a.g.oy, a.g.sy, by * 8 + 7);
+            const float ly = wn_lattice_coord(a.g.oy, a.g.sy, y0 + by * 8), hy = wn_lattice_coord(a.g.oy, a.g.sy, y0 + by * 8 + 7);
             const float lz = wn_lattice_coord(a.g.oz, a.g.sz, a.g.z0 + bz * 8), hz = wn_lattice_coord(a.g.oz, a.g.sz, a.g.z0 + bz * 8 + 7);
             s_red[0][0] = fminf(lx, hx);
             s_red[0][1] = fminf(ly, hy);

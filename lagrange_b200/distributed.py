@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["slab_range", "shard_range", "broadcast_packed", "replicate_engine"]
+__all__ = ["slab_range", "shard_range", "interleaved_layers", "gather_sharded", "broadcast_packed", "replicate_engine"]
 
 
 def shard_range(n: int, rank: int, world: int):
@@ -41,6 +41,23 @@ def interleaved_layers(nz: int, rank: int, world: int, depth: int = 8):
             out[-1] = (out[-1][0], z1)
         else:
             out.append((z0, z1))
+    return out
+
+
+def gather_sharded(dims, world: int, outputs):
+    """Lay the per-rank results of ``FastWindingNumber.query_grid(shard=(rank, world))`` out in lattice order (host side, numpy).
+    ``outputs[rank]`` = that rank's compact array (one value per point, not bit-packed). Returns an array of shape (nz, ny, nx)."""
+    from .winding import FastWindingNumber
+
+    nx, ny, nz = int(dims[0]), int(dims[1]), int(dims[2])
+    out = np.empty((nz, ny, nx), dtype=np.asarray(outputs[0]).dtype)
+    for rank in range(world):
+        src = np.asarray(outputs[rank]).reshape(-1)
+        pos = 0
+        for z0, z1, y0, y1 in FastWindingNumber.shard_layout(dims, rank, world)["units"]:
+            cnt = (z1 - z0) * (y1 - y0) * nx
+            out[z0:z1, y0:y1, :] = src[pos:pos + cnt].reshape(z1 - z0, y1 - y0, nx)
+            pos += cnt
     return out
 
 

@@ -233,17 +233,21 @@ class FastWindingNumber:
         return o, s, d, z0, z1, n
 
     def query_grid(self, origin, spacing, dims, z_range=None, accuracy_scale=None, want_omega=False, want_inside=True, device_output=False,
-                   out_omega=None, out_inside=None, tiling=True, layers=None, bits=False):
+                   out_omega=None, out_inside=None, tiling=True, layers=None, bits=False, shard=None):
         """Evaluate the cell-centred lattice p = origin + spacing*(ijk+0.5), x fastest; returns (omega, inside) (None if not wanted).
 
         ``device_output`` allocates torch CUDA outputs (results stay in HBM); otherwise numpy (copied to the host).
         ``layers=(first, step)``: strided multi-GPU sharding -- only the tile layers (8 z-planes each) first, first+step, ...
         are evaluated and returned compactly in that order (see ``strided_layer_planes``).
+        ``shard=(rank, world)``: diagonal multi-GPU sharding (wn_query_grid_sharded): this rank's units -- one y-part of every c-th tile
+        layer, see ``shard_layout`` -- returned compactly in layer order.
         ``bits=True``: ``inside`` is a bit array, point i -> bit (i & 7) of byte i >> 3 ((n + 7) // 8 bytes; WN_QUERY_OUT_BITS):
         an eighth of the device-to-host traffic for host outputs."""
         o, s, d, z0, z1, n = self._grid_args(origin, spacing, dims, z_range)
         if layers is not None:
             n = int(dims[0]) * int(dims[1]) * len(self.strided_layer_planes(int(dims[2]), *layers))
+        if shard is not None:
+            n = self.shard_layout(dims, *shard)["n_points"]
         def mk(dtype, given, want, count):
             if given is not None:
                 return given
@@ -259,13 +263,34 @@ class FastWindingNumber:
         pom = _Buf(om, np.float32, writable=True).ptr if om is not None else None
         pin = _Buf(ins, np.uint8, writable=True).ptr if ins is not None else None
         flags = self._flags(False, tiling) | (_capi.WN_QUERY_OUT_BITS if (bits and ins is not None) else 0)
-        if layers is not None:
+        if shard is not None:
+            self._check(self._lib.wn_query_grid_sharded(self._handle(), o, s, d, int(shard[0]), int(shard[1]), float(accuracy_scale or 0.0), flags, pom,
+                                                        pin, _current_stream_ptr()))
+        elif layers is not None:
             self._check(self._lib.wn_query_grid_strided(self._handle(), o, s, d, int(layers[0]), int(layers[1]), float(accuracy_scale or 0.0),
                                                         flags, pom, pin, _current_stream_ptr()))
         else:
             self._check(self._lib.wn_query_grid(self._handle(), o, s, d, z0, z1, float(accuracy_scale or 0.0), flags, pom,
                                                 pin, _current_stream_ptr()))
         return om, ins
+
+    @staticmethod
+    def shard_layout(dims, rank, world) -> dict:
+        """Layout of ``query_grid(shard=(rank, world))``'s output: {parts_y, layer_step, part_rows, n_units, n_points, units}, with
+        units = [(z0, z1, y0, y1), ...] in output order (each unit holds (z1 - z0) * (y1 - y0) * nx values, x fastest)."""
+        lib = _capi.lib()
+        d = (ctypes.c_int64 * 3)(*[int(x) for x in dims])
+        q, c = ctypes.c_int32(), ctypes.c_int32()
+        rows, nu, npts = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        _capi.check(lib.wn_grid_shard_layout(d, int(rank), int(world), ctypes.byref(q), ctypes.byref(c), ctypes.byref(rows), ctypes.byref(nu),
+                                             ctypes.byref(npts)))
+        Q, C, R, nz = q.value, c.value, rows.value, int(dims[2])
+        units = []
+        for k in range(nu.value):
+            lz = rank % C + k * C
+            part = ((rank - lz) // C) % Q
+            units.append((8 * lz, min(nz, 8 * lz + 8), part * R, (part + 1) * R))
+        return {"parts_y": Q, "layer_step": C, "part_rows": R, "n_units": nu.value, "n_points": npts.value, "units": units}
 
     @staticmethod
     def strided_layer_planes(nz, first, step):

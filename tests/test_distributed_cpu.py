@@ -80,3 +80,26 @@ def test_two_ranks_gloo(tmp_path):
     mp.spawn(_worker, args=(world, _free_port(), nz, str(tmp_path)), nprocs=world, join=True)
     slabs = np.concatenate([np.load(tmp_path / f"slab{r}.npy") for r in range(world)])
     assert np.array_equal(slabs, np.arange(nz))
+
+
+def test_diagonal_shard_layout_tiles_the_lattice_exactly():
+    """wn_grid_shard_layout (host code, no GPU): over all ranks every (tile layer, y part) is owned exactly once, the parts a rank
+    owns cycle through all of them, and whole-layer striding is the Q = 1 special case."""
+    from lagrange_b200.winding import FastWindingNumber as W
+
+    for dims, world, want_q in (((512, 512, 512), 8, 4), ((512, 512, 512), 4, 4), ((512, 512, 512), 2, 2), ((96, 64, 100), 8, 4),
+                                ((40, 24, 37), 8, 1), ((64, 48, 64), 6, 2), ((64, 64, 64), 3, 1), ((64, 64, 64), 1, 1)):
+        cover = np.zeros((dims[2], dims[1]), dtype=np.int32)
+        total = 0
+        for rank in range(world):
+            lay = W.shard_layout(dims, rank, world)
+            assert lay["parts_y"] == want_q and lay["layer_step"] * lay["parts_y"] == world
+            pts = 0
+            for z0, z1, y0, y1 in lay["units"]:
+                cover[z0:z1, y0:y1] += 1
+                pts += (z1 - z0) * (y1 - y0) * dims[0]
+            assert pts == lay["n_points"]
+            total += pts
+            if lay["parts_y"] > 1 and lay["n_units"] >= lay["parts_y"]:
+                assert len({u[2] for u in lay["units"]}) == lay["parts_y"]  # every part of the lattice shows up on every rank
+        assert np.all(cover == 1) and total == dims[0] * dims[1] * dims[2]
