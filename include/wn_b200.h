@@ -243,8 +243,8 @@ WN_API wn_status wn_create_from_packed(const void* src, int64_t nbytes, const wn
 /* Single-process multi-GPU: copies of `src` on the listed devices (device-to-device copies of the packed tree, all in
  * flight together; NVLink peer copies where the topology allows), out[i] on devices[i]. Destroy each with wn_destroy. */
 WN_API wn_status wn_replicate(const wn_engine* src, const int32_t* devices, int32_t n_devices, wn_engine** out);
-/* One lattice over several engines holding the same tree (the builder + its replicas): engine i evaluates the tile layers i, i + N, ...
- * on its own device from its own host thread, results are gathered in lattice order into HOST buffers (out_inside honours
+/* One lattice over several engines holding the same tree (the builder + its replicas): engine i evaluates rank i's share of the diagonal
+ * sharding (wn_query_grid_sharded) on its own device from its own host thread, results are gathered in lattice order into HOST buffers (out_inside honours
  * WN_QUERY_OUT_BITS). No exchange step between devices. */
 WN_API wn_status wn_query_grid_multi(wn_engine* const* engines, int32_t n_engines, const float origin[3], const float spacing[3],
                                      const int64_t dims[3], float beta, uint32_t flags, float* out_omega, uint8_t* out_inside);

@@ -887,19 +887,13 @@ wn_status stage_points(const wn_engine* e, const float* q_xyz, int64_t n, const 
     return WN_OK;
 }
 
-// `blocks` = groups of 8 warp tasks (a lattice tile of 8 x 8 x 4*QPL points, or 256*QPL consecutive points); a CTA takes a run of them
 template <bool GRID, bool STATS>
-void launch_query(int qpl, int blocks, const wn::QueryArgs& a_in, cudaStream_t st)
+void launch_query(int qpl, int blocks, const wn::QueryArgs& a, cudaStream_t st)
 {
-    wn::QueryArgs a = a_in;
-    const int run_env = env_int("WN_QUERY_RUN", 0);
-    a.tiles_per_cta = run_env > 0 ? run_env : (int)std::min<int64_t>(4, std::max<int64_t>(1, (int64_t)blocks / 8192));
-    a.launch_tiles = blocks;
-    const int ctas = (blocks + a.tiles_per_cta - 1) / a.tiles_per_cta;
     if (qpl == 2)
-        wn::k_query<2, GRID, STATS><<<ctas, wn::kQueryThreads, 0, st>>>(a);
+        wn::k_query<2, GRID, STATS><<<blocks, wn::kQueryThreads, 0, st>>>(a);
     else
-        wn::k_query<1, GRID, STATS><<<ctas, wn::kQueryThreads, 0, st>>>(a);
+        wn::k_query<1, GRID, STATS><<<blocks, wn::kQueryThreads, 0, st>>>(a);
 }
 
 int pick_qpl(int64_t n)
@@ -2075,24 +2069,24 @@ wn_status wn_query_grid_multi(wn_engine* const* engines, int32_t n_engines, cons
     if (s != WN_OK) return s;
     if (n == 0) return WN_OK;
     if (n_engines == 1) return wn_query_grid(engines[0], origin, spacing, dims, 0, dims[2], beta, flags, out_omega, out_inside, nullptr);
-    // Engine i classifies the tile layers i, i + N, i + 2N, ... (8 z-planes each: the same mix of work on every device, no
-    // exchange step), one host thread per device; the compact per-device results are then laid out in lattice order.
+    // Engine i takes rank i's share of the diagonal sharding (one y-part of every c-th tile layer: the same mix of work on every
+    // device, no exchange step), one host thread per device; the compact per-device results are then laid out in lattice order.
     const bool bits = (flags & WN_QUERY_OUT_BITS) != 0 && out_inside;
-    const int64_t per_layer = dims[0] * dims[1] * 8, n_layers = (dims[2] + 7) / 8;
+    const int64_t nx = dims[0], ny = dims[1], nz = dims[2];
     std::vector<std::vector<float>> om((size_t)n_engines);
     std::vector<std::vector<uint8_t>> in((size_t)n_engines);
     std::vector<wn_status> status((size_t)n_engines, WN_OK);
     std::vector<std::string> errors((size_t)n_engines);
+    std::vector<ShardLayout> lay((size_t)n_engines);
     std::vector<std::thread> pool;
     for (int i = 0; i < n_engines; ++i) {
-        int64_t planes = 0;
-        for (int64_t L = i; L < n_layers; L += n_engines) planes += std::min<int64_t>(8, dims[2] - L * 8);
-        const int64_t ni = dims[0] * dims[1] * planes;
+        lay[i] = shard_layout(dims, i, n_engines);
+        const int64_t ni = nx * lay[i].part_rows * lay[i].planes;
         if (out_omega) om[i].resize((size_t)ni);
         if (out_inside) in[i].resize((size_t)(bits ? (ni + 7) / 8 : ni));
         pool.emplace_back([&, i, ni]() {
             if (ni == 0) return;
-            status[i] = wn_query_grid_strided(engines[i], origin, spacing, dims, i, n_engines, beta, flags, out_omega ? om[i].data() : nullptr,
+            status[i] = wn_query_grid_sharded(engines[i], origin, spacing, dims, i, n_engines, beta, flags, out_omega ? om[i].data() : nullptr,
                                               out_inside ? in[i].data() : nullptr, nullptr);
             if (status[i] != WN_OK) errors[i] = wn_last_error();
         });
@@ -2101,25 +2095,29 @@ wn_status wn_query_grid_multi(wn_engine* const* engines, int32_t n_engines, cons
     for (int i = 0; i < n_engines; ++i)
         if (status[i] != WN_OK) return fail(status[i], "device %d: %s", engines[i]->device, errors[i].c_str());
     for (int i = 0; i < n_engines; ++i) {
+        const ShardLayout& L = lay[i];
         int64_t local = 0; // points of engine i consumed so far
-        for (int64_t L = i; L < n_layers; L += n_engines) {
-            const int64_t cnt = dims[0] * dims[1] * std::min<int64_t>(8, dims[2] - L * 8);
-            const int64_t first = L * per_layer;
-            if (out_omega) memcpy(out_omega + first, om[i].data() + local, (size_t)cnt * sizeof(float));
-            if (out_inside && bits) {
-                if ((first & 7) == 0 && (local & 7) == 0) {
-                    memcpy(out_inside + first / 8, in[i].data() + local / 8, (size_t)(cnt + 7) / 8);
-                } else { // layers of nx*ny*8 points are byte aligned; only a ragged lattice tail can land here
-                    for (int64_t k = 0; k < cnt; ++k) {
-                        const int bit = (in[i][(size_t)((local + k) >> 3)] >> ((local + k) & 7)) & 1;
-                        uint8_t& dst = out_inside[(first + k) >> 3];
-                        dst = (uint8_t)((dst & ~(1u << ((first + k) & 7))) | (bit << ((first + k) & 7)));
+        for (int64_t lz = i % L.c; lz * 8 < nz; lz += L.c) {
+            int64_t q = ((i - lz) / L.c) % L.Q;
+            if (q < 0) q += L.Q;
+            const int64_t y0 = L.Q > 1 ? q * L.part_rows : 0, chunk = L.part_rows * nx; // one plane of the unit
+            for (int64_t z = lz * 8; z < std::min<int64_t>(nz, lz * 8 + 8); ++z, local += chunk) {
+                const int64_t first = (z * ny + y0) * nx;
+                if (out_omega) memcpy(out_omega + first, om[i].data() + local, (size_t)chunk * sizeof(float));
+                if (out_inside && bits) {
+                    if ((first & 7) == 0 && (local & 7) == 0 && ((chunk & 7) == 0 || first + chunk == nx * ny * nz)) {
+                        memcpy(out_inside + first / 8, in[i].data() + local / 8, (size_t)(chunk + 7) / 8);
+                    } else { // ragged lattices only: bit by bit
+                        for (int64_t k = 0; k < chunk; ++k) {
+                            const int bit = (in[i][(size_t)((local + k) >> 3)] >> ((local + k) & 7)) & 1;
+                            uint8_t& dst = out_inside[(first + k) >> 3];
+                            dst = (uint8_t)((dst & ~(1u << ((first + k) & 7))) | (bit << ((first + k) & 7)));
+                        }
                     }
+                } else if (out_inside) {
+                    memcpy(out_inside + first, in[i].data() + local, (size_t)chunk);
                 }
-            } else if (out_inside) {
-                memcpy(out_inside + first, in[i].data() + local, (size_t)cnt);
             }
-            local += cnt;
         }
     }
     return WN_OK;
