@@ -162,9 +162,20 @@ struct wn_engine
     mutable cudaEvent_t ev_batch = nullptr; // orders a finished batch before its copy on copy_stream
     mutable bool ev_last_valid = false;
     mutable std::mutex sdf_mu; // wn_sdf_grid runs two passes (sign, distance) over shared scratch: one caller at a time
-    mutable DevBuf s_in, s_out_f, s_out_b, s_out_bits, s_sort, s_stats, s_partial, s_plan_hdr, s_plan_items, s_plan_samples, s_plan_order, s_plan_lvl, s_sdf_inside, s_sdf_dense;
+    mutable DevBuf s_in, s_out_f, s_out_b, s_out_bits, s_sort, s_stats, s_partial, s_sdf_inside, s_sdf_dense;
+    // plan scratch of the tiled path, one set per lane: consecutive batches of a call alternate between two streams, so that the
+    // launch tail of one batch's kernels is filled by the other batch's (see dispatch_query)
+    struct PlanScratch
+    {
+        DevBuf hdr, items, samples, order, lvl;
+        void release() { hdr.release(), items.release(), samples.release(), order.release(), lvl.release(); }
+    };
+    mutable PlanScratch s_plan[2];
+    mutable cudaStream_t lane_stream = nullptr; // second lane; the first is the caller's stream
+    mutable cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_lane[2] = {nullptr, nullptr};
     mutable PinnedBuf p_small;
     mutable cudaStream_t copy_stream = nullptr; // D2H of finished batches while the next batch computes
+    mutable int query_slots = 0;                // CTAs of k_tile_query the device holds at once (SMs x occupancy), set on first use
     mutable int64_t last_plan_tiles = 0;        // tiles of the last k_tile_plan launch (wn_debug_last_plan)
     mutable float last_probe_share = -1.0f;     // far-set share measured by the last tiling probe (diagnostics)
     mutable float probe_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -1020,6 +1031,12 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
         // hierarchical planning (lattices): blocks of 2^k x 2^k x (2^k | 1) tiles above the tiles; a batch must hold whole blocks
         const int plan_levels = GRID ? std::max(0, std::min(3, env_int("WN_PLAN_LEVELS", 2))) : 0;
         const bool zgroup = GRID && a.layer_step == 1 && a.shard_q <= 1;
+        // Two lanes: consecutive batches alternate between the caller's stream and a second one (own plan scratch each), so that the
+        // GPU always holds kernels of two batches: when one batch's kernel drains (launch tail, and the dependent launch behind it
+        // waiting for the last CTA), the other batch's CTAs take the free SMs. Needs at least two batches of a useful size.
+        const int64_t total_tiles = units * tiles_per_unit;
+        const int lanes = (env_int("WN_TILE_LANES", 1) >= 2 && units >= 2 && total_tiles >= env_int("WN_TILE_LANES_MIN", 1 << 14)) ? 2 : 1;
+        if (lanes == 2) units_per_launch = std::min(units_per_launch, (units + 1) / 2);
         if (plan_levels > 0 && zgroup && units_per_launch >= (1 << plan_levels)) units_per_launch &= ~(int64_t)((1 << plan_levels) - 1);
         const int64_t launch_tiles = std::min(units, units_per_launch) * tiles_per_unit;
         if (launch_tiles > INT_MAX / 2)
@@ -1028,16 +1045,14 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
         // from an arena sized for the average tile; a tile that does not fit falls back to the generic traversal.
         const int64_t arena_bytes = std::min<int64_t>(std::max<int64_t>(launch_tiles * env_int("WN_TILE_ARENA_PER_TILE", 12288), (int64_t)64 << 20),
                                                       (int64_t)4 << 30);
-        WN_CUDA(e->s_plan_hdr.reserve((size_t)launch_tiles * sizeof(wn::TileHeader) + 256));
-        WN_CUDA(e->s_plan_items.reserve((size_t)arena_bytes));
-        WN_CUDA(e->s_plan_samples.reserve((size_t)launch_tiles * wn::kTileSampleStride * sizeof(float)));
-        WN_CUDA(e->s_plan_order.reserve((size_t)launch_tiles * sizeof(int)));
-        a.plan_hdr = (wn::TileHeader*)((char*)e->s_plan_hdr.p + 256);
-        a.plan_cursor = (unsigned long long*)e->s_plan_hdr.p;
-        a.plan_arena = (char*)e->s_plan_items.p;
+        for (int ln = 0; ln < lanes; ++ln) {
+            wn_engine::PlanScratch& ps = e->s_plan[ln];
+            WN_CUDA(ps.hdr.reserve((size_t)launch_tiles * sizeof(wn::TileHeader) + 256));
+            WN_CUDA(ps.items.reserve((size_t)arena_bytes));
+            WN_CUDA(ps.samples.reserve((size_t)launch_tiles * wn::kTileSampleStride * sizeof(float)));
+            WN_CUDA(ps.order.reserve((size_t)launch_tiles * sizeof(int)));
+        }
         a.plan_arena_bytes = arena_bytes;
-        a.plan_samples = (float*)e->s_plan_samples.p;
-        a.tile_order = (int*)e->s_plan_order.p;
         a.heavy_cond = env_int("WN_TILE_HEAVY", 192);
         a.kappa = tile_kappa();
         // Batches. Device outputs: as few as the scratch allows (every batch boundary costs a launch tail). Host outputs: the same,
@@ -1060,10 +1075,47 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
         }
         const bool overlap = GRID && ob && (ob->h_omega || ob->h_inside) && batch_units.size() > 1;
         if (overlap && !e->copy_stream) WN_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+        // Diagnostics: WN_TRACE_FILE=<path> records {start, end, SM} of every CTA of the tiled kernels of this call (tools/cta_timeline.py)
+        const char* trace_path = getenv("WN_TRACE_FILE");
+        struct TraceLaunch { int tag, lane; int64_t offset, count; };
+        std::vector<TraceLaunch> trace_launches;
+        unsigned long long* d_trace = nullptr;
+        int64_t trace_used = 0;
+        const int64_t trace_cap = trace_path && *trace_path ? 3 * total_tiles + 65536 : 0;
+        if (trace_cap > 0) {
+            WN_CUDA(cudaMalloc(&d_trace, (size_t)trace_cap * 32));
+            WN_CUDA(cudaMemsetAsync(d_trace, 0, (size_t)trace_cap * 32, st));
+        }
+        auto trace_slot = [&](int tag, int lane, int64_t count) -> unsigned long long* {
+            if (!d_trace || trace_used + count > trace_cap) return nullptr;
+            trace_launches.push_back({tag, lane, trace_used, count});
+            trace_used += count;
+            return d_trace + (trace_used - count) * 4;
+        };
+        cudaStream_t lane_st[2] = {st, st};
+        const bool forked = lanes == 2 && batch_units.size() > 1;
+        if (forked) {
+            if (!e->lane_stream) WN_CUDA(cudaStreamCreateWithFlags(&e->lane_stream, cudaStreamNonBlocking));
+            if (!e->ev_fork) WN_CUDA(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+            if (!e->ev_join) WN_CUDA(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+            WN_CUDA(cudaEventRecord(e->ev_fork, st)); // the inputs (uploaded or sorted points, counters) are ready on `st`
+            WN_CUDA(cudaStreamWaitEvent(e->lane_stream, e->ev_fork, 0));
+            lane_st[1] = e->lane_stream;
+        }
         int64_t u0 = 0;
         for (size_t bi = 0; bi < batch_units.size(); u0 += batch_units[bi], ++bi) {
             const int64_t nunits = batch_units[bi];
             const int blocks = (int)(nunits * tiles_per_unit);
+            const int ln = forked ? (int)(bi & 1) : 0;
+            cudaStream_t bs = lane_st[ln];
+            {
+                const wn_engine::PlanScratch& ps = e->s_plan[ln];
+                a.plan_hdr = (wn::TileHeader*)((char*)ps.hdr.p + 256);
+                a.plan_cursor = (unsigned long long*)ps.hdr.p;
+                a.plan_arena = (char*)ps.items.p;
+                a.plan_samples = (float*)ps.samples.p;
+                a.tile_order = (int*)ps.order.p;
+            }
             if (GRID) {
                 a.tile_z0 = layer_first + (int)u0 * a.layer_step;
                 a.out_layer0 = (int)u0;
@@ -1071,7 +1123,7 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
                 a.tile_base = u0;
             }
             a.launch_tiles = blocks;
-            WN_CUDA(cudaMemsetAsync(a.plan_cursor, 0, 2 * sizeof(unsigned long long), st)); // arena cursor + the two order counters
+            WN_CUDA(cudaMemsetAsync(a.plan_cursor, 0, 2 * sizeof(unsigned long long), bs)); // arena cursor + the two order counters
             a.up_hdr = nullptr;
             a.up_samples = nullptr;
             if (plan_levels > 0 && (int64_t)a.tiles_x * a.tiles_y * nunits >= 64) {
@@ -1086,9 +1138,9 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
                     total += nb[k];
                 }
                 const size_t hdr_bytes = align_up((size_t)total * sizeof(wn::PlanBlockHeader), 256);
-                WN_CUDA(e->s_plan_lvl.reserve(hdr_bytes + (size_t)total * wn::kTileSampleStride * sizeof(float)));
-                wn::PlanBlockHeader* hdr_base = (wn::PlanBlockHeader*)e->s_plan_lvl.p;
-                float* samp_base = (float*)((char*)e->s_plan_lvl.p + hdr_bytes);
+                WN_CUDA(e->s_plan[ln].lvl.reserve(hdr_bytes + (size_t)total * wn::kTileSampleStride * sizeof(float)));
+                wn::PlanBlockHeader* hdr_base = (wn::PlanBlockHeader*)e->s_plan[ln].lvl.p;
+                float* samp_base = (float*)((char*)e->s_plan[ln].lvl.p + hdr_bytes);
                 int64_t first[4] = {0, 0, 0, 0};
                 for (int k = 2; k <= plan_levels; ++k) first[k] = first[k - 1] + nb[k - 1];
                 for (int k = plan_levels; k >= 1; --k) {
@@ -1106,7 +1158,8 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
                         b.up_by = lby[k + 1];
                         b.up_zs = zgroup ? 1 : 0;
                     }
-                    wn::k_plan_block<<<(int)nb[k], wn::kPlanThreads, 0, st>>>(b);
+                    b.trace = trace_slot(10 + k, ln, nb[k]);
+                    wn::k_plan_block<<<(int)nb[k], wn::kPlanThreads, 0, bs>>>(b);
                 }
                 a.up_hdr = hdr_base + first[1];
                 a.up_samples = samp_base + first[1] * wn::kTileSampleStride;
@@ -1114,10 +1167,11 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
                 a.up_by = lby[1];
                 a.up_zs = zgroup ? 1 : 0;
             }
-            wn::k_tile_plan<GRID><<<blocks, wn::kPlanThreads, 0, st>>>(a);
+            a.trace = trace_slot(1, ln, blocks);
+            wn::k_tile_plan<GRID><<<blocks, wn::kPlanThreads, 0, bs>>>(a);
             // a CTA walks a run of consecutive tiles, its warps taking sub-blocks dynamically (see k_tile_query)
             a.launch_tiles = blocks;
-            e->last_plan_tiles = blocks;
+            if (ln == 0) e->last_plan_tiles = blocks;
             // A CTA takes a run of consecutive tiles of the heavy-first order and its 8 warps pull the 8 x run sub-block tasks from a
             // CTA-local counter: with one tile per CTA every warp gets exactly one task and the CTA lives as long as its slowest
             // warp. Measured on cfg2 (131072 tiles per launch): run 1 / 2 / 4 / 6 / 8 / 12 -> 7.56 / 7.81 / 7.94 / 7.96 / 7.95 / 7.92
@@ -1125,19 +1179,31 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
             const int run_auto = (int)std::min<int64_t>(6, std::max<int64_t>(1, (int64_t)blocks / 8192));
             const int run_env = env_int("WN_TILE_RUN", 0);
             a.tiles_per_cta = run_env > 0 ? run_env : run_auto;
-            const int qblocks = (blocks + a.tiles_per_cta - 1) / a.tiles_per_cta;
+            // ... and the last WN_TILE_TAIL x (resident CTAs) x run tiles go one per CTA (CTA timeline, tools/cta_timeline.py: with
+            // uniform runs the launch tail was one run of light tiles long, 5 % of a 32768-tile launch)
+            if (e->query_slots == 0) {
+                int sms = 148, per_sm = 5;
+                WN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device));
+                WN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wn::k_tile_query<GRID, false>, wn::kQueryThreads, 0));
+                e->query_slots = sms * std::max(1, per_sm);
+            }
+            const int64_t tail_tiles =
+                std::min<int64_t>(blocks, (int64_t)env_int("WN_TILE_TAIL", 2) * e->query_slots * (a.tiles_per_cta > 1 ? a.tiles_per_cta : 0));
+            a.run_ctas = (int)((blocks - tail_tiles) / a.tiles_per_cta);
+            const int qblocks = a.run_ctas + (blocks - a.run_ctas * a.tiles_per_cta);
+            a.trace = trace_slot(2, ln, qblocks);
             if (stats)
-                wn::k_tile_query<GRID, true><<<qblocks, wn::kQueryThreads, 0, st>>>(a);
+                wn::k_tile_query<GRID, true><<<qblocks, wn::kQueryThreads, 0, bs>>>(a);
             else
-                wn::k_tile_query<GRID, false><<<qblocks, wn::kQueryThreads, 0, st>>>(a);
+                wn::k_tile_query<GRID, false><<<qblocks, wn::kQueryThreads, 0, bs>>>(a);
             if (overlap) {
                 // results of z layers [8*u0, 8*(u0+nunits)) of the slab are final: ship them while the next batch runs
                 const int64_t per_layer = (int64_t)a.g.nx * a.part_ny;
                 const int64_t first = 8 * u0 * per_layer;
                 const int64_t count = std::min<int64_t>(8 * nunits, grid_layers - 8 * u0) * per_layer;
-                if (ob->bits) pack_bits(*ob, first, count, st); // first = 8 * u0 * per_layer: byte aligned
+                if (ob->bits) pack_bits(*ob, first, count, bs); // first = 8 * u0 * per_layer: byte aligned
                 if (!e->ev_batch) WN_CUDA(cudaEventCreateWithFlags(&e->ev_batch, cudaEventDisableTiming));
-                WN_CUDA(cudaEventRecord(e->ev_batch, st)); // re-recording is fine: the wait below captures this record
+                WN_CUDA(cudaEventRecord(e->ev_batch, bs)); // re-recording is fine: the wait below captures this record
                 WN_CUDA(cudaStreamWaitEvent(e->copy_stream, e->ev_batch, 0));
                 if (ob->h_omega)
                     WN_CUDA(cudaMemcpyAsync(ob->h_omega + first, ob->d_omega + first, (size_t)count * sizeof(float), cudaMemcpyDeviceToHost,
@@ -1147,6 +1213,31 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
                                             e->copy_stream));
                 else if (ob->h_inside)
                     WN_CUDA(cudaMemcpyAsync(ob->h_inside + first, ob->d_inside + first, (size_t)count, cudaMemcpyDeviceToHost, e->copy_stream));
+            }
+        }
+        if (forked) {
+            // join: everything after this call on `st` (bit packing, copies, the next call) sees both lanes' results
+            WN_CUDA(cudaEventRecord(e->ev_join, e->lane_stream));
+            WN_CUDA(cudaStreamWaitEvent(st, e->ev_join, 0));
+        }
+        if (d_trace) {
+            // file: "WNTR", launches, then per launch {tag (1 tile plan, 2 tile query, 10+k block plan of level k), lane, count, count x 4 u64}
+            a.trace = nullptr;
+            std::vector<unsigned long long> h((size_t)trace_used * 4);
+            WN_CUDA(cudaStreamSynchronize(st));
+            WN_CUDA(cudaMemcpy(h.data(), d_trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            cudaFree(d_trace);
+            if (FILE* f = fopen(trace_path, "wb")) {
+                const int32_t nl = (int32_t)trace_launches.size();
+                fwrite("WNTR", 1, 4, f);
+                fwrite(&nl, sizeof(nl), 1, f);
+                for (const TraceLaunch& tl : trace_launches) {
+                    const int32_t hd[2] = {tl.tag, tl.lane};
+                    fwrite(hd, sizeof(hd), 1, f);
+                    fwrite(&tl.count, sizeof(tl.count), 1, f);
+                    fwrite(h.data() + tl.offset * 4, sizeof(unsigned long long), (size_t)tl.count * 4, f);
+                }
+                fclose(f);
             }
         }
         if (overlap) {
@@ -1563,15 +1654,15 @@ wn_status wn_destroy(wn_engine* e)
         e->s_sort.release();
         e->s_stats.release();
         e->s_partial.release();
-        e->s_plan_hdr.release();
-        e->s_plan_items.release();
-        e->s_plan_samples.release();
-        e->s_plan_order.release();
-        e->s_plan_lvl.release();
+        e->s_plan[0].release();
+        e->s_plan[1].release();
         e->s_sdf_inside.release();
         e->s_sdf_dense.release();
         e->p_small.release();
         if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+        if (e->lane_stream) cudaStreamDestroy(e->lane_stream);
+        if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+        if (e->ev_join) cudaEventDestroy(e->ev_join);
         if (e->ev_last) cudaEventDestroy(e->ev_last);
         if (e->ev_batch) cudaEventDestroy(e->ev_batch);
     }
@@ -2134,7 +2225,7 @@ wn_status wn_debug_last_plan(const wn_engine* e, int32_t* out, int64_t capacity_
     DeviceGuard guard(e->device);
     std::vector<wn::TileHeader> h((size_t)e->last_plan_tiles);
     WN_CUDA(cudaDeviceSynchronize());
-    WN_CUDA(cudaMemcpy(h.data(), (const char*)e->s_plan_hdr.p + 256, h.size() * sizeof(wn::TileHeader), cudaMemcpyDeviceToHost));
+    WN_CUDA(cudaMemcpy(h.data(), (const char*)e->s_plan[0].hdr.p + 256, h.size() * sizeof(wn::TileHeader), cudaMemcpyDeviceToHost));
     for (size_t i = 0; i < h.size(); ++i) {
         out[4 * i + 0] = h[i].n_cond;
         out[4 * i + 1] = h[i].n_dir;

@@ -121,10 +121,12 @@ struct QueryArgs
     long long plan_arena_bytes;
     float kappa;              // far set needs |c - P| >= kappa * tile radius and |c - P| - R >= kappa/2 * tile radius
     int tiles_per_cta, launch_tiles; // k_tile_query: consecutive tiles per CTA, tiles in this launch
+    int run_ctas;             // k_tile_query: the first run_ctas CTAs take tiles_per_cta tiles each, the CTAs after them one tile each
     int* tile_order;          // [launch_tiles] tiles with long conditional lists first (written by k_tile_plan, counters after plan_cursor)
     int heavy_cond;           // a tile is 'heavy' from this many conditional records on
     int probe_stride;         // > 0: k_tile_plan only classifies every probe_stride-th tile and adds the class sizes to `probe`
     unsigned long long* probe; // [5] far, conditional, direct, exact records, fallback tiles
+    unsigned long long* trace; // diagnostics (WN_TRACE_FILE): per CTA of this launch {start ns, end ns, SM id, 0}; null in production
     // hierarchical planning (lattices): a block of level k covers 2^k x 2^k x (2^k | 1) tiles. The level being planned reads its
     // parent level (up_*), the block kernel writes lvl_*.
     const PlanBlockHeader* up_hdr; // parent level's entry lists; null: plan from the root
@@ -681,6 +683,27 @@ __device__ __forceinline__ float plan_parent_interp(const float* __restrict__ up
     return acc;
 }
 
+// CTA timeline for tools/cta_timeline.py: one branch on a kernel parameter per CTA when tracing is off.
+__device__ __forceinline__ unsigned long long trace_clock()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void trace_begin(const QueryArgs& a)
+{
+    if (a.trace && threadIdx.x == 0) {
+        unsigned int sm;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        a.trace[(size_t)blockIdx.x * 4 + 0] = trace_clock();
+        a.trace[(size_t)blockIdx.x * 4 + 2] = sm;
+    }
+}
+__device__ __forceinline__ void trace_end(const QueryArgs& a)
+{
+    if (a.trace && threadIdx.x == 0) a.trace[(size_t)blockIdx.x * 4 + 1] = trace_clock();
+}
+
 __global__ void __launch_bounds__(kPlanThreads) k_plan_block(const QueryArgs a)
 {
     __shared__ int s_front[2][kTileFrontCap];
@@ -696,6 +719,7 @@ __global__ void __launch_bounds__(kPlanThreads) k_plan_block(const QueryArgs a)
     const int X = (int)blockIdx.x % a.lvl_bx, Y = ((int)blockIdx.x / a.lvl_bx) % a.lvl_by, Z = (int)blockIdx.x / (a.lvl_bx * a.lvl_by);
     const int pidx = a.up_hdr ? ((Z >> a.up_zs) * a.up_by + (Y >> 1)) * a.up_bx + (X >> 1) : 0;
     bool my_ovf = false;
+    trace_begin(a);
     if (tid < 4) s_cnt[tid] = 0;
     for (int r = tid; r <= kPlanMaxRounds; r += kPlanThreads) s_fcnt[r] = 0;
     if (tid == 0) s_off = 0;
@@ -850,6 +874,7 @@ __global__ void __launch_bounds__(kPlanThreads) k_plan_block(const QueryArgs a)
         h.flags = fallback ? kTileFallback : 0;
         a.lvl_hdr[blockIdx.x] = h;
         if (a.stats) atomicAdd(a.stats + 1, (unsigned long long)(fallback ? 0 : n_far) * kTileSamples);
+        trace_end(a);
     }
 }
 
@@ -872,6 +897,7 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
     // probe mode (probe_stride > 0): classify every probe_stride-th tile only and add up the class sizes, so that the host
     // can decide whether the tiled path pays off for this batch (it does when the far set is a large share of the work)
     const int tile = a.probe_stride > 0 ? (int)blockIdx.x * a.probe_stride : (int)blockIdx.x;
+    trace_begin(a);
     int pidx = 0; // parent block of this tile (hierarchical planning, lattices only)
     if (GRID && a.up_hdr) {
         const int tbx = tile % a.tiles_x, tby = (tile / a.tiles_x) % a.tiles_y, tl = tile / (a.tiles_x * a.tiles_y);
@@ -1208,6 +1234,7 @@ __global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
             // executed work of the plan: far-set evaluations at the sample points (counted as far-field evaluations)
             atomicAdd(a.stats + 1, (unsigned long long)(fallback ? 0 : n_far) * kTileSamples);
         }
+        trace_end(a);
     }
 }
 
@@ -1223,9 +1250,13 @@ __global__ void __launch_bounds__(kQueryThreads, WN_TQ_MIN_CTAS) k_tile_query(co
     constexpr int QPL = kTileQPL;
     const int lane = threadIdx.x & 31;
     if (threadIdx.x == 0) s_next = 0;
+    trace_begin(a);
     __syncthreads();
-    const int tile0 = (int)blockIdx.x * a.tiles_per_cta;
-    const int n_task = min(a.tiles_per_cta, a.launch_tiles - tile0) * kTileTasks;
+    // runs of tiles_per_cta tiles, except at the end of the launch (the light end of the heavy-first order), where a CTA takes one
+    // tile: the launch tail is as long as its last CTAs, and those are then the shortest ones
+    const bool in_run = (int)blockIdx.x < a.run_ctas;
+    const int tile0 = in_run ? (int)blockIdx.x * a.tiles_per_cta : a.run_ctas * a.tiles_per_cta + ((int)blockIdx.x - a.run_ctas);
+    const int n_task = min(in_run ? a.tiles_per_cta : 1, a.launch_tiles - tile0) * kTileTasks;
     TravCounters cnt;
     while (true) {
         int task = 0;
@@ -1324,6 +1355,10 @@ __global__ void __launch_bounds__(kQueryThreads, WN_TQ_MIN_CTAS) k_tile_query(co
         write_results<QPL>(a, oidx, acc);
     }
     if (STATS) flush_counters(a, cnt);
+    if (a.trace) {
+        __syncthreads();
+        trace_end(a);
+    }
 }
 
 } // namespace wn
