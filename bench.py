@@ -8,8 +8,9 @@ Default workload (BASELINE.json configs[1]): is_inside classif
 [-1.1, 1.1]^3 (134 217 728 queries) against an icosahedron midpoint-subdivided 8x (1 310 720 triangles), beta = 2, order 2,
 on the reference builder's own hierarchy built on the GPU (WN_HIERARCHY_REFERENCE: results match the reference algorithm).
 One "step" = one pass of the query path over the whole query set (the tree is built once, before the timed region; its build
-time is reported beside the throughput). With N GPUs the queries are sharded (lattices: diagonally, one y-part of every c-th
-tile layer per rank; point sets: index ranges), the tree is built on rank 0 and broadcast once with NCCL; there is no collective on the query path.
+time is reported beside the throughput). With N GPUs the queries are sharded (lattices: 8-plane tile layers dealt round-robin,
+one call per rank; point sets: index ranges), the tree is built on rank 0 and broadcast once with NCCL; there is no collective
+on the query path.
 --config 1/3/4/5 run the other BASELINE configs through the same flow (cfg4/cfg5 are point sets: device-resident points for
 `value`, pinned host points + H2D inside the timed region for `e2e`); --mode exact times the brute-force all-pairs mode (cfg5's
 mesh, a bounded number of queries per step).
@@ -107,7 +108,7 @@ def workload(args):
 def config_dict(args, name, n_total):
     """The same `config` for both arms (the driver compares them key by key)."""
     return {"workload": name, "queries_per_step": n_total, "mode": args.mode,
-            "sharding": f"lattices: diagonal over {args.gpus} rank(s) (one y-part of every c-th 8-plane tile layer per rank, wn_query_grid_sharded); "
+            "sharding": f"lattices: 8-plane tile layers dealt round-robin over {args.gpus} rank(s) (wn_query_grid_layers, one call per rank); "
                         "point sets: index ranges; tree built on rank 0 and broadcast; CPU arm: rank 0 only",
             "l2": "GPU arm: flushed between timed steps (256 MiB fill); CPU arm: not applicable",
             "gpu_arm": {"hierarchy": args.hierarchy, "leaf_size": 1 if args.hierarchy == "reference" else args.leaf_size,
@@ -336,11 +337,14 @@ def main():
     lo = 0
     if grid:
         origin, spacing, dims = wl["lattice"]
-        # diagonal sharding (wn_query_grid_sharded): rank r takes, of every c-th tile layer, one of Q y-parts, so that every rank sees
-        # every part and every height equally often; ONE call per rank, results compact in the rank's buffer. (Whole layers dealt
-        # round-robin cap the efficiency at 0.906 on 8 GPUs: 58 of the 64 layers carry work, 8 + 7 + ...; contiguous z-slabs: 0.81.)
-        shard = (rank, world) if world > 1 else None
-        layout = lb.FastWindingNumber.shard_layout(dims, rank, world)
+        # tile layers (8 z-planes) dealt round-robin: every rank sees every height, ONE call per rank, results compact in the rank's
+        # buffer. Measured on one GPU rank by rank (tools/shard_balance.py): the 8 shares differ by 2-3 %; what is lost against
+        # 1/8 of the full lattice is per-call (smaller launches: tails and the planning levels). Contiguous z-slabs: 0.81 at 8 ranks.
+        # The diagonal (layer x y-part) sharding of wn_query_grid_sharded measured the same within 1 % and is not used here.
+        layers = (rank, world) if world > 1 else None
+        nx_, ny_, nz_ = int(dims[0]), int(dims[1]), int(dims[2])
+        unit_list = [(8 * l, min(nz_, 8 * l + 8), 0, ny_) for l in range(rank, (nz_ + 7) // 8, world)]
+        layout = {"units": unit_list, "n_points": sum((z1 - z0) * (y1 - y0) * nx_ for z0, z1, y0, y1 in unit_list)}
         n_local = layout["n_points"]
         h2d_bytes = 60
     else:
@@ -356,7 +360,7 @@ def main():
         if exact:
             eng.exact_solid_angle(pts_dev, out=out_dev)
         elif grid:
-            eng.query_grid(origin, spacing, dims, want_inside=True, out_inside=out_dev, shard=shard)
+            eng.query_grid(origin, spacing, dims, want_inside=True, out_inside=out_dev, layers=layers)
         else:
             eng.is_inside(pts_dev, out=out_dev)
 
@@ -409,7 +413,7 @@ def main():
         if exact:
             eng.exact_solid_angle(pts_np, out=out_host)
         elif grid:
-            eng.query_grid(origin, spacing, dims, want_inside=True, out_inside=out_host, shard=shard, bits=True)
+            eng.query_grid(origin, spacing, dims, want_inside=True, out_inside=out_host, layers=layers, bits=True)
         else:
             eng.is_inside(pts_np, out=out_host, bits=True)
 
@@ -537,14 +541,22 @@ def main():
     if not args.no_cpu_baseline:
         cpu = cpu_baseline(wl, args.mode, args.cpu_seconds if world == 1 else min(args.cpu_seconds, 6.0))
 
-    # launches of OUR kernels per step and rank: tiled = (k_tile_plan + k_tile_query) per batch of <= 131072 tiles (the probe that
-    # picks the path runs once, in the cold call, and is remembered per lattice); generic = one k_query; point sets add the Morton
-    # sort of the queries (2 + 4 passes x 5 launches); exact = k_exact + k_exact_reduce
+    # launches of OUR kernels per timed (device-output) step on this rank. Tiled lattice: per batch of <= 131072 tiles two k_plan_block
+    # levels + k_tile_plan + k_tile_query (the probe that picks the path runs once, in the cold call, and is remembered per lattice);
+    # tiled point set: k_tile_plan + k_tile_query per batch; generic = one k_query; point sets add the Morton sort of the queries
+    # (2 + 4 passes x 5 launches); exact = k_exact + k_exact_reduce. profiles/r2_launches_tiled.csv is the ncu list of the same command.
     tiles = -(-n_local // 512)
     if exact:
         launches = 2
+    elif extra.get("path", "").startswith("tiled") and grid:
+        per_layer = -(-int(dims[0]) // 8) * -(-int(dims[1]) // 8)
+        layers_local = len(layout["units"])
+        per_launch = max(1, 131072 // per_layer)
+        if world == 1 and per_launch >= 4:
+            per_launch -= per_launch % 4  # whole 4x4x4 planning blocks per batch
+        launches = 4 * max(1, -(-layers_local // per_launch))
     elif extra.get("path", "").startswith("tiled"):
-        launches = 2 * max(1, -(-tiles // 131072)) + (0 if grid else 22)
+        launches = 2 * max(1, -(-tiles // 131072)) + 22
     else:
         launches = 1 + (0 if grid else 22)
     api = ("FastWindingNumber.exact_solid_angle(host points) -> wn_exact: pinned HOST points in, float32 solid angles out" if exact else
