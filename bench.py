@@ -541,7 +541,7 @@ def main():
     if not args.no_cpu_baseline:
         cpu = cpu_baseline(wl, args.mode, args.cpu_seconds if world == 1 else min(args.cpu_seconds, 6.0))
 
-    # launches of OUR kernels per timed (device-output) step on this rank. Tiled lattice: per batch of <= 131072 tiles two k_plan_block
+    # launches of OUR kernels per timed (device-output) step on this rank. Tiled lattice: per batch of <= 262144 tiles two k_plan_block
     # levels + k_tile_plan + k_tile_query (the probe that picks the path runs once, in the cold call, and is remembered per lattice);
     # tiled point set: k_tile_plan + k_tile_query per batch; generic = one k_query; point sets add the Morton sort of the queries
     # (2 + 4 passes x 5 launches); exact = k_exact + k_exact_reduce. profiles/r2_launches_tiled.csv is the ncu list of the same command.
@@ -551,12 +551,12 @@ def main():
     elif extra.get("path", "").startswith("tiled") and grid:
         per_layer = -(-int(dims[0]) // 8) * -(-int(dims[1]) // 8)
         layers_local = len(layout["units"])
-        per_launch = max(1, 131072 // per_layer)
+        per_launch = max(1, 262144 // per_layer)
         if world == 1 and per_launch >= 4:
             per_launch -= per_launch % 4  # whole 4x4x4 planning blocks per batch
         launches = 4 * max(1, -(-layers_local // per_launch))
     elif extra.get("path", "").startswith("tiled"):
-        launches = 2 * max(1, -(-tiles // 131072)) + 22
+        launches = 2 * max(1, -(-tiles // 262144)) + 22
     else:
         launches = 1 + (0 if grid else 22)
     api = ("FastWindingNumber.exact_solid_angle(host points) -> wn_exact: pinned HOST points in, float32 solid angles out" if exact else

@@ -1025,7 +1025,7 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
             units = (n + wn::kTileQueries - 1) / wn::kTileQueries;
             tiles_per_unit = 1;
         }
-        const int64_t default_tiles = 1 << 17;
+        const int64_t default_tiles = 1 << 18; // 3.2 GB of packet arena at 12 KB per tile; measured on cfg2: 2^17 -> 2^18 tiles per batch +0.7 %
         const int64_t max_tiles = std::max<int64_t>(1, env_int("WN_TILE_BATCH", (int)default_tiles));
         int64_t units_per_launch = std::max<int64_t>(1, max_tiles / tiles_per_unit);
         // hierarchical planning (lattices): blocks of 2^k x 2^k x (2^k | 1) tiles above the tiles; a batch must hold whole blocks
@@ -1063,7 +1063,7 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
             int64_t tail = 0;
             // (small batches, e.g. one rank's share of a lattice on 8 GPUs: a second batch boundary costs more than the ~2 MB copy)
             if (GRID && host_out && units >= 4 && units * tiles_per_unit > env_int("WN_TILE_SPLIT_MIN", 1 << 16)) {
-                tail = std::max<int64_t>(1, units / 8);
+                tail = std::max<int64_t>(1, units / std::max(2, env_int("WN_TILE_TAIL_DIV", 8)));
                 if (plan_levels > 0 && zgroup) {
                     // planning blocks span 2^levels tile layers: the last batch has to start on a block boundary
                     const int64_t g = (int64_t)1 << plan_levels, start = (units - tail) / g * g;
