@@ -1076,6 +1076,24 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
         const bool overlap = GRID && ob && (ob->h_omega || ob->h_inside) && batch_units.size() > 1;
         if (overlap && !e->copy_stream) WN_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
         // Diagnostics: WN_TRACE_FILE=<path> records {start, end, SM} of every CTA of the tiled kernels of this call (tools/cta_timeline.py)
+        // (error paths: whatever returns early below still joins the second lane into `st` and frees the trace buffer)
+        struct Cleanup
+        {
+            const wn_engine* e;
+            cudaStream_t st;
+            bool forked = false;
+            void* trace = nullptr;
+            void join()
+            {
+                if (forked && cudaEventRecord(e->ev_join, e->lane_stream) == cudaSuccess) cudaStreamWaitEvent(st, e->ev_join, 0);
+                forked = false;
+            }
+            ~Cleanup()
+            {
+                join();
+                if (trace) cudaFree(trace);
+            }
+        } cleanup{e, st};
         const char* trace_path = getenv("WN_TRACE_FILE");
         struct TraceLaunch { int tag, lane; int64_t offset, count; };
         std::vector<TraceLaunch> trace_launches;
@@ -1084,6 +1102,7 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
         const int64_t trace_cap = trace_path && *trace_path ? 3 * total_tiles + 65536 : 0;
         if (trace_cap > 0) {
             WN_CUDA(cudaMalloc(&d_trace, (size_t)trace_cap * 32));
+            cleanup.trace = d_trace;
             WN_CUDA(cudaMemsetAsync(d_trace, 0, (size_t)trace_cap * 32, st));
         }
         auto trace_slot = [&](int tag, int lane, int64_t count) -> unsigned long long* {
@@ -1101,6 +1120,7 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
             WN_CUDA(cudaEventRecord(e->ev_fork, st)); // the inputs (uploaded or sorted points, counters) are ready on `st`
             WN_CUDA(cudaStreamWaitEvent(e->lane_stream, e->ev_fork, 0));
             lane_st[1] = e->lane_stream;
+            cleanup.forked = true;
         }
         int64_t u0 = 0;
         for (size_t bi = 0; bi < batch_units.size(); u0 += batch_units[bi], ++bi) {
@@ -1215,18 +1235,13 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
                     WN_CUDA(cudaMemcpyAsync(ob->h_inside + first, ob->d_inside + first, (size_t)count, cudaMemcpyDeviceToHost, e->copy_stream));
             }
         }
-        if (forked) {
-            // join: everything after this call on `st` (bit packing, copies, the next call) sees both lanes' results
-            WN_CUDA(cudaEventRecord(e->ev_join, e->lane_stream));
-            WN_CUDA(cudaStreamWaitEvent(st, e->ev_join, 0));
-        }
+        cleanup.join(); // everything after this call on `st` (bit packing, copies, the next call) sees both lanes' results
         if (d_trace) {
             // file: "WNTR", launches, then per launch {tag (1 tile plan, 2 tile query, 10+k block plan of level k), lane, count, count x 4 u64}
             a.trace = nullptr;
             std::vector<unsigned long long> h((size_t)trace_used * 4);
             WN_CUDA(cudaStreamSynchronize(st));
             WN_CUDA(cudaMemcpy(h.data(), d_trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-            cudaFree(d_trace);
             if (FILE* f = fopen(trace_path, "wb")) {
                 const int32_t nl = (int32_t)trace_launches.size();
                 fwrite("WNTR", 1, 4, f);

@@ -29,6 +29,16 @@ for kw in ({"hierarchy": "reference"}, {"hierarchy": "lbvh"}, {"hierarchy": "lbv
     sq, tri, xyz = eng.closest_point(q)
     strided = eng.query_grid(o, s, d, layers=(1, 2))[1]
     strided_bits = eng.query_grid(o, s, d, layers=(0, 3), bits=True)[1]
+    o2, s2, d2 = prim.lattice_for_bbox(*prim.mesh_bbox(V), (24, 64, 40))  # ny % 32 == 0: the diagonal sharding splits rows in 4 / 2 parts
+    for rank, world in ((0, 4), (3, 4), (1, 2), (2, 8)):
+        eng.query_grid(o2, s2, d2, shard=(rank, world), bits=(rank == 3))
+    if kw["hierarchy"] == "reference":
+        # the CTA timeline hooks of the tiled kernels (diagnostics)
+        import tempfile
+
+        os.environ["WN_TRACE_FILE"] = os.path.join(tempfile.mkdtemp(), "trace.bin")
+        eng.query_grid(o, s, d)
+        del os.environ["WN_TRACE_FILE"]
     rep = lb.FastWindingNumber.from_packed(eng.pack())
     assert np.array_equal(rep.solid_angle(q[:100], tiling=False), e[:100])
     print(kw, "grid tiled-vs-generic", float(np.abs(a - b).max()), "points", float(np.abs(c - e).max()), "exact", float(np.abs(x - e[:300]).max()),
