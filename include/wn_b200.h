@@ -178,11 +178,11 @@ WN_API wn_status wn_query_grid_strided(const wn_engine* e, const float origin[3]
                                        int64_t layer_first, int64_t layer_step, float beta, uint32_t flags, float* out_omega,
                                        uint8_t* out_inside, void* stream);
 
-/* Diagonal sharding of a lattice across `world` GPUs (what bench.py uses): the lattice is cut in Q parts along y (Q = 4, 2 or 1: the
+/* Diagonal sharding of a lattice across `world` GPUs: the lattice is cut in Q parts along y (Q = 4, 2 or 1: the
  * largest that divides both `world` and the tile rows, ny % (8 Q) == 0) and rank r evaluates, of every c-th tile layer (c = world / Q,
  * starting at layer r mod c), the one part ((r - layer) / c) mod Q. Every rank sees every part and every height equally often and the
- * unit of balance is a Q-th of a layer (whole layers dealt to 8 ranks cap the efficiency at 0.906 on a 64-layer lattice whose end
- * layers are empty). Output: the rank's units in layer order, each planes x part_rows x nx values (planes = 8, fewer for the last
+ * unit of balance is a Q-th of a layer: for lattices with few tile layers per rank. (bench.py deals whole layers,
+ * wn_query_grid_strided: on the 64-layer cfg2 lattice both measured the same within 1 %.) Output: the rank's units in layer order, each planes x part_rows x nx values (planes = 8, fewer for the last
  * layer); wn_grid_shard_layout describes it. Q == 1 is exactly wn_query_grid_strided(rank, world). Honours WN_QUERY_OUT_BITS. */
 WN_API wn_status wn_query_grid_sharded(const wn_engine* e, const float origin[3], const float spacing[3], const int64_t dims[3], int32_t rank,
                                        int32_t world, float beta, uint32_t flags, float* out_omega, uint8_t* out_inside, void* stream);

@@ -1425,9 +1425,10 @@ wn_status check_grid(const float* origin, const float* spacing, const int64_t* d
 // layer_first + layer_step, ... of the whole lattice, results stored compactly in that order (z0/z1 ignored).
 // Diagonal sharding of a lattice over `world` ranks (wn_query_grid_sharded): the lattice is cut in Q parts along y and rank r takes,
 // of every c-th tile layer (c = world / Q, starting at r mod c), the ONE part ((r - layer) / c) mod Q. Every rank sees every part and
-// every height equally often, and the unit of balance is a Q-th of a layer: dealing whole layers to 8 ranks leaves 64 layers of which
-// 58 carry work as 8 + 7 + ... (efficiency bound 0.906 on cfg2, measured 0.908). Q = 4 or 2 when world and the tile rows allow it,
-// else 1 (whole layers, the same as wn_query_grid_strided).
+// every height equally often, and the unit of balance is a Q-th of a layer (useful when a lattice has fewer tile layers than there are
+// ranks; on cfg2, 64 layers over 8 ranks, it measured the same as whole layers within 1 %: the ranks' shares are already balanced to
+// 2-3 %). Q = 4 or 2 when world and the tile rows allow it, else 1 (whole layers, the same as
+// wn_query_grid_strided).
 struct ShardLayout
 {
     int Q = 1, c = 1;
