@@ -249,9 +249,11 @@ def run_reference(args):
 
 def profile_traffic():
     """DRAM bytes (read + write) per launch of the dominant kernel, k_tile_query, from the newest committed `ncu --set full` summary
-    under profiles/ (STATIC: captured on the commit named in the file, not in this run; one launch = 131072 tiles = 67.1 M queries
-    of cfg2). The tree is part of it: every launch streams the records it touches from HBM once; the algorithmic output is 1 byte per query."""
-    for fn in ("r2_tile_plan_query_ncu_full.txt", "r1q_tile_plan_query_ncu_full.txt"):
+    under profiles/ (STATIC: captured with tools/final_capture.sh on the final code of the round, not in this run; one launch = the
+    whole cfg2 lattice, 262144 tiles = 134.2 M queries). The tree is part of it: every launch streams the records it touches from HBM
+    once; the algorithmic output is 1 byte per query."""
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for fn, tiles in (("r2_tile_plan_query_ncu_full.txt", 262144), ("r1q_tile_plan_query_ncu_full.txt", 131072)):
         path = os.path.join(ROOT, "profiles", fn)
         try:
             rd = wr = None
@@ -259,12 +261,15 @@ def profile_traffic():
             for ln in open(path):
                 if ln.startswith("## "):
                     in_query = "k_tile_query" in ln
-                elif in_query and ln.startswith("dram__bytes_read.sum "):
-                    rd = float(ln.split()[-1]) * 1e6
-                elif in_query and ln.startswith("dram__bytes_write.sum "):
-                    wr = float(ln.split()[-1]) * 1e6
+                elif in_query and (ln.startswith("dram__bytes_read.sum ") or ln.startswith("dram__bytes_write.sum ")):
+                    f = ln.split()
+                    v = float(f[-1]) * scale[f[-2]]
+                    if ln.startswith("dram__bytes_read"):
+                        rd = v
+                    else:
+                        wr = v
             if rd is not None and wr is not None:
-                return {"bytes_per_launch": rd + wr, "queries_per_launch": 131072 * 512, "source": f"profiles/{fn} (k_tile_query)",
+                return {"bytes_per_launch": rd + wr, "queries_per_launch": tiles * 512, "source": f"profiles/{fn} (k_tile_query)",
                         "static": True}
         except Exception:
             continue

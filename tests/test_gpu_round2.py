@@ -348,3 +348,49 @@ def test_diagonal_sharding_reassembles_the_lattice(lb, prim, monkeypatch, dims, 
     in_t = gather_sharded(d, world, parts_bits).reshape(-1)
     clear = np.abs(om_ref / (4 * np.pi) - 0.5) > 1e-4
     assert np.array_equal(in_t[clear], in_ref[clear])
+
+
+def test_cta_timeline_trace_and_launch_shapes(lb, prim, monkeypatch, tmp_path):
+    """WN_TRACE_FILE (diagnostics): every CTA of the tiled kernels records {start, end, SM}; the dump lists, per batch, the two block
+    levels, the tile plan (one CTA per tile) and the tile query, whose grid is runs of tiles plus single-tile CTAs at the light end
+    (WN_TILE_RUN / WN_TILE_TAIL). Results do not depend on the run length, the tail or the two-lane dispatch."""
+    import importlib.util
+    import os
+
+    spec = importlib.util.spec_from_file_location("cta_timeline", os.path.join(os.path.dirname(__file__), "..", "tools", "cta_timeline.py"))
+    tl = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tl)
+    monkeypatch.setenv("WN_TILE", "1")
+    V, F = prim.generate_torus(5.0, 1.0, 64, 32)
+    eng = lb.FastWindingNumber(V, F)
+    lo, hi = prim.mesh_bbox(V)
+    d = np.array((96, 80, 72), dtype=np.int64)  # 12 x 10 x 9 = 1080 tiles
+    o = (lo - 0.3).astype(np.float32)
+    s = ((hi - lo + 0.6) / d).astype(np.float32)
+    ref = eng.query_grid(o, s, d, want_omega=True)[0]
+    for run, tail, lanes in (("3", "0", "1"), ("4", "1", "1"), ("1", "2", "1"), ("2", "2", "2")):
+        monkeypatch.setenv("WN_TILE_RUN", run)
+        monkeypatch.setenv("WN_TILE_TAIL", tail)
+        monkeypatch.setenv("WN_TILE_LANES", lanes)
+        monkeypatch.setenv("WN_TILE_LANES_MIN", "1")
+        path = tmp_path / f"trace_{run}_{tail}_{lanes}.bin"
+        monkeypatch.setenv("WN_TRACE_FILE", str(path))
+        om = eng.query_grid(o, s, d, want_omega=True)[0]
+        monkeypatch.delenv("WN_TRACE_FILE")
+        assert np.array_equal(om, ref), (run, tail, lanes)
+        launches = tl.read_trace(str(path))
+        tags = [t for t, _, _ in launches]
+        assert tags.count(1) == tags.count(2) >= 1 and tags.count(11) == tags.count(12) == tags.count(1)
+        assert sum(len(dd) for t, _, dd in launches if t == 1) == 1080  # one plan CTA per tile
+        assert {ln for _, ln, _ in launches} == ({0, 1} if lanes == "2" else {0})
+        for t, _, dd in launches:
+            assert np.all(dd[:, 1] >= dd[:, 0]) and np.all(dd[:, 0] > 0), t  # every CTA wrote its start and end
+        if lanes == "1":
+            q = [dd for t, _, dd in launches if t == 2][0]
+            r = int(run)
+            slots = tl.summarise(launches)["launches"][-1]["sms"]  # >= 1 SM seen; the tail is sized from the device's resident CTAs
+            assert slots >= 1
+            if tail == "0" or r == 1:
+                assert len(q) == -(-1080 // r)
+            else:
+                assert -(-1080 // r) < len(q) <= 1080  # some tiles went one per CTA
