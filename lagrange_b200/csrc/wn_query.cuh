@@ -59,11 +59,22 @@ constexpr int kPlanWarps = kPlanThreads / 32;
 #ifndef WN_TILE_CAP_SCALE
 #define WN_TILE_CAP_SCALE 1
 #endif
-constexpr int kTileAllCap = 2048 * WN_TILE_CAP_SCALE;   // classified records per tile (conditional + direct + exact)
-constexpr int kTileFrontCap = 1024 * WN_TILE_CAP_SCALE; // breadth-first frontier
+// k_tile_plan is latency-bound (barrier per breadth-first round), so resident CTAs count: list capacities of 3/4 of round 1's
+// (1536 / 768 / 768: 21 KB of shared memory) and 56 registers put 9 CTAs on an SM instead of 8. Measured on cfg2 (G q/s), capacity
+// quarters x CTAs/SM: 4 x 8 (64 regs) 7.92; 3 x 9 (56 regs) 8.03; 3 x 10 (48 regs, 44 B spilled) 7.97; 2 x 12 (40 regs, 100 B
+// spilled) 7.99; uncapped registers (112, 4 CTAs) 7.27. cfg3 +1 %, forced-tiled cfg5 +4 %, overflow fallbacks unchanged.
+#ifndef WN_TILE_CAP_Q
+#define WN_TILE_CAP_Q 3
+#endif
+#ifndef WN_PLAN_MIN_CTAS
+#define WN_PLAN_MIN_CTAS 9
+#endif
+#define WN_PLAN_BOUNDS __launch_bounds__(kPlanThreads, WN_PLAN_MIN_CTAS)
+constexpr int kTileAllCap = 512 * WN_TILE_CAP_Q * WN_TILE_CAP_SCALE;   // classified records per tile (conditional + direct + exact)
+constexpr int kTileFrontCap = 256 * WN_TILE_CAP_Q * WN_TILE_CAP_SCALE; // breadth-first frontier
 constexpr int kTileFarCap = 512;                  // far set
 constexpr int kTileDirCap = 512;                  // direct records
-constexpr int kTileExactCap = 1024 * WN_TILE_CAP_SCALE; // exact leaves (also bounded by the frontier buffer reused for offsets)
+constexpr int kTileExactCap = 256 * WN_TILE_CAP_Q * WN_TILE_CAP_SCALE; // exact leaves (also bounded by the frontier buffer reused for offsets)
 constexpr int kPlanMaxRounds = 96;                // breadth-first rounds = hierarchy depth bound (deeper: generic path)
 constexpr int kTileSamples = 64;                  // 4^3 Chebyshev points
 constexpr int kTileSampleStride = 72;             // 64 samples + centre(3) + 1/half-extent(3) + radius + pad
@@ -879,7 +890,7 @@ __global__ void __launch_bounds__(kPlanThreads) k_plan_block(const QueryArgs a)
 }
 
 template <bool GRID>
-__global__ void __launch_bounds__(kPlanThreads) k_tile_plan(const QueryArgs a)
+__global__ void WN_PLAN_BOUNDS k_tile_plan(const QueryArgs a)
 {
     __shared__ int s_front[2][kTileFrontCap];
     __shared__ int s_cond[kTileAllCap];
