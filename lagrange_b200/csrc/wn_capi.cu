@@ -957,7 +957,7 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
     if (tile_mode == 2) {
         // Probe: classify ~1000 tiles spread over the batch (breadth-first part of k_tile_plan only) and estimate the share of
         // far-field evaluations the tiled path would take off every query: far / (far + direct + ~half the conditional ones).
-        // Tiling pays off when that share is large (measured: cfg2 0.6 -> 1.33x faster; shares below ~0.4 -> slower).
+        // Tiling pays off when that share is large (measured: cfg2 0.75 -> 1.9x faster; cfg5 0.13 -> +10 %; cfg1 0.03 -> slower).
         const int64_t total_tiles = GRID ? (int64_t)a.tiles_x * a.tiles_y * ((grid_layers + 7) / 8) : (n + wn::kTileQueries - 1) / wn::kTileQueries;
         const int stride = (int)std::max<int64_t>(1, total_tiles / 1024);
         const int blocks = (int)((total_tiles + stride - 1) / stride);
@@ -977,9 +977,9 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
         const double far = (double)h[0], cond = (double)h[1], dir = (double)h[2];
         const double share = far / (far + dir + 0.5 * cond + 1e-9);
         const char* thr = getenv("WN_TILE_MIN_SHARE");
-        // threshold re-measured in round 2 (hierarchical planning made the plan cheaper): cfg3 share 0.39 -> tiled +11 %,
-        // cfg5 0.13 -> +3 % (not worth it), cfg1 0.03 -> -7 %
-        tiled = share >= (thr && *thr ? atof(thr) : 0.30) && (double)h[4] < 0.5 * blocks;
+        // threshold re-measured at the end of round 2 (hierarchical planning, 9 plan CTAs per SM: planning got cheaper): cfg3 share
+        // 0.39 -> tiled +18 %, cfg5 0.13 -> +10 %, cfg1 0.03 -> -7 %; cfg4: every sampled tile overflows -> generic
+        tiled = share >= (thr && *thr ? atof(thr) : 0.10) && (double)h[4] < 0.5 * blocks;
         e->last_probe_share = (float)share;
         if (GRID) {
             memcpy(e->probe_key, key, sizeof(key));
