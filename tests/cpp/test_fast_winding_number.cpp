@@ -347,16 +347,23 @@ int main()
             lat.dims = {96, 40, 96};
             const size_t n = 96 * 40 * 96;
             std::vector<uint8_t> one(n), two(n), bits((n + 7) / 8);
+            std::vector<float> omega(n);
             engine.is_inside(lat, one.data());
+            engine.solid_angle(lat, omega.data());
             multi->is_inside(lat, two.data());
             multi->is_inside_bits(lat, bits.data());
-            size_t diff = 0, bitdiff = 0;
+            // if the tiled path is picked, a rank's planning blocks differ from the whole lattice's: answers may differ by the far-field
+            // interpolation (<= 3e-5 * 4 pi), i.e. only inside the strict band |w - 1/2| <= 1e-3; the bits are the bytes of the same path
+            size_t diff = 0, diff_outside_band = 0, bitdiff = 0;
             for (size_t i = 0; i < n; ++i) {
-                diff += one[i] != two[i];
-                bitdiff += ((bits[i >> 3] >> (i & 7)) & 1) != one[i];
+                const bool differs = one[i] != two[i];
+                diff += differs;
+                diff_outside_band += differs && std::fabs(omega[i] / (4.f * 3.14159265358979f) - 0.5f) > 1e-3f;
+                bitdiff += ((bits[i >> 3] >> (i & 7)) & 1) != two[i];
             }
-            std::printf("two GPUs, one process: %zu lattice points, %zu differ from the single-GPU answer\n", n, diff);
-            CHECK(diff == 0 && bitdiff == 0);
+            std::printf("two GPUs, one process: %zu lattice points, %zu differ from the single-GPU answer (%zu outside the strict band)\n", n, diff,
+                        diff_outside_band);
+            CHECK(diff_outside_band == 0 && bitdiff == 0);
         }
     }
 
