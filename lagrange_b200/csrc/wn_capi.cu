@@ -1071,7 +1071,8 @@ wn_status dispatch_query(const wn_engine* e, wn::QueryArgs& a, int64_t n, int64_
                 }
             }
             for (int64_t left = units - tail; left > 0; left -= std::min(left, units_per_launch)) batch_units.push_back(std::min(left, units_per_launch));
-            if (tail > 0) batch_units.push_back(tail);
+            // (very wide layers: the short last batch may exceed what the scratch holds -- split it like the rest)
+            for (int64_t left = tail; left > 0; left -= std::min(left, units_per_launch)) batch_units.push_back(std::min(left, units_per_launch));
         }
         const bool overlap = GRID && ob && (ob->h_omega || ob->h_inside) && batch_units.size() > 1;
         if (overlap && !e->copy_stream) WN_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
